@@ -1,0 +1,35 @@
+"""Loaders for tests/golden/*.npz (written by oracle/gen_golden.py from the unmodified reference)."""
+import os
+
+import numpy as np
+
+GOLDEN_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+VERSIONS = ["barrage", "standard", "short_standard", "short_barrage", "medium_standard", "octa_barrage",
+            "standard2", "medium", "fives", "tiny", "micro"]
+
+_cache = {}
+
+
+def load(name):
+    if name not in _cache:
+        with np.load(os.path.join(GOLDEN_DIR, name + ".npz")) as d:
+            _cache[name] = {k: d[k] for k in d.files}
+    return _cache[name]
+
+
+def traj(version):
+    return load("traj_" + version)
+
+
+def known():
+    return load("known_answers")
+
+
+def unpack_mask(bits, n):
+    return np.unpackbits(bits, axis=-1)[..., :n]
+
+
+def transitions(t):
+    """indices i with a recorded move states[i] -(actions[i])-> states[i+1]"""
+    return np.flatnonzero(t["actions_spatial"] >= 0)
