@@ -1,0 +1,675 @@
+// sx_device.cuh -- device-side game logic of the B200 Stratego engine (one warp per game).
+//
+// Everything here is warp-synchronous: the 32 lanes of a warp cooperate on ONE game whose compact
+// state is staged in that warp's slice of shared memory.  Scalar rule logic (action decode, combat)
+// is computed redundantly by all lanes (warp-uniform control flow, one issue slot per op); board
+// scans are spread over lanes, K = ceil(cells / 32) consecutive cells per lane.
+//
+// Reference being restated: stratego_env/game/stratego_procedural_impl.py ("impl") and
+// stratego_env/stratego_multiagent_env.py ("maenv") of JBLanier/stratego_env.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace sx {
+
+// ---- piece codes (impl:145-163) -----------------------------------------------------------------
+constexpr int SP_SPY = 1, SP_SCOUT = 2, SP_MINER = 3, SP_MARSHAL = 10, SP_FLAG = 11, SP_BOMB = 12, SP_UNKNOWN = 13;
+
+// ---- packed board cell: one byte per square ------------------------------------------------------
+// Sufficient because on every reachable state the partially observable rank is either UNKNOWN or the
+// true rank (impl:955-995), so the reference's six per-cell layers (true rank x2, PO rank x2, still
+// x2) plus the obstacle layer collapse to rank/owner/revealed/still/obstacle.
+constexpr uint32_t CELL_RANK = 0x0F, CELL_OWNER = 0x10, CELL_REVEALED = 0x20, CELL_STILL = 0x40, CELL_OBST = 0x80;
+
+constexpr int NO_CELL = 255;
+constexpr uint32_t FULL = 0xffffffffu;
+
+// ---- per-variant constants, passed by value as a kernel parameter ---------------------------------
+struct DevConfig {
+    int R, C, N, A, mpa, action_size;
+    int board_stride, cap_stride;  // bytes / uint16 entries per env
+    int max_turns, usable_rows, setup_len, n_pieces, p2_rot180;
+    int po_floats, fo_floats, mask_bytes;
+    float cap_lut[12 * 9];
+    float recent_lut[5];
+    float unit_lut[2];
+    uint8_t obstacles[256];
+    uint8_t piece_seq[128];  // pieces in placement order (piece code ascending, util:24-28)
+};
+
+// ---- scalar part of a game's state (aux tensor, 8 x int16) ----------------------------------------
+struct Aux {
+    int turn, max_turns;
+    int over, invalid, winner;  // winner in {-1, 0, +1}
+    int to_move;                // 0 = player +1, 1 = player -1
+    int rfrom[2], rto[2], rcode[2];  // recent-move squares per player (NO_CELL = none); rcode = -code of `to` (1..3)
+    int ncap;
+    uint32_t episode;
+};
+
+__device__ __forceinline__ void aux_unpack(const uint32_t w[4], Aux &a)
+{
+    a.turn = w[0] & 0xffff;
+    a.max_turns = w[0] >> 16;
+    const uint32_t flags = w[1] & 0xff;
+    a.over = flags & 1;
+    a.invalid = (flags >> 1) & 1;
+    a.winner = int((flags >> 2) & 3) - 1;
+    a.to_move = (flags >> 4) & 1;
+    a.ncap = (w[1] >> 8) & 0xff;
+    a.rfrom[0] = (w[1] >> 16) & 0xff;
+    a.rto[0] = (w[1] >> 24) & 0xff;
+    a.rfrom[1] = w[2] & 0xff;
+    a.rto[1] = (w[2] >> 8) & 0xff;
+    a.rcode[0] = (w[2] >> 16) & 0xff;
+    a.rcode[1] = (w[2] >> 24) & 0xff;
+    a.episode = w[3];
+}
+
+__device__ __forceinline__ void aux_pack(const Aux &a, uint32_t w[4])
+{
+    w[0] = uint32_t(a.turn & 0xffff) | (uint32_t(a.max_turns & 0xffff) << 16);
+    const uint32_t flags = uint32_t(a.over) | (uint32_t(a.invalid) << 1) | (uint32_t(a.winner + 1) << 2) |
+                           (uint32_t(a.to_move) << 4);
+    w[1] = flags | (uint32_t(a.ncap) << 8) | (uint32_t(a.rfrom[0]) << 16) | (uint32_t(a.rto[0]) << 24);
+    w[2] = uint32_t(a.rfrom[1]) | (uint32_t(a.rto[1]) << 8) | (uint32_t(a.rcode[0]) << 16) |
+           (uint32_t(a.rcode[1]) << 24);
+    w[3] = a.episode;
+}
+
+// capture entry: cell | owner<<8 | (type-1)<<9 | (count-1)<<13
+__device__ __forceinline__ uint32_t cap_key(int cell, int owner, int type) { return uint32_t(cell) | (uint32_t(owner) << 8) | (uint32_t(type - 1) << 9); }
+
+// ---- Philox4x32-10 (counter-based; results depend only on key/counter, not on placement) -----------
+__device__ __forceinline__ uint4 philox4x32_10(uint4 c, uint2 k)
+{
+#pragma unroll
+    for (int i = 0; i < 10; ++i) {
+        const uint32_t hi0 = __umulhi(0xD2511F53u, c.x), lo0 = 0xD2511F53u * c.x;
+        const uint32_t hi1 = __umulhi(0xCD9E8D57u, c.z), lo1 = 0xCD9E8D57u * c.z;
+        c = make_uint4(hi1 ^ c.y ^ k.x, lo1, hi0 ^ c.w ^ k.y, lo0);
+        k.x += 0x9E3779B9u;
+        k.y += 0xBB67AE85u;
+    }
+    return c;
+}
+
+enum : uint32_t { RNG_RESET = 0x52535430u, RNG_SAMPLE = 0x53414d50u, RNG_SHUFFLE = 0x53484600u };
+
+// ---- this warp's slice of shared memory -----------------------------------------------------------
+struct WarpMem {
+    float *po;         // [N*67] partial-observation tile (background + patches)
+    float *fo;         // [N*79] full-observation tile
+    uint8_t *mask;     // [mask_bytes + 16] spatial mask tile; the live tile starts at mask + moff
+    uint8_t *board;    // [board_stride]
+    uint16_t *cap;     // [cap_stride]
+    uint32_t *lines;   // [64] occupancy bit-lines: any[0..15 rows | 16..31 cols], enemy[32 + same]
+    uint16_t *reach;   // [N] per-cell packed reach (4 x 4 bit), consumed by the action sampler
+    uint8_t *scratch;  // [>= 2 * setup_len] shuffle workspace
+};
+
+__device__ __forceinline__ int lane_id() { return threadIdx.x & 31; }
+
+// flat cell index in `me`'s frame <-> absolute frame: a 180-degree rotation is index reversal
+__device__ __forceinline__ int view(int cell, int flip, int N) { return flip ? N - 1 - cell : cell; }
+
+// ---- TMA bulk copy shared -> global (SASS: UBLKCP), tracked by the issuing thread's bulk group -----
+__device__ __forceinline__ void bulk_store(void *gdst, const void *ssrc, uint32_t bytes)
+{
+    const uint32_t saddr = static_cast<uint32_t>(__cvta_generic_to_shared(ssrc));
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst), "r"(saddr), "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+// Emits `bytes` from shared memory to global memory.  When src and dst are congruent mod 16 the
+// 16-byte aligned body goes out as one TMA bulk copy issued by lane 0 (caller commits/waits) and the
+// <16-byte head and tail as plain word stores; otherwise (odd-sized variants such as 5x5 and 15x15,
+// whose per-env byte counts are not multiples of 16) the tile is copied with plain stores.
+__device__ __forceinline__ void emit_tile(uint8_t *gdst, const uint8_t *ssrc, int bytes)
+{
+    const int lane = lane_id();
+    const uintptr_t g = reinterpret_cast<uintptr_t>(gdst);
+    const uint32_t s = static_cast<uint32_t>(__cvta_generic_to_shared(ssrc));
+    if (((g | s | uint32_t(bytes)) & 3) != 0) {
+        for (int i = lane; i < bytes; i += 32) gdst[i] = ssrc[i];
+        return;
+    }
+    if (((g ^ s) & 15) != 0) {
+        for (int i = lane; i < (bytes >> 2); i += 32)
+            reinterpret_cast<uint32_t *>(gdst)[i] = reinterpret_cast<const uint32_t *>(ssrc)[i];
+        return;
+    }
+    int head = int((16 - (g & 15)) & 15);
+    if (head > bytes) head = bytes;
+    const int body = (bytes - head) & ~15;
+    const int tail = bytes - head - body;
+    if (lane < (head >> 2)) reinterpret_cast<uint32_t *>(gdst)[lane] = reinterpret_cast<const uint32_t *>(ssrc)[lane];
+    if (lane >= 8 && lane - 8 < (tail >> 2)) {
+        const int off = head + body + ((lane - 8) << 2);
+        *reinterpret_cast<uint32_t *>(gdst + off) = *reinterpret_cast<const uint32_t *>(ssrc + off);
+    }
+    if (body > 0 && lane == 0) bulk_store(gdst + head, ssrc + head, uint32_t(body));
+}
+
+// ---- occupancy bit-lines in `me`'s frame ------------------------------------------------------------
+// lanes 0..15 build one row each (bit c), lanes 16..31 one column each (bit r); "any" marks pieces and
+// lakes, "enemy" marks the opponent's pieces.  Replaces the per-square ray walk of impl:426-490.
+__device__ __forceinline__ void build_lines(const DevConfig &cfg, const WarpMem &m, int me, int flip)
+{
+    const int lane = lane_id();
+    const bool is_row = lane < 16;
+    const int idx = is_row ? lane : lane - 16;
+    const int count = is_row ? cfg.C : cfg.R;
+    const int stride = is_row ? 1 : cfg.C;
+    const int base = is_row ? idx * cfg.C : idx;
+    const bool live = idx < (is_row ? cfg.R : cfg.C);
+    uint32_t any = 0, enemy = 0;
+    if (live) {
+        for (int j = 0; j < count; ++j) {
+            const uint32_t b = m.board[view(base + j * stride, flip, cfg.N)];
+            any |= uint32_t(b != 0) << j;
+            enemy |= uint32_t((b & CELL_RANK) != 0 && int((b >> 4) & 1) != me) << j;
+        }
+    }
+    m.lines[lane] = any;
+    m.lines[32 + lane] = enemy;
+    __syncwarp();
+}
+
+// distance a sliding piece can travel from bit `pos` towards higher / lower bits of a line; the last
+// square counts when it holds an enemy piece (impl:434-437, 454-456)
+__device__ __forceinline__ int ray_up(uint32_t any, uint32_t enemy, int pos, int len)
+{
+    const uint32_t x = any >> (pos + 1);
+    if (x == 0) return len - 1 - pos;
+    const int d = __ffs(x);
+    return (d - 1) + int((enemy >> (pos + d)) & 1);
+}
+__device__ __forceinline__ int ray_down(uint32_t any, uint32_t enemy, int pos)
+{
+    const uint32_t x = any & ((1u << pos) - 1u);
+    if (x == 0) return pos;
+    const int top = 31 - __clz(x);
+    return (pos - top - 1) + int((enemy >> top) & 1);
+}
+
+// The single move the two-square rule can forbid for the player to move (impl:439-445, 501-505):
+// from the square coded -3 back onto the square coded +1, if that square is empty.
+struct Blocked {
+    int cell, dir, dist;  // in `me`'s frame; cell < 0 = nothing blocked
+};
+
+__device__ __forceinline__ Blocked blocked_move(const DevConfig &cfg, const WarpMem &m, const Aux &a, int me, int flip,
+                                                bool allow_osc)
+{
+    Blocked b{-1, 0, 0};
+    if (allow_osc || a.rcode[me] != 3 || a.rto[me] == NO_CELL || a.rfrom[me] == NO_CELL) return b;
+    if ((m.board[a.rfrom[me]] & CELL_RANK) != 0) return b;  // an enemy stepped onto it: attacking is allowed
+    const int s = view(a.rto[me], flip, cfg.N), e = view(a.rfrom[me], flip, cfg.N);
+    const int sr = s / cfg.C, sc = s - sr * cfg.C, er = e / cfg.C, ec = e - er * cfg.C;
+    if (sr != er && sc != ec) return b;
+    if (s == e) return b;
+    b.cell = s;
+    if (sc == ec) { b.dir = er > sr ? 0 : 1; b.dist = er > sr ? er - sr : sr - er; }
+    else { b.dir = ec > sc ? 2 : 3; b.dist = ec > sc ? ec - sc : sc - ec; }
+    return b;
+}
+
+// ---- valid-move generation (impl:400-517 / impl:522-642) -------------------------------------------
+struct MarkNone {
+    __device__ __forceinline__ void operator()(int, int, int, int) const {}
+};
+// spatial mask tile in shared memory: [cell][channel], channel = dir base + dist - 1 (impl:292-311)
+struct MarkSpatialSmem {
+    uint8_t *tile;
+    int A, R, C;
+    __device__ __forceinline__ void operator()(int cell, int dir, int dist, int /*target*/) const
+    {
+        const int base = dir == 0 ? 0 : dir == 1 ? (R - 1) : dir == 2 ? 2 * (R - 1) : 2 * (R - 1) + (C - 1);
+        tile[cell * A + base + dist - 1] = 1;
+    }
+};
+// 1D mask straight to global memory, absolute frame (impl:264-277); facade use only
+struct Mark1DGlobal {
+    uint8_t *out;
+    int N, R, C, flip;
+    __device__ __forceinline__ void operator()(int cell, int dir, int /*dist*/, int target) const
+    {
+        const int s = flip ? N - 1 - cell : cell, e = flip ? N - 1 - target : target;
+        const int er = e / C, ec = e - er * C;
+        out[s * (R + C) + (dir < 2 ? er : R + ec)] = 1;
+    }
+};
+
+// Enumerates the moves of player index `me`, in `me`'s frame.  Returns (warp-uniform) whether any
+// move exists.  When `reach_out` is set, stores each cell's four ray lengths for the sampler.
+template <int K, typename Mark>
+__device__ __forceinline__ bool gen_moves(const DevConfig &cfg, const WarpMem &m, const Aux &a, int me, bool allow_osc,
+                                          const Mark &mark, bool reach_out)
+{
+    if (a.over) {  // impl:414
+        if (reach_out)
+            for (int k = 0; k < K; ++k) {
+                const int p = lane_id() * K + k;
+                if (p < cfg.N) m.reach[p] = 0;
+            }
+        return false;
+    }
+    const int flip = me;  // player -1 sees the board rotated
+    build_lines(cfg, m, me, flip);
+    const Blocked blk = blocked_move(cfg, m, a, me, flip, allow_osc);
+    const int lane = lane_id();
+    int found = 0;
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+        const int p = lane * K + k;
+        uint32_t packed = 0;
+        if (p < cfg.N) {
+            const uint32_t b = m.board[view(p, flip, cfg.N)];
+            const int rank = b & CELL_RANK;
+            if (rank != 0 && rank <= SP_MARSHAL && int((b >> 4) & 1) == me) {  // impl:420
+                const int r = p / cfg.C, c = p - r * cfg.C;
+                const uint32_t col_any = m.lines[16 + c], col_en = m.lines[48 + c];
+                const uint32_t row_any = m.lines[r], row_en = m.lines[32 + r];
+                int reach[4];
+                reach[0] = ray_up(col_any, col_en, r, cfg.R);
+                reach[1] = ray_down(col_any, col_en, r);
+                reach[2] = ray_up(row_any, row_en, c, cfg.C);
+                reach[3] = ray_down(row_any, row_en, c);
+                const int step[4] = {cfg.C, -cfg.C, 1, -1};
+#pragma unroll
+                for (int d = 0; d < 4; ++d) {
+                    if (rank != SP_SCOUT && reach[d] > 1) reach[d] = 1;  // impl:492-499
+                    packed |= uint32_t(reach[d]) << (4 * d);
+                    for (int t = 1; t <= reach[d]; ++t) {
+                        if (p == blk.cell && d == blk.dir && t == blk.dist) continue;
+                        mark(p, d, t, p + step[d] * t);
+                        found = 1;
+                    }
+                }
+            }
+            if (reach_out) m.reach[p] = uint16_t(packed);
+        }
+    }
+    return __any_sync(FULL, found);
+}
+
+// ---- action decode ----------------------------------------------------------------------------------
+struct Move {
+    int start, end;  // absolute cells
+    bool noop, bad;
+};
+
+// flat spatial index in the mover's frame: maenv:685 (unravel) + impl:316-335 + impl:700-720.
+// The spatial noop channel never decodes to a playable move in the reference (it maps to a
+// zero-length or out-of-range 1D index), so it is rejected here as well.
+__device__ __forceinline__ Move decode_spatial(const DevConfig &cfg, int action, int flip)
+{
+    Move mv{0, 0, false, true};
+    if (action < 0 || action >= cfg.N * cfg.A) return mv;
+    const int cell = action / cfg.A, ch = action - cell * cfg.A;
+    const int r = cell / cfg.C, c = cell - r * cfg.C;
+    const int mr = cfg.R - 1, mc = cfg.C - 1;
+    int er = r, ec = c;
+    if (ch < mr) er = r + ch + 1;
+    else if (ch < 2 * mr) er = r - (ch - mr + 1);
+    else if (ch < 2 * mr + mc) ec = c + (ch - 2 * mr + 1);
+    else if (ch < 2 * mr + 2 * mc) ec = c - (ch - 2 * mr - mc + 1);
+    else return mv;
+    if (er < 0 || er >= cfg.R || ec < 0 || ec >= cfg.C) return mv;
+    mv.start = view(cell, flip, cfg.N);
+    mv.end = view(er * cfg.C + ec, flip, cfg.N);
+    mv.bad = false;
+    return mv;
+}
+
+// absolute 1D index (impl:352-383); the last index is the noop
+__device__ __forceinline__ Move decode_1d(const DevConfig &cfg, int action)
+{
+    Move mv{0, 0, false, true};
+    if (action == cfg.action_size - 1) { mv.noop = true; mv.bad = false; return mv; }
+    if (action < 0 || action >= cfg.action_size) return mv;
+    const int cell = action / cfg.mpa, off = action - cell * cfg.mpa;
+    const int r = cell / cfg.C, c = cell - r * cfg.C;
+    const int er = off >= cfg.R ? r : off, ec = off >= cfg.R ? off - cfg.R : c;
+    mv.start = cell;
+    mv.end = er * cfg.C + ec;
+    mv.bad = false;
+    return mv;
+}
+
+enum StepStatus { STEP_ILLEGAL = 0, STEP_UNCHANGED = 1, STEP_NOOP_LOSS = 2, STEP_MOVED = 3 };
+
+// impl:726-798 on the compact state (warp-uniform)
+__device__ __forceinline__ bool move_is_legal(const DevConfig &cfg, const WarpMem &m, const Aux &a, const Move &mv,
+                                              bool allow_osc)
+{
+    if (a.over || mv.bad) return false;
+    const int me = a.to_move;
+    const uint32_t sb = m.board[mv.start], eb = m.board[mv.end];
+    const int rank = sb & CELL_RANK;
+    if (rank == 0 || rank > SP_MARSHAL || int((sb >> 4) & 1) != me) return false;
+    if (eb & CELL_OBST) return false;
+    if ((eb & CELL_RANK) != 0 && int((eb >> 4) & 1) == me) return false;
+    const int sr = mv.start / cfg.C, sc = mv.start - sr * cfg.C, er = mv.end / cfg.C, ec = mv.end - er * cfg.C;
+    if ((sr != er) == (sc != ec)) return false;  // diagonal or zero-length
+    if (!allow_osc && a.rcode[me] == 3 && a.rto[me] == mv.start && a.rfrom[me] == mv.end && (eb & CELL_RANK) == 0)
+        return false;  // impl:771-777
+    const int delta = sr != er ? (er - sr) * cfg.C : (ec - sc);
+    const int dist = sr != er ? (er > sr ? er - sr : sr - er) : (ec > sc ? ec - sc : sc - ec);
+    if (rank == SP_SCOUT) {
+        const int stepv = delta / dist;
+        for (int t = 1, cell = mv.start + stepv; t < dist; ++t, cell += stepv)
+            if (m.board[cell] != 0) return false;  // impl:779-792
+    } else if (dist > 1) {
+        return false;  // impl:794
+    }
+    return true;
+}
+
+// records one captured piece (impl:999-1009) in the capture list; lanes search entries in parallel
+__device__ __forceinline__ void add_capture(const DevConfig &cfg, const WarpMem &m, Aux &a, int cell, int owner, int type)
+{
+    const uint32_t key = cap_key(cell, owner, type);
+    const int lane = lane_id();
+    int hit = -1;
+    for (int e = lane; e < a.ncap; e += 32)
+        if ((uint32_t(m.cap[e]) & 0x1fffu) == key) hit = e;
+    const uint32_t vote = __ballot_sync(FULL, hit >= 0);
+    if (vote) {
+        if (hit >= 0 && (m.cap[hit] >> 13) < 7) m.cap[hit] = uint16_t(m.cap[hit] + (1u << 13));
+    } else if (a.ncap < cfg.cap_stride) {
+        if (lane == 0) m.cap[a.ncap] = uint16_t(key);
+        a.ncap += 1;
+    }
+    __syncwarp();
+}
+
+// impl:897-1028: applies a decoded move for the player to move.  The opponent-stuck and max-turn
+// checks (impl:1031-1043) need the next player's move list and are done by the caller.
+__device__ __forceinline__ StepStatus apply_move(const DevConfig &cfg, const WarpMem &m, Aux &a, const Move &mv,
+                                                 bool allow_osc, int &attack)
+{
+    attack = 0;
+    const int me = a.to_move, player = me == 0 ? 1 : -1;
+    if (mv.noop) {  // impl:809-814: a noop is legal only when nothing else is
+        if (mv.bad) return STEP_ILLEGAL;
+        if (a.over) { a.to_move ^= 1; return STEP_UNCHANGED; }  // impl:907-909
+        // K is not known here; the caller pre-computes `has_moves` for noops via gen_moves and passes
+        // mv.bad = true when moves exist, so reaching this point means the player is stuck.
+        a.turn += 1;  // impl:912-920
+        a.over = 1;
+        a.winner = -player;
+        a.to_move ^= 1;
+        return STEP_NOOP_LOSS;
+    }
+    if (!move_is_legal(cfg, m, a, mv, allow_osc)) return STEP_ILLEGAL;
+
+    const uint32_t sb = m.board[mv.start], eb = m.board[mv.end];
+    const int rank = sb & CELL_RANK, defender = eb & CELL_RANK;
+    const int sr = mv.start / cfg.C, er = mv.end / cfg.C;
+    const int dist = sr != er ? (er > sr ? er - sr : sr - er)
+                              : (mv.end > mv.start ? mv.end - mv.start : mv.start - mv.end);
+    a.turn += 1;
+    uint32_t new_start = 0, new_end;  // still flags at start/end are cleared for both sides (impl:939-941)
+    bool wins = false, tie = false;
+    if (defender == 0) {  // impl:955-964
+        const uint32_t revealed = dist > 1 ? CELL_REVEALED : (sb & CELL_REVEALED);
+        new_end = uint32_t(rank) | (uint32_t(me) << 4) | revealed;
+    } else {  // impl:966-995
+        attack = 1;
+        if (rank == SP_MINER && defender == SP_BOMB) wins = true;
+        else if (rank == SP_SPY && defender == SP_MARSHAL) wins = true;
+        else if (defender == SP_FLAG) { a.over = 1; a.winner = player; wins = true; }
+        else if (defender != SP_BOMB) { tie = rank == defender; wins = rank > defender; }
+        if (wins) new_end = uint32_t(rank) | (uint32_t(me) << 4) | CELL_REVEALED;
+        else if (tie) new_end = 0;
+        else new_end = (eb & (CELL_RANK | CELL_OWNER)) | CELL_REVEALED;
+    }
+    __syncwarp();
+    if (lane_id() == 0) { m.board[mv.start] = uint8_t(new_start); m.board[mv.end] = uint8_t(new_end); }
+    __syncwarp();
+    if (defender != 0) {  // impl:999-1009
+        if (!wins) add_capture(cfg, m, a, mv.end, me, rank);
+        if (wins || tie) add_capture(cfg, m, a, mv.end, me ^ 1, defender);
+    }
+    // impl:1013-1028: the mover's recent-move record is rebuilt from scratch
+    if (defender == 0) {
+        const bool onto_came_from = a.rfrom[me] == mv.end;
+        const bool from_next_illegal = a.rto[me] == mv.start && a.rcode[me] == 2;
+        a.rcode[me] = onto_came_from ? (from_next_illegal ? 3 : 2) : 1;
+        a.rfrom[me] = mv.start;
+        a.rto[me] = mv.end;
+    } else {
+        a.rfrom[me] = NO_CELL; a.rto[me] = NO_CELL; a.rcode[me] = 0;
+    }
+    a.to_move ^= 1;
+    return STEP_MOVED;
+}
+
+// ---- setups / reset (impl:213-249, util:13-53, util:241-319) ---------------------------------------
+// own_map[i], i < setup_len: piece code at own-frame cell i (row-major over the usable rows).
+__device__ __forceinline__ void place_side(const DevConfig &cfg, const WarpMem &m, const uint8_t *own_map, int side)
+{
+    for (int i = lane_id(); i < cfg.setup_len; i += 32) {
+        const int code = own_map[i];
+        if (code == 0) continue;
+        const int r = i / cfg.C, c = i - r * cfg.C;
+        int cell;
+        if (side == 0) cell = i;                                                    // impl:220
+        else if (cfg.p2_rot180) cell = cfg.N - 1 - i;                                // impl:221
+        else cell = (cfg.R - 1 - r) * cfg.C + c;                                     // util:263-273 net effect
+        m.board[cell] = uint8_t(uint32_t(code) | (uint32_t(side) << 4) | CELL_STILL);  // impl:224-243
+    }
+}
+
+__device__ __forceinline__ void shuffle_side(const DevConfig &cfg, const WarpMem &m, uint8_t *perm, uint8_t *own_map,
+                                             uint2 key, uint64_t gid, uint32_t episode, int side)
+{
+    // util:13-30: shuffle the usable cells, then deal pieces in piece-code order
+    const int n = cfg.setup_len;
+    for (int i = lane_id(); i < n; i += 32) { perm[i] = uint8_t(i); own_map[i] = 0; }
+    __syncwarp();
+    if (lane_id() == 0) {
+        uint4 rnd = make_uint4(0, 0, 0, 0);
+        int have = 0;
+        uint32_t block = 0;
+        for (int i = n - 1; i >= 1; --i) {
+            if (have == 0) {
+                rnd = philox4x32_10(make_uint4(uint32_t(gid), uint32_t(gid >> 32), RNG_SHUFFLE + uint32_t(side) + 2 * block, episode), key);
+                have = 4;
+                ++block;
+            }
+            const uint32_t u = have == 4 ? rnd.x : have == 3 ? rnd.y : have == 2 ? rnd.z : rnd.w;
+            --have;
+            const int j = int(__umulhi(u, uint32_t(i + 1)));
+            const uint8_t t = perm[i]; perm[i] = perm[j]; perm[j] = t;
+        }
+        for (int k = 0; k < cfg.n_pieces; ++k) own_map[perm[k]] = cfg.piece_seq[k];
+    }
+    __syncwarp();
+}
+
+struct ResetSource {
+    const uint8_t *setups;     // [n_setups][setup_len] or null
+    int n_setups;
+    const int32_t *setup_idx;  // [2] rows for this env, or null = draw
+    bool shuffle;
+};
+
+__device__ __forceinline__ void reset_game(const DevConfig &cfg, const WarpMem &m, Aux &a, const ResetSource &src,
+                                           uint2 key, uint64_t gid)
+{
+    const int lane = lane_id();
+    __syncwarp();
+    for (int i = lane; i < cfg.board_stride; i += 32) m.board[i] = (i < cfg.N && cfg.obstacles[i]) ? uint8_t(CELL_OBST) : uint8_t(0);
+    __syncwarp();
+    const uint32_t episode = a.episode;
+    if (src.shuffle || src.setups == nullptr) {
+        uint8_t *perm = m.scratch, *own_map = m.scratch + cfg.setup_len;
+        for (int side = 0; side < 2; ++side) {
+            shuffle_side(cfg, m, perm, own_map, key, gid, episode, side);
+            place_side(cfg, m, own_map, side);
+            __syncwarp();
+        }
+    } else {
+        int i0, i1;
+        if (src.setup_idx) { i0 = src.setup_idx[0]; i1 = src.setup_idx[1]; }
+        else {
+            const uint4 rnd = philox4x32_10(make_uint4(uint32_t(gid), uint32_t(gid >> 32), RNG_RESET, episode), key);
+            i0 = int(__umulhi(rnd.x, uint32_t(src.n_setups)));  // util:313-314: two independent uniform draws
+            i1 = int(__umulhi(rnd.y, uint32_t(src.n_setups)));
+        }
+        place_side(cfg, m, src.setups + size_t(i0) * cfg.setup_len, 0);
+        place_side(cfg, m, src.setups + size_t(i1) * cfg.setup_len, 1);
+    }
+    __syncwarp();
+    a.turn = 0;
+    a.max_turns = cfg.max_turns;  // impl:247
+    a.over = 0; a.invalid = 0; a.winner = 0;
+    a.to_move = 0;                // maenv:546
+    a.rfrom[0] = a.rfrom[1] = NO_CELL;
+    a.rto[0] = a.rto[1] = NO_CELL;
+    a.rcode[0] = a.rcode[1] = 0;
+    a.ncap = 0;
+    a.episode = episode + 1;
+}
+
+// ---- observation tiles (impl:1232-1397 + maenv:499-508) ---------------------------------------------
+// Channel map of the partial (impl:1306-1332) and full (impl:1200-1227) observations.
+struct ObsMap {
+    int channels, own_true, enemy_true /* -1 = absent */, own_po, enemy_po, obstacle, own_recent, enemy_recent,
+        own_cap, enemy_cap, own_still, enemy_still;
+};
+__device__ __forceinline__ ObsMap po_map() { return ObsMap{67, 0, -1, 12, 25, 38, 39, 40, 41, 53, 65, 66}; }
+__device__ __forceinline__ ObsMap fo_map() { return ObsMap{79, 0, 12, 24, 37, 50, 51, 52, 53, 65, 77, 78}; }
+
+// fills a tile with what an empty board looks like after normalisation
+__device__ __forceinline__ void fill_background(const DevConfig &cfg, float *tile, const ObsMap om)
+{
+    const int total = cfg.N * om.channels;
+    for (int i = lane_id(); i < total; i += 32) {
+        const int ch = i % om.channels;
+        float v = cfg.unit_lut[0];
+        if (ch == om.own_recent || ch == om.enemy_recent) v = cfg.recent_lut[3];
+        else if (ch >= om.own_cap && ch < om.own_cap + 12) v = cfg.cap_lut[(ch - om.own_cap) * 9];
+        else if (ch >= om.enemy_cap && ch < om.enemy_cap + 12) v = cfg.cap_lut[(ch - om.enemy_cap) * 9];
+        tile[i] = v;
+    }
+}
+
+// Writes (SET) or removes (!SET) the sparse, state-dependent entries of a tile for observer `me`.
+template <int K, bool SET>
+__device__ __forceinline__ void patch_obs(const DevConfig &cfg, const WarpMem &m, const Aux &a, float *tile,
+                                          const ObsMap om, int me)
+{
+    const int lane = lane_id(), flip = me, CH = om.channels;
+    const float one = SET ? cfg.unit_lut[1] : cfg.unit_lut[0];
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+        const int p = lane * K + k;
+        if (p < cfg.N) {
+            const uint32_t b = m.board[view(p, flip, cfg.N)];
+            float *cell = tile + p * CH;
+            if (b & CELL_OBST) cell[om.obstacle] = one;
+            const int rank = b & CELL_RANK;
+            if (rank) {
+                const int po = (b & CELL_REVEALED) ? rank : SP_UNKNOWN;
+                if (int((b >> 4) & 1) == me) {
+                    cell[om.own_true + rank - 1] = one;
+                    cell[om.own_po + po - 1] = one;
+                    if (b & CELL_STILL) cell[om.own_still] = one;
+                } else {
+                    if (om.enemy_true >= 0) cell[om.enemy_true + rank - 1] = one;
+                    cell[om.enemy_po + po - 1] = one;
+                    if (b & CELL_STILL) cell[om.enemy_still] = one;
+                }
+            }
+        }
+    }
+    if (lane < 4) {  // recent-move squares: lanes 0/1 own from/to, lanes 2/3 enemy from/to
+        const int who = (lane < 2) ? me : (me ^ 1);
+        const int cell_abs = (lane & 1) ? a.rto[who] : a.rfrom[who];
+        const int code = (lane & 1) ? -a.rcode[who] : 1;
+        if (cell_abs != NO_CELL)
+            tile[view(cell_abs, flip, cfg.N) * CH + (lane < 2 ? om.own_recent : om.enemy_recent)] =
+                cfg.recent_lut[(SET ? code : 0) + 3];
+    }
+    for (int e = lane; e < a.ncap; e += 32) {
+        const uint32_t ent = m.cap[e];
+        const int cell_abs = ent & 0xff, owner = (ent >> 8) & 1, type0 = (ent >> 9) & 15, count = int(ent >> 13) + 1;
+        tile[view(cell_abs, flip, cfg.N) * CH + (owner == me ? om.own_cap : om.enemy_cap) + type0] =
+            cfg.cap_lut[type0 * 9 + (SET ? count : 0)];
+    }
+}
+
+// ---- uniform draw over the generated moves (replaces maenv:830-834) ----------------------------------
+// Order = ascending flat spatial index (cell, then channel), which is the generation order.
+template <int K>
+__device__ __forceinline__ int sample_move(const DevConfig &cfg, const WarpMem &m, const Aux &a, int me, bool allow_osc,
+                                           bool any_moves, uint32_t rnd)
+{
+    if (!any_moves) return cfg.A - 1;  // the noop entry [0,0,A-1]
+    const int lane = lane_id();
+    const Blocked blk = blocked_move(cfg, m, a, me, me, allow_osc);
+    int cnt[K], mine = 0;
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+        const int p = lane * K + k;
+        int c = 0;
+        if (p < cfg.N) {
+            const uint32_t packed = m.reach[p];
+            c = int(packed & 15) + int((packed >> 4) & 15) + int((packed >> 8) & 15) + int((packed >> 12) & 15);
+            if (p == blk.cell && int((packed >> (4 * blk.dir)) & 15) >= blk.dist) c -= 1;
+        }
+        cnt[k] = c;
+        mine += c;
+    }
+    int incl = mine;
+#pragma unroll
+    for (int off = 1; off < 32; off <<= 1) {
+        const int v = __shfl_up_sync(FULL, incl, off);
+        if (lane >= off) incl += v;
+    }
+    const int total = __shfl_sync(FULL, incl, 31);
+    int t = int(__umulhi(rnd, uint32_t(total)));
+    int action = 0;
+    const bool owner = t >= incl - mine && t < incl;
+    if (owner) {
+        t -= incl - mine;
+#pragma unroll
+        for (int k = 0; k < K; ++k) {
+            if (t >= 0 && t < cnt[k]) {
+                const int p = lane * K + k;
+                const uint32_t packed = m.reach[p];
+                const int base[4] = {0, cfg.R - 1, 2 * (cfg.R - 1), 2 * (cfg.R - 1) + (cfg.C - 1)};
+                int left = t;
+                for (int d = 0; d < 4; ++d) {
+                    const int reach = (packed >> (4 * d)) & 15;
+                    const bool skip = p == blk.cell && d == blk.dir && reach >= blk.dist;
+                    const int n = reach - (skip ? 1 : 0);
+                    if (left < n) {
+                        int dist = left + 1;
+                        if (skip && dist >= blk.dist) dist += 1;
+                        action = p * cfg.A + base[d] + dist - 1;
+                        break;
+                    }
+                    left -= n;
+                }
+                t = -1;
+            } else if (t >= 0) {
+                t -= cnt[k];
+            }
+        }
+    }
+    const uint32_t who = __ballot_sync(FULL, owner);
+    return __shfl_sync(FULL, action, __ffs(who) - 1);
+}
+
+}  // namespace sx

@@ -1,0 +1,952 @@
+// sx_kernels.cu -- sm_100a kernels and C ABI of the B200 Stratego engine (include/stratego_b200.h).
+//
+// One persistent warp per game.  The fused kernel stages a game's compact state in shared memory,
+// applies the action, generates the next player's move mask with occupancy bit-lines, renders the
+// observation as "constant background tile + sparse patches" in shared memory and hands the tile to
+// the TMA engine (cp.async.bulk shared->global), so the ~30 KB per env-step of output costs one
+// instruction instead of ~1900 vector stores.  No tensor cores, no CPU fallback.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "../../include/stratego_b200.h"
+#include "sx_device.cuh"
+
+namespace sx {
+
+enum : uint32_t {
+    OP_STEP = 1,         // decode + apply args.actions
+    OP_MASK = 2,         // spatial mask tile -> out.valid_mask
+    OP_PO = 4,           // partial observation -> out.partial_obs
+    OP_FO = 8,           // full observation -> out.full_obs
+    OP_RESET = 16,       // re-set envs selected by reset_mask before anything else
+    OP_WRITE_STATE = 32, // store the state back
+    OP_MASK_1D = 64,     // 1D mask straight to global (facade)
+    OP_NEED_MOVES = 128  // run move generation even without a mask output (stuck check / sampler)
+};
+
+struct KernelArgs {
+    DevConfig cfg;
+    uint8_t *board;
+    int16_t *aux;
+    uint16_t *cap;
+    long long num_envs, env_base;
+    const int32_t *actions;
+    int action_format;
+    const int8_t *player_override;
+    uint32_t flags, ops;
+    sx_outputs out;
+    uint8_t *mask1d;
+    const uint8_t *setups;
+    int n_setups;
+    const int32_t *setup_idx;
+    const uint8_t *reset_mask;
+    uint2 key;
+    long long *stats;
+    int warp_bytes;
+};
+
+__host__ __device__ inline int round16(int v) { return (v + 15) & ~15; }
+
+// shared-memory slice of one warp; host and device must agree on this layout
+__host__ __device__ inline int carve(const DevConfig &cfg, uint32_t ops, uint8_t *base, WarpMem *m)
+{
+    int off = 0;
+    const int po = (ops & OP_PO) ? round16(cfg.po_floats * 4) : 0;
+    const int fo = (ops & OP_FO) ? round16(cfg.fo_floats * 4) : 0;
+    const int mask = (ops & OP_MASK) ? round16(cfg.mask_bytes + 16) : 0;
+    if (m) m->po = reinterpret_cast<float *>(base + off);
+    off += po;
+    if (m) m->fo = reinterpret_cast<float *>(base + off);
+    off += fo;
+    if (m) m->mask = base + off;
+    off += mask;
+    if (m) m->board = base + off;
+    off += cfg.board_stride;
+    if (m) m->cap = reinterpret_cast<uint16_t *>(base + off);
+    off += round16(cfg.cap_stride * 2);
+    if (m) m->lines = reinterpret_cast<uint32_t *>(base + off);
+    off += 256;
+    if (m) m->reach = reinterpret_cast<uint16_t *>(base + off);
+    off += round16(cfg.N * 2);
+    if (m) m->scratch = base + off;
+    off += round16(2 * cfg.setup_len);
+    return off;
+}
+
+__device__ __forceinline__ void zero_bytes16(uint8_t *p, int bytes)
+{
+    const uint4 z = make_uint4(0, 0, 0, 0);
+    for (int i = lane_id(); i < (bytes >> 4); i += 32) reinterpret_cast<uint4 *>(p)[i] = z;
+}
+
+template <int K>
+__global__ void __launch_bounds__(512) sx_fused_kernel(const __grid_constant__ KernelArgs args)
+{
+    extern __shared__ __align__(16) uint8_t smem[];
+    const DevConfig &cfg = args.cfg;
+    const int lane = lane_id(), warp = threadIdx.x >> 5, warps_per_block = blockDim.x >> 5;
+    const uint32_t ops = args.ops, flags = args.flags;
+    WarpMem m;
+    carve(cfg, ops, smem + size_t(warp) * args.warp_bytes, &m);
+
+    const bool do_step = ops & OP_STEP, do_mask = ops & OP_MASK, do_po = ops & OP_PO, do_fo = ops & OP_FO;
+    const bool do_sample = (flags & SX_SAMPLE_NEXT) && args.out.next_action != nullptr;
+    const bool allow_osc = flags & SX_ALLOW_OSCILLATION;
+    const int mask_tile_bytes = round16(cfg.mask_bytes + 16);
+    const ObsMap pom = po_map(), fom = fo_map();
+
+    if (do_po) fill_background(cfg, m.po, pom);
+    if (do_fo) fill_background(cfg, m.fo, fom);
+    if (do_mask) zero_bytes16(m.mask, mask_tile_bytes);
+    __syncwarp();
+
+    long long n_games = 0, n_p1 = 0, n_p2 = 0, n_invalid = 0, n_illegal = 0;
+    const long long total_warps = (long long)gridDim.x * warps_per_block;
+    for (long long env = (long long)blockIdx.x * warps_per_block + warp; env < args.num_envs; env += total_warps) {
+        const uint64_t gid = uint64_t(args.env_base + env);
+        // ---- stage the compact state in shared memory ------------------------------------------
+        {
+            const uint32_t *gb = reinterpret_cast<const uint32_t *>(args.board + env * cfg.board_stride);
+            for (int i = lane; i < (cfg.board_stride >> 2); i += 32) reinterpret_cast<uint32_t *>(m.board)[i] = gb[i];
+            const uint32_t *gc = reinterpret_cast<const uint32_t *>(args.cap + env * cfg.cap_stride);
+            for (int i = lane; i < (cfg.cap_stride >> 1); i += 32) reinterpret_cast<uint32_t *>(m.cap)[i] = gc[i];
+        }
+        const uint4 aw = *reinterpret_cast<const uint4 *>(args.aux + env * 8);
+        Aux a;
+        {
+            const uint32_t w[4] = {aw.x, aw.y, aw.z, aw.w};
+            aux_unpack(w, a);
+        }
+        __syncwarp();
+
+        bool dirty = false;
+        ResetSource src{args.setups, args.n_setups, args.setup_idx ? args.setup_idx + env * 2 : nullptr,
+                        (flags & SX_RESET_RANDOM_SHUFFLE) != 0};
+        if ((ops & OP_RESET) && (args.reset_mask == nullptr || args.reset_mask[env] != 0)) {
+            reset_game(cfg, m, a, src, args.key, gid);
+            dirty = true;
+        }
+
+        // ---- step: decode, validate, apply (impl:897-1028) ----------------------------------------
+        StepStatus status = STEP_UNCHANGED;
+        const int mover = a.to_move;
+        if (do_step) {
+            const int action = args.actions[env];
+            Move mv = args.action_format == SX_ACTION_SPATIAL ? decode_spatial(cfg, action, mover) : decode_1d(cfg, action);
+            if (mv.noop && !mv.bad && !a.over) {  // impl:809-814
+                if (gen_moves<K>(cfg, m, a, mover, false, MarkNone{}, false)) mv.bad = true;
+            }
+            int attack;
+            status = apply_move(cfg, m, a, mv, allow_osc, attack);
+            dirty |= status != STEP_ILLEGAL;
+        }
+
+        // ---- moves of the player the outputs are for ---------------------------------------------
+        int viewer = a.to_move;
+        if (args.player_override) viewer = args.player_override[env] == 1 ? 0 : 1;
+        const int moff = do_mask ? int(reinterpret_cast<uintptr_t>(args.out.valid_mask + env * cfg.mask_bytes) & 15) : 0;
+        bool any = false, have_moves = false;
+        if (do_mask) {
+            any = gen_moves<K>(cfg, m, a, viewer, false, MarkSpatialSmem{m.mask + moff, cfg.A, cfg.R, cfg.C}, do_sample);
+            have_moves = true;
+        } else if ((ops & OP_MASK_1D) != 0) {
+            uint8_t *row = args.mask1d + env * cfg.action_size;
+            any = gen_moves<K>(cfg, m, a, viewer, false, Mark1DGlobal{row, cfg.N, cfg.R, cfg.C, viewer}, false);
+            if (!any && lane == 0) row[cfg.action_size - 1] = 1;  // impl:639-640
+            have_moves = true;
+        } else if ((ops & OP_NEED_MOVES) != 0 && (status == STEP_MOVED || !do_step)) {
+            any = gen_moves<K>(cfg, m, a, viewer, false, MarkNone{}, do_sample);
+            have_moves = true;
+        }
+
+        bool timeout = false;
+        if (status == STEP_MOVED) {
+            if (have_moves && !any && !a.over) { a.over = 1; a.winner = mover == 0 ? 1 : -1; }  // impl:1031-1036
+            if (a.turn >= a.max_turns && !a.over) { a.over = 1; a.invalid = 1; timeout = true; }  // impl:1040-1043
+        }
+        const bool done = do_step && status != STEP_ILLEGAL && a.over;
+        if (do_step) {
+            if (lane == 0) {
+                const int w = a.winner;
+                if (args.out.done) args.out.done[env] = done ? 1 : 0;
+                if (args.out.winner) args.out.winner[env] = int8_t(done ? w : 0);
+                if (args.out.ending_invalid) args.out.ending_invalid[env] = (done && a.invalid) ? 1 : 0;
+                if (args.out.illegal) args.out.illegal[env] = status == STEP_ILLEGAL ? 1 : 0;
+                if (args.out.reward) args.out.reward[env] = (done && !a.invalid) ? float(w) : 0.0f;  // maenv:777-801
+            }
+            if (status == STEP_ILLEGAL) n_illegal += 1;
+            if (done && status != STEP_UNCHANGED) {
+                n_games += 1;
+                n_p1 += a.winner == 1;
+                n_p2 += a.winner == -1;
+                n_invalid += a.invalid;
+            }
+        }
+
+        if (done && (flags & SX_AUTO_RESET)) {
+            reset_game(cfg, m, a, src, args.key, gid);
+            viewer = a.to_move;
+            if (do_mask) {
+                zero_bytes16(m.mask, mask_tile_bytes);
+                __syncwarp();
+                any = gen_moves<K>(cfg, m, a, viewer, false, MarkSpatialSmem{m.mask + moff, cfg.A, cfg.R, cfg.C}, do_sample);
+            } else if (do_sample) {
+                any = gen_moves<K>(cfg, m, a, viewer, false, MarkNone{}, true);
+            }
+        } else if (timeout && do_mask && any) {
+            // the game ended on the turn limit after its mask was generated: terminal masks are noop-only
+            __syncwarp();
+            zero_bytes16(m.mask, mask_tile_bytes);
+            any = false;
+            if (do_sample)
+                for (int k = 0; k < K; ++k)
+                    if (lane * K + k < cfg.N) m.reach[lane * K + k] = 0;
+            __syncwarp();
+        }
+        if (do_mask && !any && lane == 0) m.mask[moff + cfg.A - 1] = 1;  // [0,0,A-1], impl:514-515
+
+        // ---- render + emit -----------------------------------------------------------------------
+        if (do_po) patch_obs<K, true>(cfg, m, a, m.po, pom, viewer);
+        if (do_fo) patch_obs<K, true>(cfg, m, a, m.fo, fom, viewer);
+        if (do_po || do_fo || do_mask) {
+            fence_async_smem();  // make this thread's generic-proxy writes visible to the async proxy
+            __syncwarp();
+            if (do_po) emit_tile(reinterpret_cast<uint8_t *>(args.out.partial_obs + env * cfg.po_floats),
+                                 reinterpret_cast<const uint8_t *>(m.po), cfg.po_floats * 4);
+            if (do_fo) emit_tile(reinterpret_cast<uint8_t *>(args.out.full_obs + env * cfg.fo_floats),
+                                 reinterpret_cast<const uint8_t *>(m.fo), cfg.fo_floats * 4);
+            if (do_mask) emit_tile(args.out.valid_mask + env * cfg.mask_bytes, m.mask + moff, cfg.mask_bytes);
+            if (lane == 0) bulk_commit();
+        }
+        if (args.out.player && lane == 0) args.out.player[env] = viewer == 0 ? 1 : -1;
+
+        if ((ops & OP_WRITE_STATE) && dirty) {
+            uint32_t *gb = reinterpret_cast<uint32_t *>(args.board + env * cfg.board_stride);
+            for (int i = lane; i < (cfg.board_stride >> 2); i += 32) gb[i] = reinterpret_cast<const uint32_t *>(m.board)[i];
+            uint32_t *gc = reinterpret_cast<uint32_t *>(args.cap + env * cfg.cap_stride);
+            for (int i = lane; i < (cfg.cap_stride >> 1); i += 32) gc[i] = reinterpret_cast<const uint32_t *>(m.cap)[i];
+            if (lane == 0) {
+                uint32_t w[4];
+                aux_pack(a, w);
+                *reinterpret_cast<uint4 *>(args.aux + env * 8) = make_uint4(w[0], w[1], w[2], w[3]);
+            }
+        }
+
+        if (do_sample) {
+            const uint4 rnd = philox4x32_10(make_uint4(uint32_t(gid), uint32_t(gid >> 32), RNG_SAMPLE ^ uint32_t(a.turn), a.episode), args.key);
+            const int act = sample_move<K>(cfg, m, a, viewer, false, any, rnd.x);
+            if (lane == 0) args.out.next_action[env] = act;
+        }
+
+        // ---- restore the tiles once the TMA engine has read them ------------------------------------
+        if (do_po || do_fo || do_mask) {
+            if (lane == 0) bulk_wait_read();
+            __syncwarp();
+            if (do_po) patch_obs<K, false>(cfg, m, a, m.po, pom, viewer);
+            if (do_fo) patch_obs<K, false>(cfg, m, a, m.fo, fom, viewer);
+            if (do_mask) zero_bytes16(m.mask, mask_tile_bytes);
+        }
+        __syncwarp();
+    }
+
+    if ((do_po || do_fo || do_mask) && lane == 0) bulk_wait_all();  // global writes of the last tiles
+    if (args.stats) {
+        if (lane == 0) {  // all lanes carry identical counters; lane 0 publishes
+            if (n_games) atomicAdd(reinterpret_cast<unsigned long long *>(args.stats + 0), (unsigned long long)n_games);
+            if (n_p1) atomicAdd(reinterpret_cast<unsigned long long *>(args.stats + 1), (unsigned long long)n_p1);
+            if (n_p2) atomicAdd(reinterpret_cast<unsigned long long *>(args.stats + 2), (unsigned long long)n_p2);
+            if (n_invalid) atomicAdd(reinterpret_cast<unsigned long long *>(args.stats + 3), (unsigned long long)n_invalid);
+            if (n_illegal) atomicAdd(reinterpret_cast<unsigned long long *>(args.stats + 4), (unsigned long long)n_illegal);
+        }
+    }
+}
+
+// ---- dense reference state <-> compact state (impl:16-60) -------------------------------------------
+__global__ void sx_export_kernel(DevConfig cfg, const uint8_t *board, const int16_t *aux, const uint16_t *cap,
+                                 long long num_envs, int64_t *dense, int8_t *player_out)
+{
+    const int lane = lane_id();
+    const long long env = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (env >= num_envs) return;
+    const int N = cfg.N;
+    int64_t *d = dense + env * (long long)SX_NUM_STATE_LAYERS * N;
+    for (int i = lane; i < SX_NUM_STATE_LAYERS * N; i += 32) d[i] = 0;
+    __syncwarp();
+    const uint4 aw = *reinterpret_cast<const uint4 *>(aux + env * 8);
+    const uint32_t w[4] = {aw.x, aw.y, aw.z, aw.w};
+    Aux a;
+    aux_unpack(w, a);
+    const uint8_t *b = board + env * cfg.board_stride;
+    for (int p = lane; p < N; p += 32) {
+        const uint32_t c = b[p];
+        const int rank = c & CELL_RANK, owner = (c >> 4) & 1;
+        if (c & CELL_OBST) d[2 * N + p] = 1;
+        if (rank) {
+            d[owner * N + p] = rank;
+            d[(3 + owner) * N + p] = (c & CELL_REVEALED) ? rank : SP_UNKNOWN;
+            if (c & CELL_STILL) d[(32 + owner) * N + p] = 1;
+        }
+    }
+    if (lane == 0) {
+        d[5 * N + 0] = a.turn;
+        d[5 * N + 1] = a.over;
+        d[5 * N + 2] = a.winner;
+        d[5 * N + cfg.C + 0] = a.max_turns;
+        d[5 * N + cfg.C + 1] = a.invalid;
+        for (int s = 0; s < 2; ++s) {
+            if (a.rfrom[s] != NO_CELL) d[(6 + s) * N + a.rfrom[s]] = 1;
+            if (a.rto[s] != NO_CELL) d[(6 + s) * N + a.rto[s]] = -a.rcode[s];
+        }
+        if (player_out) player_out[env] = a.to_move == 0 ? 1 : -1;
+    }
+    const uint16_t *ce = cap + env * cfg.cap_stride;
+    for (int e = lane; e < a.ncap; e += 32) {
+        const uint32_t ent = ce[e];
+        const int cell = ent & 0xff, owner = (ent >> 8) & 1, type0 = (ent >> 9) & 15, count = int(ent >> 13) + 1;
+        d[(8 + 12 * owner + type0) * N + cell] = count;
+    }
+}
+
+__global__ void sx_import_kernel(DevConfig cfg, uint8_t *board, int16_t *aux, uint16_t *cap, long long num_envs,
+                                 const int64_t *dense, const int8_t *player, uint8_t *status)
+{
+    const int lane = lane_id();
+    const long long env = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (env >= num_envs) return;
+    const int N = cfg.N;
+    const int64_t *d = dense + env * (long long)SX_NUM_STATE_LAYERS * N;
+    uint8_t *b = board + env * cfg.board_stride;
+    uint16_t *ce = cap + env * cfg.cap_stride;
+    int err = 0;
+    for (int p = lane; p < cfg.board_stride; p += 32) {
+        uint32_t c = 0;
+        if (p < N) {
+            const int64_t t1 = d[p], t2 = d[N + p], ob = d[2 * N + p], po1 = d[3 * N + p], po2 = d[4 * N + p];
+            const int64_t s1 = d[32 * N + p], s2 = d[33 * N + p];
+            err |= (t1 < 0 || t1 > 12 || t2 < 0 || t2 > 12 || (t1 != 0 && t2 != 0));
+            err |= (ob != 0 && ob != 1) || (s1 != 0 && s1 != 1) || (s2 != 0 && s2 != 1);
+            err |= t1 ? (po1 != t1 && po1 != SP_UNKNOWN) : (po1 != 0);
+            err |= t2 ? (po2 != t2 && po2 != SP_UNKNOWN) : (po2 != 0);
+            err |= (s1 && !t1) || (s2 && !t2);
+            if (ob) c |= CELL_OBST;
+            if (t1) c |= uint32_t(t1) | (po1 == t1 ? CELL_REVEALED : 0) | (s1 ? CELL_STILL : 0);
+            else if (t2) c |= uint32_t(t2) | CELL_OWNER | (po2 == t2 ? CELL_REVEALED : 0) | (s2 ? CELL_STILL : 0);
+        }
+        b[p] = uint8_t(c);
+    }
+    Aux a;
+    for (int s = 0; s < 2; ++s) {
+        int from = -1, to = -1, code = 0, nfrom = 0, nto = 0;
+        for (int p = lane; p < N; p += 32) {
+            const int64_t v = d[(6 + s) * N + p];
+            if (v == 1) { from = p; nfrom++; }
+            else if (v <= -1 && v >= -3) { to = p; code = int(-v); nto++; }
+            else if (v != 0) err = 1;
+        }
+        for (int off = 16; off > 0; off >>= 1) {
+            from = max(from, __shfl_xor_sync(FULL, from, off));
+            to = max(to, __shfl_xor_sync(FULL, to, off));
+            code = max(code, __shfl_xor_sync(FULL, code, off));
+            nfrom += __shfl_xor_sync(FULL, nfrom, off);
+            nto += __shfl_xor_sync(FULL, nto, off);
+        }
+        err |= nfrom > 1 || nto > 1;
+        a.rfrom[s] = from < 0 ? NO_CELL : from;
+        a.rto[s] = to < 0 ? NO_CELL : to;
+        a.rcode[s] = to < 0 ? 0 : code;
+    }
+    int ncap = 0;
+    for (int layer = 0; layer < 24; ++layer) {
+        for (int p0 = 0; p0 < N; p0 += 32) {
+            const int p = p0 + lane;
+            int64_t cnt = 0;
+            if (p < N) cnt = d[(8 + layer) * N + p];
+            err |= cnt < 0 || cnt > SX_MAX_CAPTURE_COUNT;
+            const bool has = cnt > 0 && cnt <= SX_MAX_CAPTURE_COUNT;
+            const uint32_t vote = __ballot_sync(FULL, has);
+            if (has) {
+                const int slot = ncap + __popc(vote & ((1u << lane) - 1u));
+                if (slot < cfg.cap_stride)
+                    ce[slot] = uint16_t(cap_key(p, layer / 12, layer % 12 + 1) | (uint32_t(cnt - 1) << 13));
+            }
+            ncap += __popc(vote);
+        }
+    }
+    err |= ncap > cfg.cap_stride;
+    for (int e = ncap + lane; e < cfg.cap_stride; e += 32) ce[e] = 0;
+    const int64_t turn = d[5 * N], over = d[5 * N + 1], winner = d[5 * N + 2], maxt = d[5 * N + cfg.C], inval = d[5 * N + cfg.C + 1];
+    err |= turn < 0 || turn > 65535 || maxt < 0 || maxt > 65535 || (over != 0 && over != 1) || winner < -1 || winner > 1 ||
+           (inval != 0 && inval != 1);
+    err = __any_sync(FULL, err);
+    a.turn = int(turn) & 0xffff;
+    a.max_turns = int(maxt) & 0xffff;
+    a.over = over != 0;
+    a.invalid = inval != 0;
+    a.winner = winner > 0 ? 1 : winner < 0 ? -1 : 0;
+    a.to_move = (player && player[env] == -1) ? 1 : 0;
+    a.ncap = min(ncap, cfg.cap_stride);
+    a.episode = 0;
+    if (lane == 0) {
+        uint32_t w[4];
+        aux_pack(a, w);
+        *reinterpret_cast<uint4 *>(aux + env * 8) = make_uint4(w[0], w[1], w[2], w[3]);
+        if (status) status[env] = err ? 1 : 0;
+    }
+}
+
+// uniform draw over the set entries of arbitrary uint8 masks (replaces maenv:830-834)
+__global__ void sx_sample_kernel(const uint8_t *mask, long long num_envs, int mask_len, long long env_base, uint2 key,
+                                 uint32_t step, int32_t *actions)
+{
+    const int lane = lane_id();
+    const long long env = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (env >= num_envs) return;
+    const uint8_t *row = mask + env * mask_len;
+    const int chunk = (mask_len + 31) / 32, lo = lane * chunk, hi = min(mask_len, lo + chunk);
+    int mine = 0;
+    for (int i = lo; i < hi; ++i) mine += row[i] != 0;
+    int incl = mine;
+    for (int off = 1; off < 32; off <<= 1) {
+        const int v = __shfl_up_sync(FULL, incl, off);
+        if (lane >= off) incl += v;
+    }
+    const int total = __shfl_sync(FULL, incl, 31);
+    const uint64_t gid = uint64_t(env_base + env);
+    const uint4 rnd = philox4x32_10(make_uint4(uint32_t(gid), uint32_t(gid >> 32), RNG_SAMPLE, step), key);
+    int t = int(__umulhi(rnd.x, uint32_t(total)));
+    int action = -1;
+    const bool owner = total > 0 && t >= incl - mine && t < incl;
+    if (owner) {
+        t -= incl - mine;
+        for (int i = lo; i < hi; ++i)
+            if (row[i] != 0 && t-- == 0) { action = i; break; }
+    }
+    const uint32_t who = __ballot_sync(FULL, owner);
+    action = who ? __shfl_sync(FULL, action, __ffs(who) - 1) : -1;
+    if (lane == 0) actions[env] = action;
+}
+
+}  // namespace sx
+
+// =====================================================================================================
+// host side
+// =====================================================================================================
+using namespace sx;
+
+struct sx_config {
+    DevConfig dev;
+    sx_layout layout;
+    int cells_per_lane;  // K
+};
+
+static thread_local std::string g_error;
+static int fail(const std::string &msg)
+{
+    g_error = msg;
+    return -1;
+}
+static int cuda_fail(const char *what, cudaError_t e) { return fail(std::string(what) + ": " + cudaGetErrorString(e)); }
+
+extern "C" const char *sx_last_error(void) { return g_error.c_str(); }
+extern "C" int sx_version(void) { return 1; }
+
+extern "C" int sx_config_create(const sx_config_desc *desc, sx_config **out)
+{
+    if (!desc || !out) return fail("sx_config_create: null argument");
+    if (desc->rows < 3 || desc->cols < 3) return fail("Both rows and columns have to be at least 3");  // penv:28-30
+    if (desc->rows > 15 || desc->cols > 15) return fail("boards larger than 15x15 are not supported");
+    if (desc->max_turns < 1 || desc->max_turns > 65535) return fail("max_turns must be in 1..65535");
+    if (!desc->obstacles || !desc->captured_lut || !desc->recent_lut || !desc->unit_lut) return fail("sx_config_create: null table");
+    sx_config *c = new (std::nothrow) sx_config();
+    if (!c) return fail("out of memory");
+    DevConfig &d = c->dev;
+    std::memset(&d, 0, sizeof(d));
+    d.R = desc->rows; d.C = desc->cols; d.N = d.R * d.C;
+    d.A = 2 * (d.R - 1) + 2 * (d.C - 1) + 1;
+    d.mpa = d.R + d.C;
+    d.action_size = d.N * d.mpa + 1;
+    d.board_stride = (d.N + 15) & ~15;
+    d.max_turns = desc->max_turns;
+    d.usable_rows = desc->usable_rows;
+    d.setup_len = desc->usable_rows * d.C;
+    d.p2_rot180 = desc->p2_rot180 ? 1 : 0;
+    int pieces = 0;
+    for (int t = 1; t <= 12; ++t) {
+        if (desc->piece_amounts[t] < 0 || desc->piece_amounts[t] > SX_MAX_CAPTURE_COUNT) { delete c; return fail("piece amount out of range 0..8"); }
+        for (int k = 0; k < desc->piece_amounts[t]; ++k) {
+            if (pieces >= 128) { delete c; return fail("too many pieces"); }
+            d.piece_seq[pieces++] = uint8_t(t);
+        }
+    }
+    d.n_pieces = pieces;
+    if (d.usable_rows < 1 || 2 * d.usable_rows > d.R || d.setup_len > 120 || pieces > d.setup_len) { delete c; return fail("pieces do not fit in the usable rows"); }
+    d.cap_stride = std::max(8, (2 * pieces + 7) & ~7);
+    d.po_floats = d.N * SX_PO_CHANNELS;
+    d.fo_floats = d.N * SX_FO_CHANNELS;
+    d.mask_bytes = d.N * d.A;
+    std::memcpy(d.cap_lut, desc->captured_lut, sizeof(d.cap_lut));
+    std::memcpy(d.recent_lut, desc->recent_lut, sizeof(d.recent_lut));
+    std::memcpy(d.unit_lut, desc->unit_lut, sizeof(d.unit_lut));
+    for (int i = 0; i < d.N; ++i) d.obstacles[i] = desc->obstacles[i] ? 1 : 0;
+    const int k = (d.N + 31) / 32;
+    c->cells_per_lane = k <= 1 ? 1 : k <= 2 ? 2 : k <= 4 ? 4 : 8;
+    sx_layout &l = c->layout;
+    l.rows = d.R; l.cols = d.C; l.cells = d.N; l.spatial_channels = d.A; l.spatial_actions = d.mask_bytes;
+    l.action_size = d.action_size; l.board_stride = d.board_stride; l.aux_stride = 8; l.captured_stride = d.cap_stride;
+    l.po_floats = d.po_floats; l.fo_floats = d.fo_floats; l.setup_len = d.setup_len; l.pieces_per_side = pieces;
+    *out = c;
+    return 0;
+}
+
+extern "C" void sx_config_destroy(sx_config *cfg) { delete cfg; }
+
+extern "C" int sx_config_layout(const sx_config *cfg, sx_layout *out)
+{
+    if (!cfg || !out) return fail("sx_config_layout: null argument");
+    *out = cfg->layout;
+    return 0;
+}
+
+typedef void (*fused_fn)(const KernelArgs);
+static fused_fn fused_for(int k)
+{
+    switch (k) {
+    case 1: return sx_fused_kernel<1>;
+    case 2: return sx_fused_kernel<2>;
+    case 4: return sx_fused_kernel<4>;
+    default: return sx_fused_kernel<8>;
+    }
+}
+
+struct LaunchPlan {
+    int warps_per_block, blocks_per_sm, smem_per_block, num_sms, grid, regs;
+};
+
+// picks the block shape that maximises resident warps per SM for this variant's shared-memory slice
+static int plan_launch(const sx_config *cfg, uint32_t ops, long long num_envs, LaunchPlan *plan, int *warp_bytes_out)
+{
+    const int warp_bytes = carve(cfg->dev, ops, nullptr, nullptr);
+    fused_fn fn = fused_for(cfg->cells_per_lane);
+    int device = 0;
+    cudaError_t e = cudaGetDevice(&device);
+    if (e != cudaSuccess) return cuda_fail("cudaGetDevice", e);
+    int num_sms = 0, max_smem_optin = 0;
+    cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, device);
+    cudaDeviceGetAttribute(&max_smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device);
+    if (warp_bytes > max_smem_optin) return fail("variant does not fit in shared memory");
+    e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem_optin);
+    if (e != cudaSuccess) return cuda_fail("cudaFuncSetAttribute", e);
+    cudaFuncAttributes attr;
+    e = cudaFuncGetAttributes(&attr, fn);
+    if (e != cudaSuccess) return cuda_fail("cudaFuncGetAttributes", e);
+    int best_w = 1, best_blocks = 0, best_warps = 0;
+    for (int w = 1; w <= 16; ++w) {
+        const long long smem = (long long)w * warp_bytes;
+        if (smem > max_smem_optin) break;
+        int blocks = 0;
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks, fn, w * 32, size_t(smem));
+        if (e != cudaSuccess) return cuda_fail("cudaOccupancyMaxActiveBlocksPerMultiprocessor", e);
+        if (blocks * w > best_warps) { best_warps = blocks * w; best_w = w; best_blocks = blocks; }
+    }
+    if (best_warps == 0) return fail("fused kernel cannot be resident on this device");
+    plan->warps_per_block = best_w;
+    plan->blocks_per_sm = best_blocks;
+    plan->smem_per_block = best_w * warp_bytes;
+    plan->num_sms = num_sms;
+    plan->regs = attr.numRegs;
+    long long grid = (long long)num_sms * best_blocks;
+    const long long needed = (num_envs + best_w - 1) / best_w;
+    plan->grid = int(std::max(1LL, std::min(grid, needed)));
+    *warp_bytes_out = warp_bytes;
+    return 0;
+}
+
+static int launch_fused(const sx_config *cfg, KernelArgs &args, cudaStream_t stream)
+{
+    if (args.num_envs <= 0) return 0;
+    LaunchPlan plan;
+    int warp_bytes = 0;
+    if (int rc = plan_launch(cfg, args.ops, args.num_envs, &plan, &warp_bytes)) return rc;
+    args.cfg = cfg->dev;
+    args.warp_bytes = warp_bytes;
+    fused_for(cfg->cells_per_lane)<<<plan.grid, plan.warps_per_block * 32, plan.smem_per_block, stream>>>(args);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return cuda_fail("sx fused kernel launch", e);
+    return 0;
+}
+
+static uint2 make_key(uint64_t seed) { return make_uint2(uint32_t(seed), uint32_t(seed >> 32)); }
+
+static void base_args(KernelArgs &a, sx_state st, int64_t num_envs, int64_t env_base)
+{
+    std::memset(&a, 0, sizeof(a));
+    a.board = st.board; a.aux = st.aux; a.cap = st.captured;
+    a.num_envs = num_envs; a.env_base = env_base;
+}
+
+static int check_state(const sx_config *cfg, sx_state st, const char *who)
+{
+    if (!cfg) return fail(std::string(who) + ": null config");
+    if (!st.board || !st.aux || !st.captured) return fail(std::string(who) + ": null state tensor");
+    return 0;
+}
+
+extern "C" int sx_reset(const sx_config *cfg, sx_state st, int64_t num_envs, int64_t env_base, const uint8_t *reset_mask_d,
+                        const uint8_t *setups_d, int32_t n_setups, const int32_t *setup_idx_d, uint64_t seed, uint32_t flags,
+                        void *stream)
+{
+    if (int rc = check_state(cfg, st, "sx_reset")) return rc;
+    if (!(flags & SX_RESET_RANDOM_SHUFFLE) && (!setups_d || n_setups < 1)) return fail("sx_reset: a setup table or SX_RESET_RANDOM_SHUFFLE is required");
+    KernelArgs a;
+    base_args(a, st, num_envs, env_base);
+    a.ops = OP_RESET | OP_WRITE_STATE;
+    a.flags = flags & SX_RESET_RANDOM_SHUFFLE;
+    a.setups = setups_d; a.n_setups = n_setups; a.setup_idx = setup_idx_d; a.reset_mask = reset_mask_d;
+    a.key = make_key(seed);
+    return launch_fused(cfg, a, static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int sx_import_ref_state(const sx_config *cfg, sx_state st, int64_t num_envs, const int64_t *dense_d,
+                                   const int8_t *player_d, uint8_t *status_d, void *stream)
+{
+    if (int rc = check_state(cfg, st, "sx_import_ref_state")) return rc;
+    if (!dense_d) return fail("sx_import_ref_state: null dense state");
+    if (num_envs <= 0) return 0;
+    const int wpb = 4;
+    sx_import_kernel<<<unsigned((num_envs + wpb - 1) / wpb), wpb * 32, 0, static_cast<cudaStream_t>(stream)>>>(
+        cfg->dev, st.board, st.aux, st.captured, num_envs, dense_d, player_d, status_d);
+    cudaError_t e = cudaGetLastError();
+    return e == cudaSuccess ? 0 : cuda_fail("sx_import_kernel", e);
+}
+
+extern "C" int sx_export_ref_state(const sx_config *cfg, sx_state st, int64_t num_envs, int64_t *dense_d, int8_t *player_d,
+                                   void *stream)
+{
+    if (int rc = check_state(cfg, st, "sx_export_ref_state")) return rc;
+    if (!dense_d) return fail("sx_export_ref_state: null dense state");
+    if (num_envs <= 0) return 0;
+    const int wpb = 4;
+    sx_export_kernel<<<unsigned((num_envs + wpb - 1) / wpb), wpb * 32, 0, static_cast<cudaStream_t>(stream)>>>(
+        cfg->dev, st.board, st.aux, st.captured, num_envs, dense_d, player_d);
+    cudaError_t e = cudaGetLastError();
+    return e == cudaSuccess ? 0 : cuda_fail("sx_export_kernel", e);
+}
+
+extern "C" int sx_valid_mask(const sx_config *cfg, sx_state st, int64_t num_envs, const int8_t *player_d, int32_t format,
+                             uint8_t *mask_d, void *stream)
+{
+    if (int rc = check_state(cfg, st, "sx_valid_mask")) return rc;
+    if (!mask_d) return fail("sx_valid_mask: null output");
+    KernelArgs a;
+    base_args(a, st, num_envs, 0);
+    a.player_override = player_d;
+    if (format == SX_ACTION_SPATIAL) {
+        a.ops = OP_MASK;
+        a.out.valid_mask = mask_d;
+    } else if (format == SX_ACTION_1D) {
+        cudaError_t e = cudaMemsetAsync(mask_d, 0, size_t(num_envs) * cfg->dev.action_size, static_cast<cudaStream_t>(stream));
+        if (e != cudaSuccess) return cuda_fail("cudaMemsetAsync", e);
+        a.ops = OP_MASK_1D;
+        a.mask1d = mask_d;
+    } else {
+        return fail("sx_valid_mask: unknown format");
+    }
+    return launch_fused(cfg, a, static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int sx_observe(const sx_config *cfg, sx_state st, int64_t num_envs, const int8_t *player_d, sx_outputs out,
+                          void *stream)
+{
+    if (int rc = check_state(cfg, st, "sx_observe")) return rc;
+    KernelArgs a;
+    base_args(a, st, num_envs, 0);
+    a.player_override = player_d;
+    a.out = out;
+    a.out.next_action = nullptr;
+    a.ops = (out.valid_mask ? OP_MASK : 0) | (out.partial_obs ? OP_PO : 0) | (out.full_obs ? OP_FO : 0);
+    if (a.ops == 0 && !out.player) return 0;
+    return launch_fused(cfg, a, static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int sx_step(const sx_config *cfg, sx_state st, int64_t num_envs, const int32_t *actions_d, int32_t action_format,
+                       uint32_t flags, sx_outputs out, void *stream)
+{
+    if (int rc = check_state(cfg, st, "sx_step")) return rc;
+    if (!actions_d) return fail("sx_step: null actions");
+    if (action_format != SX_ACTION_SPATIAL && action_format != SX_ACTION_1D) return fail("sx_step: unknown action format");
+    KernelArgs a;
+    base_args(a, st, num_envs, 0);
+    a.actions = actions_d; a.action_format = action_format;
+    a.flags = flags & SX_ALLOW_OSCILLATION;
+    a.out = out;
+    a.out.partial_obs = nullptr; a.out.full_obs = nullptr; a.out.valid_mask = nullptr; a.out.next_action = nullptr;
+    a.ops = OP_STEP | OP_WRITE_STATE | OP_NEED_MOVES;
+    return launch_fused(cfg, a, static_cast<cudaStream_t>(stream));
+}
+
+static uint32_t step_all_ops(const sx_outputs &out, uint32_t flags)
+{
+    uint32_t ops = OP_STEP | OP_WRITE_STATE | OP_NEED_MOVES;
+    if (out.valid_mask) ops |= OP_MASK;
+    if (out.partial_obs) ops |= OP_PO;
+    if (out.full_obs) ops |= OP_FO;
+    (void)flags;
+    return ops;
+}
+
+extern "C" int sx_step_all(const sx_config *cfg, sx_state st, int64_t num_envs, int64_t env_base, const int32_t *actions_d,
+                           int32_t action_format, uint32_t flags, const uint8_t *setups_d, int32_t n_setups, uint64_t seed,
+                           sx_outputs out, int64_t *stats_d, void *stream)
+{
+    if (int rc = check_state(cfg, st, "sx_step_all")) return rc;
+    if (!actions_d) return fail("sx_step_all: null actions");
+    if (action_format != SX_ACTION_SPATIAL && action_format != SX_ACTION_1D) return fail("sx_step_all: unknown action format");
+    if ((flags & SX_AUTO_RESET) && !(flags & SX_RESET_RANDOM_SHUFFLE) && (!setups_d || n_setups < 1))
+        return fail("sx_step_all: auto-reset needs a setup table or SX_RESET_RANDOM_SHUFFLE");
+    KernelArgs a;
+    base_args(a, st, num_envs, env_base);
+    a.actions = actions_d; a.action_format = action_format;
+    a.flags = flags;
+    a.out = out;
+    a.ops = step_all_ops(out, flags);
+    a.setups = setups_d; a.n_setups = n_setups;
+    a.key = make_key(seed);
+    a.stats = reinterpret_cast<long long *>(stats_d);
+    return launch_fused(cfg, a, static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int sx_sample_valid(const uint8_t *mask_d, int64_t num_envs, int32_t mask_len, int64_t env_base, uint64_t seed,
+                               uint32_t step, int32_t *actions_d, void *stream)
+{
+    if (!mask_d || !actions_d) return fail("sx_sample_valid: null argument");
+    if (num_envs <= 0) return 0;
+    const int wpb = 8;
+    sx_sample_kernel<<<unsigned((num_envs + wpb - 1) / wpb), wpb * 32, 0, static_cast<cudaStream_t>(stream)>>>(
+        mask_d, num_envs, mask_len, env_base, make_key(seed), step, actions_d);
+    cudaError_t e = cudaGetLastError();
+    return e == cudaSuccess ? 0 : cuda_fail("sx_sample_kernel", e);
+}
+
+extern "C" int sx_step_all_launch_info(const sx_config *cfg, uint32_t obs_mask, sx_launch_info *out)
+{
+    if (!cfg || !out) return fail("sx_step_all_launch_info: null argument");
+    uint32_t ops = OP_STEP | OP_WRITE_STATE | OP_NEED_MOVES;
+    if (obs_mask & 1) ops |= OP_PO;
+    if (obs_mask & 2) ops |= OP_FO;
+    if (obs_mask & 4) ops |= OP_MASK;
+    LaunchPlan plan;
+    int warp_bytes = 0;
+    if (int rc = plan_launch(cfg, ops, 1LL << 40, &plan, &warp_bytes)) return rc;
+    out->warps_per_block = plan.warps_per_block; out->blocks_per_sm = plan.blocks_per_sm;
+    out->smem_bytes_per_block = plan.smem_per_block; out->num_sms = plan.num_sms; out->grid_blocks = plan.grid;
+    out->regs_per_thread = plan.regs;
+    return 0;
+}
+
+// ---- host-buffer convenience object ------------------------------------------------------------------
+struct sx_host_env {
+    const sx_config *cfg;
+    int64_t num_envs, env_base;
+    uint32_t obs_mask, flags;
+    uint64_t seed;
+    int n_chunks;
+    sx_state st;
+    sx_outputs dev;        // device outputs, full batch
+    int32_t *actions_d;
+    uint8_t *setups_d;
+    int32_t n_setups;
+    int64_t *stats_d;
+    std::vector<cudaStream_t> streams;
+};
+
+template <typename T>
+static cudaError_t dev_alloc(T **p, size_t count) { return cudaMalloc(reinterpret_cast<void **>(p), std::max<size_t>(count, 1) * sizeof(T)); }
+
+extern "C" void sx_host_env_destroy(sx_host_env *env)
+{
+    if (!env) return;
+    for (cudaStream_t s : env->streams) cudaStreamDestroy(s);
+    cudaFree(env->st.board); cudaFree(env->st.aux); cudaFree(env->st.captured);
+    cudaFree(env->dev.partial_obs); cudaFree(env->dev.full_obs); cudaFree(env->dev.valid_mask);
+    cudaFree(env->dev.reward); cudaFree(env->dev.done); cudaFree(env->dev.winner); cudaFree(env->dev.ending_invalid);
+    cudaFree(env->dev.illegal); cudaFree(env->dev.player); cudaFree(env->dev.next_action);
+    cudaFree(env->actions_d); cudaFree(env->setups_d); cudaFree(env->stats_d);
+    delete env;
+}
+
+extern "C" int sx_host_env_create(const sx_config *cfg, int64_t num_envs, int64_t env_base, uint32_t obs_mask, uint32_t flags,
+                                  const uint8_t *setups_host, int32_t n_setups, uint64_t seed, int32_t n_chunks,
+                                  sx_host_env **out)
+{
+    if (!cfg || !out || num_envs < 1) return fail("sx_host_env_create: bad argument");
+    if (!(flags & SX_RESET_RANDOM_SHUFFLE) && (!setups_host || n_setups < 1))
+        return fail("sx_host_env_create: a setup table or SX_RESET_RANDOM_SHUFFLE is required");
+    sx_host_env *h = new (std::nothrow) sx_host_env();
+    if (!h) return fail("out of memory");
+    h->cfg = cfg; h->num_envs = num_envs; h->env_base = env_base; h->obs_mask = obs_mask; h->flags = flags; h->seed = seed;
+    h->n_chunks = int(std::max<int64_t>(1, std::min<int64_t>(n_chunks, num_envs)));
+    h->n_setups = n_setups;
+    const DevConfig &d = cfg->dev;
+    const size_t B = size_t(num_envs);
+    cudaError_t e = cudaSuccess;
+    auto ok = [&](cudaError_t r) { if (e == cudaSuccess) e = r; };
+    ok(dev_alloc(&h->st.board, B * d.board_stride));
+    ok(dev_alloc(&h->st.aux, B * 8));
+    ok(dev_alloc(&h->st.captured, B * d.cap_stride));
+    if (obs_mask & 1) ok(dev_alloc(&h->dev.partial_obs, B * d.po_floats));
+    if (obs_mask & 2) ok(dev_alloc(&h->dev.full_obs, B * d.fo_floats));
+    if (obs_mask & 4) ok(dev_alloc(&h->dev.valid_mask, B * d.mask_bytes));
+    ok(dev_alloc(&h->dev.reward, B)); ok(dev_alloc(&h->dev.done, B)); ok(dev_alloc(&h->dev.winner, B));
+    ok(dev_alloc(&h->dev.ending_invalid, B)); ok(dev_alloc(&h->dev.illegal, B)); ok(dev_alloc(&h->dev.player, B));
+    ok(dev_alloc(&h->dev.next_action, B));
+    ok(dev_alloc(&h->actions_d, B));
+    ok(dev_alloc(&h->stats_d, 8));
+    if (setups_host && n_setups > 0) {
+        ok(dev_alloc(&h->setups_d, size_t(n_setups) * d.setup_len));
+        if (e == cudaSuccess) ok(cudaMemcpy(h->setups_d, setups_host, size_t(n_setups) * d.setup_len, cudaMemcpyHostToDevice));
+    }
+    if (e == cudaSuccess) ok(cudaMemset(h->st.aux, 0, B * 8 * sizeof(int16_t)));
+    if (e == cudaSuccess) ok(cudaMemset(h->stats_d, 0, 8 * sizeof(int64_t)));
+    const int n_streams = std::min(h->n_chunks, 4);
+    for (int i = 0; i < n_streams && e == cudaSuccess; ++i) {
+        cudaStream_t s;
+        ok(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
+        if (e == cudaSuccess) h->streams.push_back(s);
+    }
+    if (e != cudaSuccess) {
+        sx_host_env_destroy(h);
+        return cuda_fail("sx_host_env_create", e);
+    }
+    *out = h;
+    return 0;
+}
+
+static sx_state offset_state(const sx_host_env *h, int64_t lo)
+{
+    const DevConfig &d = h->cfg->dev;
+    return sx_state{h->st.board + lo * d.board_stride, h->st.aux + lo * 8, h->st.captured + lo * d.cap_stride};
+}
+
+static sx_outputs offset_outputs(const DevConfig &d, const sx_outputs &o, int64_t lo)
+{
+    sx_outputs r = o;
+    if (r.partial_obs) r.partial_obs += lo * d.po_floats;
+    if (r.full_obs) r.full_obs += lo * d.fo_floats;
+    if (r.valid_mask) r.valid_mask += lo * d.mask_bytes;
+    if (r.reward) r.reward += lo;
+    if (r.done) r.done += lo;
+    if (r.winner) r.winner += lo;
+    if (r.ending_invalid) r.ending_invalid += lo;
+    if (r.illegal) r.illegal += lo;
+    if (r.player) r.player += lo;
+    if (r.next_action) r.next_action += lo;
+    return r;
+}
+
+template <typename T>
+static cudaError_t d2h(T *host, const T *dev, size_t count, cudaStream_t s)
+{
+    if (!host || !dev) return cudaSuccess;
+    return cudaMemcpyAsync(host, dev, count * sizeof(T), cudaMemcpyDeviceToHost, s);
+}
+
+static int copy_outputs(const sx_host_env *h, const sx_outputs &host, int64_t lo, int64_t n, cudaStream_t s)
+{
+    const DevConfig &d = h->cfg->dev;
+    const sx_outputs dv = offset_outputs(d, h->dev, lo), hv = offset_outputs(d, host, lo);
+    cudaError_t e = cudaSuccess;
+    auto ok = [&](cudaError_t r) { if (e == cudaSuccess) e = r; };
+    ok(d2h(hv.partial_obs, dv.partial_obs, size_t(n) * d.po_floats, s));
+    ok(d2h(hv.full_obs, dv.full_obs, size_t(n) * d.fo_floats, s));
+    ok(d2h(hv.valid_mask, dv.valid_mask, size_t(n) * d.mask_bytes, s));
+    ok(d2h(hv.reward, dv.reward, size_t(n), s));
+    ok(d2h(hv.done, dv.done, size_t(n), s));
+    ok(d2h(hv.winner, dv.winner, size_t(n), s));
+    ok(d2h(hv.ending_invalid, dv.ending_invalid, size_t(n), s));
+    ok(d2h(hv.illegal, dv.illegal, size_t(n), s));
+    ok(d2h(hv.player, dv.player, size_t(n), s));
+    ok(d2h(hv.next_action, dv.next_action, size_t(n), s));
+    return e == cudaSuccess ? 0 : cuda_fail("sx_host_env D2H", e);
+}
+
+extern "C" int sx_host_env_sync(sx_host_env *env)
+{
+    if (!env) return fail("sx_host_env_sync: null env");
+    for (cudaStream_t s : env->streams) {
+        cudaError_t e = cudaStreamSynchronize(s);
+        if (e != cudaSuccess) return cuda_fail("cudaStreamSynchronize", e);
+    }
+    return 0;
+}
+
+extern "C" int sx_host_env_reset(sx_host_env *h, sx_outputs host_out)
+{
+    if (!h) return fail("sx_host_env_reset: null env");
+    for (int c = 0; c < h->n_chunks; ++c) {
+        const int64_t lo = h->num_envs * c / h->n_chunks, hi = h->num_envs * (c + 1) / h->n_chunks;
+        cudaStream_t s = h->streams[c % h->streams.size()];
+        if (int rc = sx_reset(h->cfg, offset_state(h, lo), hi - lo, h->env_base + lo, nullptr, h->setups_d, h->n_setups, nullptr,
+                              h->seed, h->flags & SX_RESET_RANDOM_SHUFFLE, s))
+            return rc;
+        sx_outputs o = offset_outputs(h->cfg->dev, h->dev, lo);
+        KernelArgs a;
+        base_args(a, offset_state(h, lo), hi - lo, h->env_base + lo);
+        a.out = o;
+        a.flags = h->flags & SX_SAMPLE_NEXT;
+        a.key = make_key(h->seed);
+        a.ops = (o.valid_mask ? OP_MASK : 0) | (o.partial_obs ? OP_PO : 0) | (o.full_obs ? OP_FO : 0) | OP_NEED_MOVES;
+        if (int rc = launch_fused(h->cfg, a, s)) return rc;
+        if (int rc = copy_outputs(h, host_out, lo, hi - lo, s)) return rc;
+    }
+    return sx_host_env_sync(h);
+}
+
+static int host_env_step_impl(sx_host_env *h, const int32_t *actions_host, const int32_t *actions_dev_src,
+                              const sx_outputs *host_out)
+{
+    for (int c = 0; c < h->n_chunks; ++c) {
+        const int64_t lo = h->num_envs * c / h->n_chunks, hi = h->num_envs * (c + 1) / h->n_chunks;
+        cudaStream_t s = h->streams[c % h->streams.size()];
+        const int32_t *acts = actions_dev_src ? actions_dev_src + lo : h->actions_d + lo;
+        if (actions_host) {
+            cudaError_t e = cudaMemcpyAsync(h->actions_d + lo, actions_host + lo, size_t(hi - lo) * sizeof(int32_t),
+                                            cudaMemcpyHostToDevice, s);
+            if (e != cudaSuccess) return cuda_fail("sx_host_env H2D", e);
+        }
+        if (int rc = sx_step_all(h->cfg, offset_state(h, lo), hi - lo, h->env_base + lo, acts, SX_ACTION_SPATIAL, h->flags,
+                                 h->setups_d, h->n_setups, h->seed, offset_outputs(h->cfg->dev, h->dev, lo), h->stats_d, s))
+            return rc;
+        if (host_out)
+            if (int rc = copy_outputs(h, *host_out, lo, hi - lo, s)) return rc;
+    }
+    return 0;
+}
+
+extern "C" int sx_host_env_step(sx_host_env *h, const int32_t *actions_host, sx_outputs host_out)
+{
+    if (!h || !actions_host) return fail("sx_host_env_step: null argument");
+    if (int rc = host_env_step_impl(h, actions_host, nullptr, &host_out)) return rc;
+    return sx_host_env_sync(h);
+}
+
+extern "C" int sx_host_env_step_device(sx_host_env *h, int32_t use_sampled_actions)
+{
+    if (!h) return fail("sx_host_env_step_device: null env");
+    if (use_sampled_actions) {
+        // the sampled actions of the previous step become this step's input (device to device, same stream order)
+        for (int c = 0; c < h->n_chunks; ++c) {
+            const int64_t lo = h->num_envs * c / h->n_chunks, hi = h->num_envs * (c + 1) / h->n_chunks;
+            cudaStream_t s = h->streams[c % h->streams.size()];
+            cudaError_t e = cudaMemcpyAsync(h->actions_d + lo, h->dev.next_action + lo, size_t(hi - lo) * sizeof(int32_t),
+                                            cudaMemcpyDeviceToDevice, s);
+            if (e != cudaSuccess) return cuda_fail("sx_host_env D2D", e);
+        }
+    }
+    return host_env_step_impl(h, nullptr, nullptr, nullptr);
+}

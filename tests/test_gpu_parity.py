@@ -1,0 +1,170 @@
+"""GPU parity: the CUDA engine (through the C ABI) against the reference's golden vectors and the C oracle.
+
+Bit-exact everywhere: states, masks, float observations (compared as uint32), rewards, dones.
+"""
+import numpy as np
+import pytest
+import torch
+
+from _golden import VERSIONS, known, traj, transitions, unpack_mask
+
+pytestmark = pytest.mark.gpu
+
+
+def _engine(version, p2_rot180=True):
+    from stratego_env_b200.config import VERSION_CONFIGS, as_version
+    from stratego_env_b200.engine import StrategoEngine
+    return StrategoEngine(VERSION_CONFIGS[as_version(version)], device="cuda:0", p2_rot180=p2_rot180)
+
+
+def _oracle(version):
+    from oracle.binding import OracleEnvLogic
+    from stratego_env_b200.config import VERSION_CONFIGS, as_version
+    cfg = VERSION_CONFIGS[as_version(version)]
+    return OracleEnvLogic(cfg["rows"], cfg["columns"], cfg["piece_amounts"])
+
+
+def _bits(x):
+    return np.ascontiguousarray(x, dtype=np.float32).view(np.uint32)
+
+
+def _t(x, dtype):
+    return torch.as_tensor(np.ascontiguousarray(x), dtype=dtype, device="cuda:0")
+
+
+@pytest.mark.parametrize("version", VERSIONS)
+def test_step_all_vs_golden_and_oracle(version):
+    """one fused launch over every recorded transition: next state, outcome, next mask, next observations"""
+    t = traj(version)
+    eng, orc = _engine(version), _oracle(version)
+    R, C, A = eng.spatial_action_size
+    idx = transitions(t)
+    states = t["states"].astype(np.int64)
+    st = eng.import_ref_state(_t(states[idx], torch.int64), _t(t["players"][idx], torch.int8))
+    out = eng.alloc_outputs(len(idx), partial=True, full=True, mask=True)
+    eng.step_all(st, _t(t["actions_spatial"][idx], torch.int32), out)
+    dense, player = eng.export_ref_state(st)
+    torch.cuda.synchronize()
+    dense, player = dense.cpu().numpy(), player.cpu().numpy()
+    assert np.array_equal(dense, states[idx + 1]), version
+    assert np.array_equal(player, t["players"][idx + 1])
+    assert not out["illegal"].any().item()
+    assert np.array_equal(out["done"].cpu().numpy().astype(bool), t["dones"][idx])
+    assert np.array_equal(out["ending_invalid"].cpu().numpy().astype(bool), t["invalid"][idx])
+    # maenv:699: reward seen by the next player; device reports player +1's final reward
+    rew = out["reward"].cpu().numpy()
+    expect_p1 = np.where(t["dones"][idx] & ~t["invalid"][idx], t["rewards"][idx] * t["players"][idx + 1], 0.0)
+    assert np.array_equal(_bits(rew), _bits(expect_p1.astype(np.float32)))
+    mask = out["valid_mask"].cpu().numpy().reshape(len(idx), -1)
+    assert np.array_equal(mask, unpack_mask(t["mask_bits"][idx + 1], R * C * A))
+    po, fo = out["partial_obs"].cpu().numpy(), out["full_obs"].cpu().numpy()
+    where = {int(k): j for j, k in enumerate(t["obs_step"])}
+    checked = 0
+    for row, i in enumerate(idx):
+        # oracle on every row; golden on the rows the fixture holds observations for
+        m_o, po_o, fo_o = orc.current_obs(states[i + 1], int(t["players"][i + 1]), 3)
+        assert np.array_equal(_bits(po[row]), _bits(po_o)), (version, i)
+        assert np.array_equal(_bits(fo[row]), _bits(fo_o)), (version, i)
+        assert np.array_equal(mask[row], m_o.reshape(-1))
+        j = where.get(int(i) + 1)
+        if j is not None:
+            assert np.array_equal(_bits(po[row]), _bits(t["po"][j]))
+            assert np.array_equal(_bits(fo[row]), _bits(t["fo"][j]))
+            checked += 1
+    assert checked > 0
+
+
+@pytest.mark.parametrize("version", ["barrage", "standard", "micro", "octa_barrage", "standard2", "fives"])
+def test_observe_both_players(version):
+    """sx_observe (maenv:447-497) for the mover and for the waiting player, incl. terminal states"""
+    t = traj(version)
+    eng, orc = _engine(version), _oracle(version)
+    states = t["states"].astype(np.int64)
+    n = len(states)
+    st = eng.import_ref_state(_t(states, torch.int64), _t(t["players"], torch.int8))
+    for sign in (1, -1):
+        viewer = (t["players"].astype(np.int64) * sign).astype(np.int8)
+        out = eng.observe(st, _t(viewer, torch.int8))
+        torch.cuda.synchronize()
+        mask, po, fo = (out[k].cpu().numpy() for k in ("valid_mask", "partial_obs", "full_obs"))
+        assert np.array_equal(out["player"].cpu().numpy(), viewer)
+        for i in range(0, n, 3):
+            m_o, po_o, fo_o = orc.current_obs(states[i], int(viewer[i]), 3)
+            assert np.array_equal(mask[i], m_o), (version, i, sign)
+            assert np.array_equal(_bits(po[i]), _bits(po_o)), (version, i, sign)
+            assert np.array_equal(_bits(fo[i]), _bits(fo_o)), (version, i, sign)
+    if "term_step" in t:
+        for j, code in enumerate(t["term_step"]):
+            k, p = int(code) // 2, (1 if int(code) % 2 == 0 else -1)
+            out = eng.observe(st.select(k, k + 1), _t([p], torch.int8))
+            assert np.array_equal(_bits(out["partial_obs"].cpu().numpy()[0]), _bits(t["term_po"][j]))
+            assert np.array_equal(_bits(out["full_obs"].cpu().numpy()[0]), _bits(t["term_fo"][j]))
+
+
+@pytest.mark.parametrize("tag,version", [("10x10", "barrage"), ("3x4", "micro"), ("4x4", "tiny")])
+def test_known_answer_cases(tag, version):
+    """hand-built boards: combat table, scout rules, two-square rule, stuck/flag/max-turn endings, illegal moves"""
+    k = known()
+    eng = _engine(version)
+    R, C, A = eng.spatial_action_size
+    names = k["ka_%s_names" % tag]
+    states = k["ka_%s_states" % tag].astype(np.int64)
+    players, actions = k["ka_%s_players" % tag], k["ka_%s_actions" % tag]
+    allow, ok = k["ka_%s_allow" % tag], k["ka_%s_ok" % tag]
+    for flag in (False, True):
+        sel = np.flatnonzero(allow == flag)
+        if len(sel) == 0:
+            continue
+        st = eng.import_ref_state(_t(states[sel], torch.int64), _t(players[sel], torch.int8))
+        out = eng.step(st, _t(actions[sel], torch.int32), one_d=True, allow_piece_oscillation=flag)
+        dense, player = eng.export_ref_state(st)
+        sp = eng.valid_mask(st)
+        d1 = eng.valid_mask(st, one_d=True)
+        torch.cuda.synchronize()
+        illegal = out["illegal"].cpu().numpy().astype(bool)
+        bad = [str(names[s]) for s, a, b in zip(sel, illegal, ~ok[sel]) if a != b]
+        assert not bad, bad
+        assert np.array_equal(dense.cpu().numpy(), k["ka_%s_next" % tag][sel].astype(np.int64))
+        expect_player = np.where(ok[sel], -players[sel], players[sel])
+        assert np.array_equal(player.cpu().numpy(), expect_player)
+        assert np.array_equal(sp.cpu().numpy().reshape(len(sel), -1),
+                              unpack_mask(k["ka_%s_next_spatial_mask_bits" % tag][sel], R * C * A))
+        assert np.array_equal(d1.cpu().numpy(), unpack_mask(k["ka_%s_next_1d_mask_bits" % tag][sel], eng.action_size))
+        inval = k["ka_%s_next_invalid" % tag][sel]
+        assert np.array_equal(out["ending_invalid"].cpu().numpy().astype(bool), inval & ok[sel])
+
+
+@pytest.mark.parametrize("version", ["barrage", "standard", "micro", "standard2"])
+def test_import_export_roundtrip(version):
+    t = traj(version)
+    eng = _engine(version)
+    states = t["states"].astype(np.int64)
+    st = eng.import_ref_state(_t(states, torch.int64), _t(t["players"], torch.int8))
+    dense, player = eng.export_ref_state(st)
+    assert np.array_equal(dense.cpu().numpy(), states)
+    assert np.array_equal(player.cpu().numpy(), t["players"])
+
+
+def test_import_rejects_unrepresentable_state():
+    eng = _engine("barrage")
+    t = traj("barrage")
+    bad = t["states"][:2].astype(np.int64).copy()
+    bad[1, 3, 0, 0] = 5 if bad[1, 0, 0, 0] != 5 else 6  # PO rank that is neither UNKNOWN nor the true rank
+    with pytest.raises(ValueError):
+        eng.import_ref_state(_t(bad, torch.int64))
+
+
+@pytest.mark.parametrize("tag", ["barrage", "standard"])
+def test_reset_from_setup_table_matches_reference(tag):
+    """sx_reset with explicit table rows == the reference's create_game_from_data (util:278-298)"""
+    from stratego_env_b200.engine import load_setup_table
+    k = known()
+    eng = _engine(tag, p2_rot180=False)
+    table = load_setup_table(tag)
+    assert table.shape[0] == int(k["setup_%s_count" % tag])
+    pairs = k["setup_%s_pairs" % tag]
+    st = eng.alloc_state(len(pairs))
+    eng.reset(st, setups=eng.upload_setups(table), setup_idx=_t(pairs, torch.int32))
+    dense, player = eng.export_ref_state(st)
+    assert np.array_equal(dense.cpu().numpy(), k["setup_%s_states" % tag].astype(np.int64))
+    assert (player == 1).all().item()
