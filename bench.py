@@ -1,0 +1,399 @@
+#!/usr/bin/env python
+"""Benchmark of the hot path: env-steps/s of the fused step (mask + step + obs + auto-reset).
+
+    python bench.py --gpus N --steps K --warmup W [--workload barrage|micro|standard|standard_both]
+    python bench.py --impl reference ...      # the CPU restatement of the reference on the host cores
+
+One "step" = one pass of the fused kernel over every game of the batch: each game applies one
+uniformly sampled valid action, is re-set if it ended, and emits the next player's spatial
+valid-action mask and partial observation.  Prints ONE JSON line on rank 0.
+
+  value      device-resident throughput: actions, state and outputs live in HBM; CUDA events on the
+             launching stream; max over ranks.
+  e2e        the same step through the C ABI's host-buffer object (sx_host_env_step): actions come from
+             pinned HOST memory and every output (obs, mask, reward, done, ...) is copied back to pinned
+             HOST memory inside the timed region.
+  roofline   algorithmic bytes per launch / measured launch duration vs the measured HBM peak.
+  cpu_baseline  oracle/ (C restatement of the reference, test infrastructure) timed on the host cores.
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import statistics
+import subprocess
+import sys
+import tempfile
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+# workload name -> (version, table, envs per GPU, partial, full, mean game length for de-phasing)
+WORKLOADS = {
+    "barrage": dict(version="barrage", table="barrage", envs=262144, full=False, dephase=1200,
+                    desc="Barrage 10x10, 256k envs/GPU, random-valid self-play, auto-reset from the 3944-row human "
+                         "setup table, PO obs f32[B,10,10,67] + spatial mask u8[B,10,10,37] every step"),
+    "micro": dict(version="micro", table=None, envs=1048576, full=False, dephase=100,
+                  desc="Micro 3x4, 1M envs/GPU, random-valid self-play, auto-reset with shuffled setups, PO obs + mask"),
+    "standard": dict(version="standard", table="standard", envs=524288, full=False, dephase=3000,
+                     desc="Standard 10x10 (40 pieces/side), 512k envs/GPU, human setup table, PO obs + mask"),
+    "standard_both": dict(version="standard", table="standard", envs=262144, full=True, dephase=3000,
+                          desc="Standard 10x10, 256k envs/GPU, PO + full obs + mask"),
+}
+METRIC = "env_steps_per_sec"
+UNIT = "env-steps/s"
+
+
+def algorithmic_bytes_per_step(cells, channels_a, pieces, full):
+    """obs f32 + mask u8 + 2 x minimal state + 13 bytes of per-env scalars."""
+    obs = cells * 67 * 4 + (cells * 79 * 4 if full else 0)
+    state = cells + 4 * pieces + 16
+    return obs + cells * channels_a + 2 * state + 13
+
+
+def measured_peak():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs, copy read+write)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def recorded_traffic(workload):
+    """dram bytes per launch of the fused kernel from the committed ncu --set full capture, if any"""
+    path = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            return json.load(f).get(workload)
+    return None
+
+
+class ClockSampler:
+    FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+              "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.file = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        self.proc = None
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(gpu_index), "--query-gpu=" + self.FIELDS,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=self.file, stderr=subprocess.DEVNULL)
+        except OSError:
+            self.proc = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        if self.proc is None:
+            return out
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        self.file.flush()
+        self.file.seek(0)
+        sm, reasons, mx, power = [], set(), None, []
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in self.file.read().splitlines():
+            p = [x.strip() for x in line.split(",")]
+            if len(p) < 7:
+                continue
+            try:
+                sm.append(float(p[0]))
+                mx = float(p[1])
+                power.append(float(p[2]))
+            except ValueError:
+                continue
+            for name, v in zip(names, p[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        self.file.close()
+        os.unlink(self.file.name)
+        if sm:
+            out.update(sm_mhz=statistics.median(sm), sm_max_mhz=mx, reasons=sorted(reasons), samples=len(sm),
+                       power_w_max=max(power) if power else None)
+        return out
+
+
+def physical_gpu_index(local_rank):
+    vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+    if vis:
+        ids = [v.strip() for v in vis.split(",") if v.strip()]
+        if local_rank < len(ids) and ids[local_rank].isdigit():
+            return int(ids[local_rank])
+    return local_rank
+
+
+# ---------------------------------------------------------------------------------------------------------
+# CPU legs (oracle/ = the checker; allowed here only as the reported CPU baseline / reference arm)
+# ---------------------------------------------------------------------------------------------------------
+def cpu_selfplay(workload, budget_s, threads=None):
+    """Random-valid self-play of the C restatement of the reference on `threads` host threads; one
+    independent env per work item, same loop as examples/basic_game_loop.py:34-63."""
+    from oracle import binding
+    from stratego_env_b200.config import VERSION_CONFIGS, as_version, obstacle_map
+    from stratego_env_b200.engine import load_setup_table
+    w = WORKLOADS[workload]
+    cfg = VERSION_CONFIGS[as_version(w["version"])]
+    table = load_setup_table(w["table"]) if w["table"] else None
+    threads = threads or os.cpu_count() or 1
+    obs_mode = 3 if w["full"] else 1
+
+    def run(n_envs, steps_per_env):
+        t0 = time.perf_counter()
+        steps, games, _ = binding.selfplay(cfg["rows"], cfg["columns"], cfg["max_turns"],
+                                           cfg["initial_state_usable_rows"], cfg["piece_amounts"], obstacle_map(cfg),
+                                           table, table is None, obs_mode, n_envs, steps_per_env, seed=1234,
+                                           n_threads=threads)
+        return steps, games, time.perf_counter() - t0
+
+    steps, _, dt = run(threads * 2, 500)  # calibration (also warms caches)
+    rate = steps / dt
+    per_env = 2000
+    n_envs = max(threads * 2, int(rate * budget_s / per_env))
+    n_envs = (n_envs + threads - 1) // threads * threads
+    steps, games, dt = run(n_envs, per_env)
+    return {"value": steps / dt, "unit": UNIT, "cores": threads, "kind": "port",
+            "sample": "%d independent envs x %d steps (%d games) of the same workload, %.1f s wall, oracle/ C "
+                      "restatement of the reference (the reference itself is Python+numba and cannot travel to "
+                      "the GPU box)" % (n_envs, per_env, games, dt),
+            "seconds": dt, "steps": steps}
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    w = WORKLOADS[args.workload]
+    per_step_budget = max(1.0, min(20.0, 120.0 / max(1, args.steps + args.warmup)))
+    for _ in range(args.warmup):
+        cpu_selfplay(args.workload, per_step_budget)
+    total_steps, total_s, last = 0, 0.0, None
+    for _ in range(args.steps):
+        last = cpu_selfplay(args.workload, per_step_budget)
+        total_steps += last["steps"]
+        total_s += last["seconds"]
+    value = total_steps / total_s
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * total_s / max(1, args.steps), "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+        "config": {"workload": args.workload, "description": w["desc"]},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": last["cores"], "kind": "port", "sample": last["sample"]},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+    return 0
+
+
+# ---------------------------------------------------------------------------------------------------------
+# GPU arm
+# ---------------------------------------------------------------------------------------------------------
+def run_e2e(torch, eng, w, B, env_base, seed, steps, warmup, full):
+    """sx_host_env: pinned host actions in, every output copied back to pinned host memory, per step."""
+    from stratego_env_b200 import _lib
+    from stratego_env_b200.engine import load_setup_table
+    lib = eng.lib
+    lay = eng.layout
+    table = load_setup_table(w["table"]) if w["table"] else None
+    flags = _lib.SX_AUTO_RESET | _lib.SX_SAMPLE_NEXT | (_lib.SX_RESET_RANDOM_SHUFFLE if table is None else 0)
+    obs_mask = _lib.OBS_PO | _lib.OBS_MASK | (_lib.OBS_FO if full else 0)
+    handle = C.c_void_p()
+    _lib.check(lib.sx_host_env_create(eng._cfg, B, env_base, obs_mask, flags,
+                                      table.ctypes.data if table is not None else None,
+                                      0 if table is None else table.shape[0], seed, 16, C.byref(handle)),
+               "sx_host_env_create")
+    R, Cc, A = eng.spatial_action_size
+
+    def pinned(shape, dtype):
+        return torch.empty(shape, dtype=dtype, pin_memory=True)
+
+    host = {
+        "partial_obs": pinned((B, R, Cc, 67), torch.float32),
+        "valid_mask": pinned((B, R, Cc, A), torch.uint8),
+        "reward": pinned((B,), torch.float32), "done": pinned((B,), torch.uint8),
+        "winner": pinned((B,), torch.int8), "ending_invalid": pinned((B,), torch.uint8),
+        "illegal": pinned((B,), torch.uint8), "player": pinned((B,), torch.int8),
+        "next_action": pinned((B,), torch.int32),
+    }
+    if full:
+        host["full_obs"] = pinned((B, R, Cc, 79), torch.float32)
+    out = _lib.SxOutputs()
+    for k, t in host.items():
+        setattr(out, k, t.data_ptr())
+    actions = pinned((B,), torch.int32)
+    try:
+        _lib.check(lib.sx_host_env_reset(handle, out), "sx_host_env_reset")
+        t_steps = []
+        for i in range(warmup + steps):
+            actions.copy_(host["next_action"])  # the host-side "policy": play the sampled valid action
+            t0 = time.perf_counter()
+            _lib.check(lib.sx_host_env_step(handle, actions.data_ptr(), out), "sx_host_env_step")  # syncs
+            t1 = time.perf_counter()
+            if i >= warmup:
+                t_steps.append(t1 - t0)
+        assert int(host["illegal"].sum()) == 0, "sampled actions must be legal"
+    finally:
+        lib.sx_host_env_destroy(handle)
+    d2h = sum(t.numel() * t.element_size() for t in host.values())
+    return sum(t_steps), d2h, B * 4, lay
+
+
+def run_gpu_arm(args):
+    import torch
+    import torch.distributed as dist
+    from stratego_env_b200.config import VERSION_CONFIGS, as_version
+    from stratego_env_b200.engine import StrategoEngine, load_setup_table
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the engine has no CPU fallback (use --impl reference for the "
+                         "CPU baseline)")
+    torch.cuda.set_device(local_rank)
+    device = torch.device("cuda", local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=device)
+
+    w = WORKLOADS[args.workload]
+    B = args.envs or w["envs"]
+    full = w["full"]
+    cfg = VERSION_CONFIGS[as_version(w["version"])]
+    eng = StrategoEngine(cfg, device=device, p2_rot180=w["table"] is None)
+    setups = eng.upload_setups(load_setup_table(w["table"])) if w["table"] else None
+    shuffle = setups is None
+    env_base = rank * B  # games shard by env index; Philox streams are keyed by the global env id
+    seed = args.seed
+
+    st = eng.alloc_state(B)
+    eng.reset(st, seed=seed, env_base=env_base, setups=setups, shuffle=shuffle)
+    out = eng.alloc_outputs(B, partial=True, full=full, mask=True, sample=True)
+    eng.observe(st, out=out)
+    actions = eng.sample_valid(out["valid_mask"], seed=seed, step=0, env_base=env_base)
+    stats = torch.zeros(8, dtype=torch.int64, device=device)
+
+    def step(outputs):
+        nonlocal actions
+        eng.step_all(st, actions, outputs, env_base=env_base, auto_reset=True, sample_next=True, setups=setups,
+                     shuffle=shuffle, seed=seed, stats=stats)
+        actions, outputs["next_action"] = outputs["next_action"], actions
+
+    # de-phase the games (steady-state mix of early/mid/late positions) without rendering
+    lean = eng.alloc_outputs(B, partial=False, full=False, mask=False, sample=True)
+    lean["next_action"] = out["next_action"]
+    for _ in range(args.dephase if args.dephase is not None else w["dephase"]):
+        step(lean)
+    out["next_action"] = lean["next_action"]
+    for _ in range(args.warmup):
+        step(out)
+    stats.zero_()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    sampler = ClockSampler(physical_gpu_index(local_rank)) if rank == 0 else None
+    events = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
+    barrier()
+    events[0].record()
+    for i in range(args.steps):
+        step(out)
+        events[i + 1].record()
+    barrier()
+    clocks = sampler.stop() if sampler else None
+    launch_ms = [events[i].elapsed_time(events[i + 1]) for i in range(args.steps)]
+    total_ms = events[0].elapsed_time(events[-1])
+    illegal = int(out["illegal"].sum().item())
+    assert illegal == 0, "sampled actions must be legal"
+    if world > 1:
+        t = torch.tensor([total_ms], dtype=torch.float64, device=device)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        total_ms = float(t.item())
+        dist.all_reduce(stats, op=dist.ReduceOp.SUM)  # the only collective: end-of-run statistics
+    value = world * B * args.steps / (total_ms * 1e-3)
+
+    # ---- end to end through host buffers ----------------------------------------------------------------
+    e2e = None
+    if not args.no_e2e:
+        del lean
+        e2e_steps = max(1, min(args.steps, args.e2e_steps))
+        e2e_B = args.e2e_envs or B
+        secs, d2h, h2d, _ = run_e2e(torch, eng, w, e2e_B, rank * e2e_B, seed, e2e_steps, max(1, min(args.warmup, 3)),
+                                    full)
+        t = torch.tensor([secs], dtype=torch.float64, device=device)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e = {"value": world * e2e_B * e2e_steps / float(t.item()), "unit": UNIT,
+               "h2d_bytes_per_step": h2d * world, "d2h_bytes_per_step": d2h * world, "steps": e2e_steps,
+               "envs_per_gpu": e2e_B,
+               "what": "sx_host_env_step: int32 actions from pinned host memory, every output (obs, mask, reward, "
+                       "done, winner, flags, sampled action) copied back to pinned host memory, 16 pipelined chunks"}
+
+    if rank == 0:
+        lay = eng.layout
+        bytes_step = algorithmic_bytes_per_step(lay.cells, lay.spatial_channels, lay.pieces_per_side, full)
+        peak, peak_src = measured_peak()
+        kernel_ms = statistics.mean(launch_ms)
+        achieved = B * bytes_step / (kernel_ms * 1e-3) / 1e9
+        info = eng.launch_info(partial=True, full=full, mask=True)
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "u8", "data": "synthetic",
+            "config": {"workload": args.workload, "description": w["desc"], "envs_per_gpu": B,
+                       "global_envs": B * world, "sharding": "env index, no data-path collective",
+                       "l2": "outputs per step (%.1f GB) exceed the 126 MB L2; no flush needed" %
+                             (B * bytes_step / 1e9),
+                       "dephase_steps": args.dephase if args.dephase is not None else w["dephase"]},
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": recorded_traffic(args.workload), "peak_source": peak_src,
+                         "kernel": "sx_fused_kernel", "algorithmic_bytes_per_env_step": bytes_step,
+                         "kernel_ms": kernel_ms, "launch": info},
+            "e2e": e2e,
+            "gpu_launches": args.steps,
+            "clocks": clocks,
+            "games_finished": int(stats[0].item()),
+        }
+        if world == 1 and not args.no_cpu:
+            line["cpu_baseline"] = {k: v for k, v in cpu_selfplay(args.workload, args.cpu_seconds).items()
+                                    if k not in ("seconds", "steps")}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="barrage", choices=sorted(WORKLOADS))
+    ap.add_argument("--envs", type=int, default=None, help="envs per GPU (default: the workload's)")
+    ap.add_argument("--dephase", type=int, default=None, help="untimed render-free steps before the warm-up")
+    ap.add_argument("--seed", type=int, default=20261017)
+    ap.add_argument("--e2e-steps", type=int, default=8)
+    ap.add_argument("--e2e-envs", type=int, default=None)
+    ap.add_argument("--cpu-seconds", type=float, default=12.0)
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+    if args.warmup < 3 and args.impl == "b200":
+        args.warmup = 3  # timing rules: at least 3 warm-up steps
+    if args.impl == "reference":
+        return run_reference_arm(args)
+    return run_gpu_arm(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -100,14 +100,36 @@ enum : uint32_t { RNG_RESET = 0x52535430u, RNG_SAMPLE = 0x53414d50u, RNG_SHUFFLE
 
 // ---- this warp's slice of shared memory -----------------------------------------------------------
 struct WarpMem {
-    float *po;         // [N*67] partial-observation tile (background + patches)
-    float *fo;         // [N*79] full-observation tile
-    uint8_t *mask;     // [mask_bytes + 16] spatial mask tile; the live tile starts at mask + moff
     uint8_t *board;    // [board_stride]
     uint16_t *cap;     // [cap_stride]
     uint32_t *lines;   // [64] occupancy bit-lines: any[0..15 rows | 16..31 cols], enemy[32 + same]
-    uint16_t *reach;   // [N] per-cell packed reach (4 x 4 bit), consumed by the action sampler
+    uint16_t *reach;   // [N] per-cell packed reach (4 x 4 bit): the move list of the player the outputs are for
     uint8_t *scratch;  // [>= 2 * setup_len] shuffle workspace
+};
+
+// One output tile of the block's tile pool: the images of one game's outputs exactly as they go to
+// global memory.  Between uses a tile holds the "empty board" background (observations) / zeros (mask).
+struct Tile {
+    float *po;      // [N*67] partial observation
+    float *fo;      // [N*79] full observation
+    uint8_t *mask;  // [mask_bytes + 16] spatial mask; the live image starts at mask + (global address & 15)
+};
+
+// row/column of the K consecutive cells a lane owns, computed once per warp (no divisions in the game loop)
+template <int K>
+struct LaneCells {
+    int8_t r[K], c[K];
+    __device__ __forceinline__ void init(const DevConfig &cfg)
+    {
+#pragma unroll
+        for (int k = 0; k < K; ++k) {
+            const int p = lane_id_() * K + k;
+            const int rr = p / cfg.C;
+            r[k] = int8_t(rr);
+            c[k] = int8_t(p - rr * cfg.C);
+        }
+    }
+    static __device__ __forceinline__ int lane_id_() { return threadIdx.x & 31; }
 };
 
 __device__ __forceinline__ int lane_id() { return threadIdx.x & 31; }
@@ -222,49 +244,34 @@ __device__ __forceinline__ Blocked blocked_move(const DevConfig &cfg, const Warp
 }
 
 // ---- valid-move generation (impl:400-517 / impl:522-642) -------------------------------------------
-struct MarkNone {
-    __device__ __forceinline__ void operator()(int, int, int, int) const {}
-};
-// spatial mask tile in shared memory: [cell][channel], channel = dir base + dist - 1 (impl:292-311)
-struct MarkSpatialSmem {
-    uint8_t *tile;
-    int A, R, C;
-    __device__ __forceinline__ void operator()(int cell, int dir, int dist, int /*target*/) const
-    {
-        const int base = dir == 0 ? 0 : dir == 1 ? (R - 1) : dir == 2 ? 2 * (R - 1) : 2 * (R - 1) + (C - 1);
-        tile[cell * A + base + dist - 1] = 1;
-    }
-};
-// 1D mask straight to global memory, absolute frame (impl:264-277); facade use only
-struct Mark1DGlobal {
-    uint8_t *out;
-    int N, R, C, flip;
-    __device__ __forceinline__ void operator()(int cell, int dir, int /*dist*/, int target) const
-    {
-        const int s = flip ? N - 1 - cell : cell, e = flip ? N - 1 - target : target;
-        const int er = e / C, ec = e - er * C;
-        out[s * (R + C) + (dir < 2 ? er : R + ec)] = 1;
-    }
-};
-
-// Enumerates the moves of player index `me`, in `me`'s frame.  Returns (warp-uniform) whether any
-// move exists.  When `reach_out` is set, stores each cell's four ray lengths for the sampler.
-template <int K, typename Mark>
-__device__ __forceinline__ bool gen_moves(const DevConfig &cfg, const WarpMem &m, const Aux &a, int me, bool allow_osc,
-                                          const Mark &mark, bool reach_out)
+// Move generation produces, per cell, how far the piece on it can travel in each of the four directions
+// ("reach", 4 x 4 bit in m.reach).  The spatial mask image, the 1D mask and the uniform sampler are all
+// expansions of that list; the one move the two-square rule forbids (Blocked) is skipped on expansion.
+__device__ __forceinline__ int dir_base(const DevConfig &cfg, int dir)  // first channel of a direction, impl:292-311
 {
+    return dir == 0 ? 0 : dir == 1 ? (cfg.R - 1) : dir == 2 ? 2 * (cfg.R - 1) : 2 * (cfg.R - 1) + (cfg.C - 1);
+}
+
+// Enumerates the moves of player index `me`, in `me`'s frame, into m.reach.  Returns (warp-uniform)
+// whether any move exists.
+template <int K>
+__device__ __forceinline__ bool gen_moves(const DevConfig &cfg, const WarpMem &m, const Aux &a, int me, bool allow_osc,
+                                          const LaneCells<K> &lc, Blocked &blk)
+{
+    blk = Blocked{-1, 0, 0};
+    const int lane = lane_id();
     if (a.over) {  // impl:414
-        if (reach_out)
-            for (int k = 0; k < K; ++k) {
-                const int p = lane_id() * K + k;
-                if (p < cfg.N) m.reach[p] = 0;
-            }
+#pragma unroll
+        for (int k = 0; k < K; ++k) {
+            const int p = lane * K + k;
+            if (p < cfg.N) m.reach[p] = 0;
+        }
+        __syncwarp();
         return false;
     }
     const int flip = me;  // player -1 sees the board rotated
     build_lines(cfg, m, me, flip);
-    const Blocked blk = blocked_move(cfg, m, a, me, flip, allow_osc);
-    const int lane = lane_id();
+    blk = blocked_move(cfg, m, a, me, flip, allow_osc);
     int found = 0;
 #pragma unroll
     for (int k = 0; k < K; ++k) {
@@ -274,7 +281,7 @@ __device__ __forceinline__ bool gen_moves(const DevConfig &cfg, const WarpMem &m
             const uint32_t b = m.board[view(p, flip, cfg.N)];
             const int rank = b & CELL_RANK;
             if (rank != 0 && rank <= SP_MARSHAL && int((b >> 4) & 1) == me) {  // impl:420
-                const int r = p / cfg.C, c = p - r * cfg.C;
+                const int r = lc.r[k], c = lc.c[k];
                 const uint32_t col_any = m.lines[16 + c], col_en = m.lines[48 + c];
                 const uint32_t row_any = m.lines[r], row_en = m.lines[32 + r];
                 int reach[4];
@@ -282,22 +289,72 @@ __device__ __forceinline__ bool gen_moves(const DevConfig &cfg, const WarpMem &m
                 reach[1] = ray_down(col_any, col_en, r);
                 reach[2] = ray_up(row_any, row_en, c, cfg.C);
                 reach[3] = ray_down(row_any, row_en, c);
-                const int step[4] = {cfg.C, -cfg.C, 1, -1};
+                int total = 0;
 #pragma unroll
                 for (int d = 0; d < 4; ++d) {
                     if (rank != SP_SCOUT && reach[d] > 1) reach[d] = 1;  // impl:492-499
                     packed |= uint32_t(reach[d]) << (4 * d);
-                    for (int t = 1; t <= reach[d]; ++t) {
-                        if (p == blk.cell && d == blk.dir && t == blk.dist) continue;
-                        mark(p, d, t, p + step[d] * t);
-                        found = 1;
-                    }
+                    total += reach[d];
                 }
+                if (p == blk.cell && int((packed >> (4 * blk.dir)) & 15) >= blk.dist) total -= 1;  // impl:439-445
+                found |= total > 0;
             }
-            if (reach_out) m.reach[p] = uint16_t(packed);
+            m.reach[p] = uint16_t(packed);
         }
     }
+    __syncwarp();
     return __any_sync(FULL, found);
+}
+
+// Expands m.reach into a spatial mask image [cell][channel] (impl:292-311): writes `val` at every move.
+template <int K>
+__device__ __forceinline__ void mark_spatial(const DevConfig &cfg, const WarpMem &m, const Blocked &blk, uint8_t *image,
+                                             uint8_t val)
+{
+    const int lane = lane_id();
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+        const int p = lane * K + k;
+        if (p < cfg.N) {
+            uint32_t packed = m.reach[p];
+            uint8_t *cell = image + p * cfg.A;
+#pragma unroll
+            for (int d = 0; d < 4; ++d) {
+                const int n = packed & 15;
+                packed >>= 4;
+                uint8_t *ch = cell + dir_base(cfg, d) - 1;
+                for (int t = 1; t <= n; ++t)
+                    if (!(p == blk.cell && d == blk.dir && t == blk.dist)) ch[t] = val;
+            }
+        }
+    }
+}
+
+// Expands m.reach into a 1D mask row in global memory, absolute frame (impl:264-277); facade use only.
+template <int K>
+__device__ __forceinline__ void mark_1d_global(const DevConfig &cfg, const WarpMem &m, const Blocked &blk,
+                                               const LaneCells<K> &lc, int flip, uint8_t *row)
+{
+    const int lane = lane_id();
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+        const int p = lane * K + k;
+        if (p < cfg.N) {
+            const uint32_t packed = m.reach[p];
+            const int r = lc.r[k], c = lc.c[k];
+            const int s = view(p, flip, cfg.N);
+            for (int d = 0; d < 4; ++d) {
+                const int n = (packed >> (4 * d)) & 15;
+                for (int t = 1; t <= n; ++t) {
+                    if (p == blk.cell && d == blk.dir && t == blk.dist) continue;
+                    int er = r, ec = c;  // target in `me`'s frame
+                    if (d == 0) er += t; else if (d == 1) er -= t; else if (d == 2) ec += t; else ec -= t;
+                    if (flip) { er = cfg.R - 1 - er; ec = cfg.C - 1 - ec; }
+                    row[s * cfg.mpa + (d < 2 ? er : cfg.R + ec)] = 1;
+                }
+            }
+        }
+    }
 }
 
 // ---- action decode ----------------------------------------------------------------------------------
