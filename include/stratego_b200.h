@@ -154,6 +154,7 @@ int sx_sample_valid(const uint8_t *mask_d, int64_t num_envs, int32_t mask_len, i
 /* Kernel/launch facts for the benchmark's roofline accounting. */
 typedef struct {
     int32_t warps_per_block, blocks_per_sm, smem_bytes_per_block, num_sms, grid_blocks, regs_per_thread;
+    int32_t background_bytes; /* shared-memory background images of a block (DESIGN.md "Rendering") */
 } sx_launch_info;
 int sx_step_all_launch_info(const sx_config *cfg, uint32_t obs_mask /*1 po, 2 fo, 4 mask*/, sx_launch_info *out);
 

@@ -31,6 +31,7 @@ struct DevConfig {
     int R, C, N, A, mpa, action_size;
     int board_stride, cap_stride;  // bytes / uint16 entries per env
     int max_turns, usable_rows, setup_len, n_pieces, p2_rot180;
+    uint32_t magic_C, magic_A, magic_mpa;  // floor(2^32 / d) + 1: x / d == __umulhi(x, magic) for x * d < 2^32
     int po_floats, fo_floats, mask_bytes;
     float cap_lut[12 * 9];
     float recent_lut[5];
@@ -107,12 +108,31 @@ struct WarpMem {
     uint8_t *scratch;  // [>= 2 * setup_len] shuffle workspace
 };
 
-// One output tile of the block's tile pool: the images of one game's outputs exactly as they go to
-// global memory.  Between uses a tile holds the "empty board" background (observations) / zeros (mask).
+__host__ __device__ inline int round16(int v) { return (v + 15) & ~15; }
+
+// shared-memory slice of one warp; host and device must agree on this layout
+__host__ __device__ inline int carve_warp(const DevConfig &cfg, uint8_t *base, WarpMem *m)
+{
+    int off = 0;
+    if (m) m->board = base + off;
+    off += cfg.board_stride;
+    if (m) m->cap = reinterpret_cast<uint16_t *>(base + off);
+    off += round16(cfg.cap_stride * 2);
+    if (m) m->lines = reinterpret_cast<uint32_t *>(base + off);
+    off += 256;
+    if (m) m->reach = reinterpret_cast<uint16_t *>(base + off);
+    off += round16(cfg.N * 2);
+    if (m) m->scratch = base + off;
+    off += round16(2 * cfg.setup_len);
+    return off;
+}
+
+// The block's read-only background images: what a game's outputs look like before the state-dependent
+// entries are added ("empty board" observation after normalisation; all-zero mask).
 struct Tile {
     float *po;      // [N*67] partial observation
     float *fo;      // [N*79] full observation
-    uint8_t *mask;  // [mask_bytes + 16] spatial mask; the live image starts at mask + (global address & 15)
+    uint8_t *mask;  // [mask_bytes + 16] zeros; copies start at mask + (global address & 15)
 };
 
 // row/column of the K consecutive cells a lane owns, computed once per warp (no divisions in the game loop)
@@ -124,7 +144,7 @@ struct LaneCells {
 #pragma unroll
         for (int k = 0; k < K; ++k) {
             const int p = lane_id_() * K + k;
-            const int rr = p / cfg.C;
+            const int rr = int(__umulhi(uint32_t(p), cfg.magic_C));
             r[k] = int8_t(rr);
             c[k] = int8_t(p - rr * cfg.C);
         }
@@ -133,6 +153,7 @@ struct LaneCells {
 };
 
 __device__ __forceinline__ int lane_id() { return threadIdx.x & 31; }
+__device__ __forceinline__ int fast_div(int x, uint32_t magic) { return int(__umulhi(uint32_t(x), magic)); }
 
 // flat cell index in `me`'s frame <-> absolute frame: a 180-degree rotation is index reversal
 __device__ __forceinline__ int view(int cell, int flip, int N) { return flip ? N - 1 - cell : cell; }
@@ -153,7 +174,7 @@ __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.a
 // 16-byte aligned body goes out as one TMA bulk copy issued by lane 0 (caller commits/waits) and the
 // <16-byte head and tail as plain word stores; otherwise (odd-sized variants such as 5x5 and 15x15,
 // whose per-env byte counts are not multiples of 16) the tile is copied with plain stores.
-__device__ __forceinline__ void emit_tile(uint8_t *gdst, const uint8_t *ssrc, int bytes)
+__device__ __noinline__ void emit_tile(uint8_t *gdst, const uint8_t *ssrc, int bytes)
 {
     const int lane = lane_id();
     const uintptr_t g = reinterpret_cast<uintptr_t>(gdst);
@@ -227,6 +248,17 @@ struct Blocked {
     int cell, dir, dist;  // in `me`'s frame; cell < 0 = nothing blocked
 };
 
+__device__ __forceinline__ uint32_t pack_blocked(const Blocked &b)
+{
+    return b.cell < 0 ? 0xffffu : (uint32_t(b.cell) | (uint32_t(b.dir) << 8) | (uint32_t(b.dist) << 10));
+}
+__device__ __forceinline__ Blocked unpack_blocked(uint32_t v)
+{
+    v &= 0xffffu;
+    if (v == 0xffffu) return Blocked{-1, 0, 0};
+    return Blocked{int(v & 0xff), int((v >> 8) & 3), int((v >> 10) & 15)};
+}
+
 __device__ __forceinline__ Blocked blocked_move(const DevConfig &cfg, const WarpMem &m, const Aux &a, int me, int flip,
                                                 bool allow_osc)
 {
@@ -234,7 +266,7 @@ __device__ __forceinline__ Blocked blocked_move(const DevConfig &cfg, const Warp
     if (allow_osc || a.rcode[me] != 3 || a.rto[me] == NO_CELL || a.rfrom[me] == NO_CELL) return b;
     if ((m.board[a.rfrom[me]] & CELL_RANK) != 0) return b;  // an enemy stepped onto it: attacking is allowed
     const int s = view(a.rto[me], flip, cfg.N), e = view(a.rfrom[me], flip, cfg.N);
-    const int sr = s / cfg.C, sc = s - sr * cfg.C, er = e / cfg.C, ec = e - er * cfg.C;
+    const int sr = fast_div(s, cfg.magic_C), sc = s - sr * cfg.C, er = fast_div(e, cfg.magic_C), ec = e - er * cfg.C;
     if (sr != er && sc != ec) return b;
     if (s == e) return b;
     b.cell = s;
@@ -306,10 +338,10 @@ __device__ __forceinline__ bool gen_moves(const DevConfig &cfg, const WarpMem &m
     return __any_sync(FULL, found);
 }
 
-// Expands m.reach into a spatial mask image [cell][channel] (impl:292-311): writes `val` at every move.
+// Expands m.reach into the spatial mask [cell][channel] (impl:292-311): stores a 1 at every move on top of
+// the zero background at `image` (global memory).
 template <int K>
-__device__ __forceinline__ void mark_spatial(const DevConfig &cfg, const WarpMem &m, const Blocked &blk, uint8_t *image,
-                                             uint8_t val)
+__device__ __forceinline__ void mark_spatial(const DevConfig &cfg, const WarpMem &m, const Blocked &blk, uint8_t *image)
 {
     const int lane = lane_id();
 #pragma unroll
@@ -318,13 +350,13 @@ __device__ __forceinline__ void mark_spatial(const DevConfig &cfg, const WarpMem
         if (p < cfg.N) {
             uint32_t packed = m.reach[p];
             uint8_t *cell = image + p * cfg.A;
-#pragma unroll
-            for (int d = 0; d < 4; ++d) {
+#pragma unroll 1
+            for (int d = 0; packed != 0; ++d, packed >>= 4) {
                 const int n = packed & 15;
-                packed >>= 4;
                 uint8_t *ch = cell + dir_base(cfg, d) - 1;
+#pragma unroll 1
                 for (int t = 1; t <= n; ++t)
-                    if (!(p == blk.cell && d == blk.dir && t == blk.dist)) ch[t] = val;
+                    if (!(p == blk.cell && d == blk.dir && t == blk.dist)) ch[t] = 1;
             }
         }
     }
@@ -332,7 +364,7 @@ __device__ __forceinline__ void mark_spatial(const DevConfig &cfg, const WarpMem
 
 // Expands m.reach into a 1D mask row in global memory, absolute frame (impl:264-277); facade use only.
 template <int K>
-__device__ __forceinline__ void mark_1d_global(const DevConfig &cfg, const WarpMem &m, const Blocked &blk,
+__device__ __noinline__ void mark_1d_global(const DevConfig &cfg, const WarpMem &m, const Blocked &blk,
                                                const LaneCells<K> &lc, int flip, uint8_t *row)
 {
     const int lane = lane_id();
@@ -359,7 +391,8 @@ __device__ __forceinline__ void mark_1d_global(const DevConfig &cfg, const WarpM
 
 // ---- action decode ----------------------------------------------------------------------------------
 struct Move {
-    int start, end;  // absolute cells
+    int start, end;      // absolute cells
+    int sr, sc, er, ec;  // their absolute rows / columns
     bool noop, bad;
 };
 
@@ -368,10 +401,10 @@ struct Move {
 // zero-length or out-of-range 1D index), so it is rejected here as well.
 __device__ __forceinline__ Move decode_spatial(const DevConfig &cfg, int action, int flip)
 {
-    Move mv{0, 0, false, true};
+    Move mv{0, 0, 0, 0, 0, 0, false, true};
     if (action < 0 || action >= cfg.N * cfg.A) return mv;
-    const int cell = action / cfg.A, ch = action - cell * cfg.A;
-    const int r = cell / cfg.C, c = cell - r * cfg.C;
+    const int cell = fast_div(action, cfg.magic_A), ch = action - cell * cfg.A;
+    const int r = fast_div(cell, cfg.magic_C), c = cell - r * cfg.C;
     const int mr = cfg.R - 1, mc = cfg.C - 1;
     int er = r, ec = c;
     if (ch < mr) er = r + ch + 1;
@@ -380,8 +413,12 @@ __device__ __forceinline__ Move decode_spatial(const DevConfig &cfg, int action,
     else if (ch < 2 * mr + 2 * mc) ec = c - (ch - 2 * mr - mc + 1);
     else return mv;
     if (er < 0 || er >= cfg.R || ec < 0 || ec >= cfg.C) return mv;
-    mv.start = view(cell, flip, cfg.N);
-    mv.end = view(er * cfg.C + ec, flip, cfg.N);
+    mv.sr = flip ? cfg.R - 1 - r : r;
+    mv.sc = flip ? cfg.C - 1 - c : c;
+    mv.er = flip ? cfg.R - 1 - er : er;
+    mv.ec = flip ? cfg.C - 1 - ec : ec;
+    mv.start = mv.sr * cfg.C + mv.sc;
+    mv.end = mv.er * cfg.C + mv.ec;
     mv.bad = false;
     return mv;
 }
@@ -389,12 +426,13 @@ __device__ __forceinline__ Move decode_spatial(const DevConfig &cfg, int action,
 // absolute 1D index (impl:352-383); the last index is the noop
 __device__ __forceinline__ Move decode_1d(const DevConfig &cfg, int action)
 {
-    Move mv{0, 0, false, true};
+    Move mv{0, 0, 0, 0, 0, 0, false, true};
     if (action == cfg.action_size - 1) { mv.noop = true; mv.bad = false; return mv; }
     if (action < 0 || action >= cfg.action_size) return mv;
-    const int cell = action / cfg.mpa, off = action - cell * cfg.mpa;
-    const int r = cell / cfg.C, c = cell - r * cfg.C;
+    const int cell = fast_div(action, cfg.magic_mpa), off = action - cell * cfg.mpa;
+    const int r = fast_div(cell, cfg.magic_C), c = cell - r * cfg.C;
     const int er = off >= cfg.R ? r : off, ec = off >= cfg.R ? off - cfg.R : c;
+    mv.sr = r; mv.sc = c; mv.er = er; mv.ec = ec;
     mv.start = cell;
     mv.end = er * cfg.C + ec;
     mv.bad = false;
@@ -414,7 +452,7 @@ __device__ __forceinline__ bool move_is_legal(const DevConfig &cfg, const WarpMe
     if (rank == 0 || rank > SP_MARSHAL || int((sb >> 4) & 1) != me) return false;
     if (eb & CELL_OBST) return false;
     if ((eb & CELL_RANK) != 0 && int((eb >> 4) & 1) == me) return false;
-    const int sr = mv.start / cfg.C, sc = mv.start - sr * cfg.C, er = mv.end / cfg.C, ec = mv.end - er * cfg.C;
+    const int sr = mv.sr, sc = mv.sc, er = mv.er, ec = mv.ec;
     if ((sr != er) == (sc != ec)) return false;  // diagonal or zero-length
     if (!allow_osc && a.rcode[me] == 3 && a.rto[me] == mv.start && a.rfrom[me] == mv.end && (eb & CELL_RANK) == 0)
         return false;  // impl:771-777
@@ -431,7 +469,7 @@ __device__ __forceinline__ bool move_is_legal(const DevConfig &cfg, const WarpMe
 }
 
 // records one captured piece (impl:999-1009) in the capture list; lanes search entries in parallel
-__device__ __forceinline__ void add_capture(const DevConfig &cfg, const WarpMem &m, Aux &a, int cell, int owner, int type)
+__device__ __forceinline__ void add_capture_inl(const DevConfig &cfg, const WarpMem &m, Aux &a, int cell, int owner, int type)
 {
     const uint32_t key = cap_key(cell, owner, type);
     const int lane = lane_id();
@@ -448,6 +486,18 @@ __device__ __forceinline__ void add_capture(const DevConfig &cfg, const WarpMem 
     __syncwarp();
 }
 
+// Out-of-line entry (attacks are 2-4 % of moves): arguments and result by value so that the caller's
+// Aux stays in registers.
+__device__ __noinline__ int add_capture(const DevConfig *cfg, uint16_t *cap, int ncap, int cell, int owner, int type)
+{
+    WarpMem m{};
+    m.cap = cap;
+    Aux a{};
+    a.ncap = ncap;
+    add_capture_inl(*cfg, m, a, cell, owner, type);
+    return a.ncap;
+}
+
 // impl:897-1028: applies a decoded move for the player to move.  The opponent-stuck and max-turn
 // checks (impl:1031-1043) need the next player's move list and are done by the caller.
 __device__ __forceinline__ StepStatus apply_move(const DevConfig &cfg, const WarpMem &m, Aux &a, const Move &mv,
@@ -458,8 +508,8 @@ __device__ __forceinline__ StepStatus apply_move(const DevConfig &cfg, const War
     if (mv.noop) {  // impl:809-814: a noop is legal only when nothing else is
         if (mv.bad) return STEP_ILLEGAL;
         if (a.over) { a.to_move ^= 1; return STEP_UNCHANGED; }  // impl:907-909
-        // K is not known here; the caller pre-computes `has_moves` for noops via gen_moves and passes
-        // mv.bad = true when moves exist, so reaching this point means the player is stuck.
+        // the caller runs gen_moves for a noop first and passes mv.bad = true when moves exist, so
+        // reaching this point means the player is stuck.
         a.turn += 1;  // impl:912-920
         a.over = 1;
         a.winner = -player;
@@ -470,7 +520,7 @@ __device__ __forceinline__ StepStatus apply_move(const DevConfig &cfg, const War
 
     const uint32_t sb = m.board[mv.start], eb = m.board[mv.end];
     const int rank = sb & CELL_RANK, defender = eb & CELL_RANK;
-    const int sr = mv.start / cfg.C, er = mv.end / cfg.C;
+    const int sr = mv.sr, er = mv.er;
     const int dist = sr != er ? (er > sr ? er - sr : sr - er)
                               : (mv.end > mv.start ? mv.end - mv.start : mv.start - mv.end);
     a.turn += 1;
@@ -493,8 +543,8 @@ __device__ __forceinline__ StepStatus apply_move(const DevConfig &cfg, const War
     if (lane_id() == 0) { m.board[mv.start] = uint8_t(new_start); m.board[mv.end] = uint8_t(new_end); }
     __syncwarp();
     if (defender != 0) {  // impl:999-1009
-        if (!wins) add_capture(cfg, m, a, mv.end, me, rank);
-        if (wins || tie) add_capture(cfg, m, a, mv.end, me ^ 1, defender);
+        if (!wins) a.ncap = add_capture(&cfg, m.cap, a.ncap, mv.end, me, rank);
+        if (wins || tie) a.ncap = add_capture(&cfg, m.cap, a.ncap, mv.end, me ^ 1, defender);
     }
     // impl:1013-1028: the mover's recent-move record is rebuilt from scratch
     if (defender == 0) {
@@ -560,8 +610,8 @@ struct ResetSource {
     bool shuffle;
 };
 
-__device__ __forceinline__ void reset_game(const DevConfig &cfg, const WarpMem &m, Aux &a, const ResetSource &src,
-                                           uint2 key, uint64_t gid)
+__device__ __forceinline__ void reset_game_inl(const DevConfig &cfg, const WarpMem &m, Aux &a, const ResetSource &src,
+                                               uint2 key, uint64_t gid)
 {
     const int lane = lane_id();
     __syncwarp();
@@ -598,6 +648,21 @@ __device__ __forceinline__ void reset_game(const DevConfig &cfg, const WarpMem &
     a.episode = episode + 1;
 }
 
+// Out-of-line entry: re-sets the game staged in the warp slice at `warp_base`, returns the packed aux words.
+__device__ __noinline__ uint4 reset_game(const DevConfig *cfg, uint8_t *warp_base, const uint8_t *setups, int n_setups,
+                                         const int32_t *setup_idx, int shuffle, uint2 key, uint64_t gid, uint32_t episode)
+{
+    WarpMem m;
+    carve_warp(*cfg, warp_base, &m);
+    Aux a{};
+    a.episode = episode;
+    const ResetSource src{setups, n_setups, setup_idx, shuffle != 0};
+    reset_game_inl(*cfg, m, a, src, key, gid);
+    uint32_t w[4];
+    aux_pack(a, w);
+    return make_uint4(w[0], w[1], w[2], w[3]);
+}
+
 // ---- observation tiles (impl:1232-1397 + maenv:499-508) ---------------------------------------------
 // Channel map of the partial (impl:1306-1332) and full (impl:1200-1227) observations.
 struct ObsMap {
@@ -608,10 +673,11 @@ __device__ __forceinline__ ObsMap po_map() { return ObsMap{67, 0, -1, 12, 25, 38
 __device__ __forceinline__ ObsMap fo_map() { return ObsMap{79, 0, 12, 24, 37, 50, 51, 52, 53, 65, 77, 78}; }
 
 // fills a tile with what an empty board looks like after normalisation
-__device__ __forceinline__ void fill_background(const DevConfig &cfg, float *tile, const ObsMap om)
+__device__ __noinline__ void fill_background(const DevConfig &cfg, float *tile, const ObsMap om, int first, int stride)
 {
     const int total = cfg.N * om.channels;
-    for (int i = lane_id(); i < total; i += 32) {
+#pragma unroll 1
+    for (int i = first; i < total; i += stride) {
         const int ch = i % om.channels;
         float v = cfg.unit_lut[0];
         if (ch == om.own_recent || ch == om.enemy_recent) v = cfg.recent_lut[3];
@@ -621,13 +687,15 @@ __device__ __forceinline__ void fill_background(const DevConfig &cfg, float *til
     }
 }
 
-// Writes (SET) or removes (!SET) the sparse, state-dependent entries of a tile for observer `me`.
-template <int K, bool SET>
+// Writes the sparse, state-dependent entries of observer `me`'s observation on top of the background
+// image at `tile` (global memory).
+template <int K>
 __device__ __forceinline__ void patch_obs(const DevConfig &cfg, const WarpMem &m, const Aux &a, float *tile,
                                           const ObsMap om, int me)
 {
+    constexpr bool SET = true;
     const int lane = lane_id(), flip = me, CH = om.channels;
-    const float one = SET ? cfg.unit_lut[1] : cfg.unit_lut[0];
+    const float one = cfg.unit_lut[1];
 #pragma unroll
     for (int k = 0; k < K; ++k) {
         const int p = lane * K + k;
@@ -669,24 +737,20 @@ __device__ __forceinline__ void patch_obs(const DevConfig &cfg, const WarpMem &m
 // ---- uniform draw over the generated moves (replaces maenv:830-834) ----------------------------------
 // Order = ascending flat spatial index (cell, then channel), which is the generation order.
 template <int K>
-__device__ __forceinline__ int sample_move(const DevConfig &cfg, const WarpMem &m, const Aux &a, int me, bool allow_osc,
-                                           bool any_moves, uint32_t rnd)
+__device__ __forceinline__ int sample_move(const DevConfig &cfg, const WarpMem &m, const Blocked &blk, bool any_moves,
+                                           uint32_t rnd)
 {
     if (!any_moves) return cfg.A - 1;  // the noop entry [0,0,A-1]
     const int lane = lane_id();
-    const Blocked blk = blocked_move(cfg, m, a, me, me, allow_osc);
-    int cnt[K], mine = 0;
+    int mine = 0;
 #pragma unroll
     for (int k = 0; k < K; ++k) {
         const int p = lane * K + k;
-        int c = 0;
         if (p < cfg.N) {
             const uint32_t packed = m.reach[p];
-            c = int(packed & 15) + int((packed >> 4) & 15) + int((packed >> 8) & 15) + int((packed >> 12) & 15);
-            if (p == blk.cell && int((packed >> (4 * blk.dir)) & 15) >= blk.dist) c -= 1;
+            mine += int(packed & 15) + int((packed >> 4) & 15) + int((packed >> 8) & 15) + int((packed >> 12) & 15);
+            if (p == blk.cell && int((packed >> (4 * blk.dir)) & 15) >= blk.dist) mine -= 1;
         }
-        cnt[k] = c;
-        mine += c;
     }
     int incl = mine;
 #pragma unroll
@@ -699,29 +763,25 @@ __device__ __forceinline__ int sample_move(const DevConfig &cfg, const WarpMem &
     int action = 0;
     const bool owner = t >= incl - mine && t < incl;
     if (owner) {
-        t -= incl - mine;
-#pragma unroll
-        for (int k = 0; k < K; ++k) {
-            if (t >= 0 && t < cnt[k]) {
-                const int p = lane * K + k;
-                const uint32_t packed = m.reach[p];
-                const int base[4] = {0, cfg.R - 1, 2 * (cfg.R - 1), 2 * (cfg.R - 1) + (cfg.C - 1)};
-                int left = t;
-                for (int d = 0; d < 4; ++d) {
-                    const int reach = (packed >> (4 * d)) & 15;
-                    const bool skip = p == blk.cell && d == blk.dir && reach >= blk.dist;
-                    const int n = reach - (skip ? 1 : 0);
-                    if (left < n) {
-                        int dist = left + 1;
-                        if (skip && dist >= blk.dist) dist += 1;
-                        action = p * cfg.A + base[d] + dist - 1;
-                        break;
-                    }
-                    left -= n;
+        int left = t - (incl - mine);
+        bool found = false;
+#pragma unroll 1
+        for (int k = 0; k < K && !found; ++k) {
+            const int p = lane * K + k;
+            uint32_t packed = p < cfg.N ? uint32_t(m.reach[p]) : 0u;
+#pragma unroll 1
+            for (int d = 0; packed != 0; ++d, packed >>= 4) {
+                const int reach = packed & 15;
+                const bool skip = p == blk.cell && d == blk.dir && reach >= blk.dist;
+                const int n = reach - (skip ? 1 : 0);
+                if (left < n) {
+                    int dist = left + 1;
+                    if (skip && dist >= blk.dist) dist += 1;
+                    action = p * cfg.A + dir_base(cfg, d) + dist - 1;
+                    found = true;
+                    break;
                 }
-                t = -1;
-            } else if (t >= 0) {
-                t -= cnt[k];
+                left -= n;
             }
         }
     }

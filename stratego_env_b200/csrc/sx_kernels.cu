@@ -9,6 +9,7 @@
 
 #include <algorithm>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 #include <string>
@@ -48,68 +49,111 @@ struct KernelArgs {
     const uint8_t *reset_mask;
     uint2 key;
     long long *stats;
-    int warp_bytes;
+    int warp_bytes;  // shared-memory slice of one warp (game state + scratch)
+    int tile_bytes;  // the block's background images (0 = this launch renders nothing)
 };
 
-__host__ __device__ inline int round16(int v) { return (v + 15) & ~15; }
-
-// shared-memory slice of one warp; host and device must agree on this layout
-__host__ __device__ inline int carve(const DevConfig &cfg, uint32_t ops, uint8_t *base, WarpMem *m)
+// the block's background images: [partial obs][full obs][mask zeros + 16 bytes of alignment slack]
+__host__ __device__ inline int carve_tile(const DevConfig &cfg, uint32_t ops, uint8_t *base, Tile *t)
 {
     int off = 0;
-    const int po = (ops & OP_PO) ? round16(cfg.po_floats * 4) : 0;
-    const int fo = (ops & OP_FO) ? round16(cfg.fo_floats * 4) : 0;
-    const int mask = (ops & OP_MASK) ? round16(cfg.mask_bytes + 16) : 0;
-    if (m) m->po = reinterpret_cast<float *>(base + off);
-    off += po;
-    if (m) m->fo = reinterpret_cast<float *>(base + off);
-    off += fo;
-    if (m) m->mask = base + off;
-    off += mask;
-    if (m) m->board = base + off;
-    off += cfg.board_stride;
-    if (m) m->cap = reinterpret_cast<uint16_t *>(base + off);
-    off += round16(cfg.cap_stride * 2);
-    if (m) m->lines = reinterpret_cast<uint32_t *>(base + off);
-    off += 256;
-    if (m) m->reach = reinterpret_cast<uint16_t *>(base + off);
-    off += round16(cfg.N * 2);
-    if (m) m->scratch = base + off;
-    off += round16(2 * cfg.setup_len);
+    if (t) t->po = reinterpret_cast<float *>(base + off);
+    off += (ops & OP_PO) ? round16(cfg.po_floats * 4) : 0;
+    if (t) t->fo = reinterpret_cast<float *>(base + off);
+    off += (ops & OP_FO) ? round16(cfg.fo_floats * 4) : 0;
+    if (t) t->mask = base + off;
+    off += (ops & OP_MASK) ? round16(cfg.mask_bytes + 16) : 0;
     return off;
 }
 
-__device__ __forceinline__ void zero_bytes16(uint8_t *p, int bytes)
+// ---- output rendering ---------------------------------------------------------------------------------
+// A game's observation is a per-variant constant "empty board" image (zeros in the one-hot planes, -1.0
+// in the captured planes, 0.5 in the recent-move planes) plus 50-250 state-dependent entries, and its mask
+// is zeros plus ~15-25 ones.  Each block keeps ONE read-only copy of those images in shared memory.  Per
+// game, lane 0 hands the images to the TMA engine (cp.async.bulk shared -> global: ~30 KB of output for
+// three instructions) at the top of the iteration, the warp runs the rule logic while the copy drains,
+// and the sparse entries are then stored straight to global memory, where they merge with the freshly
+// written lines in L2.  No warp owns a 30 KB tile, so shared memory no longer limits residency.
+// Arguments and result by value (bit 31 = any move, low 16 bits = packed Blocked) so that the caller's
+// state stays in registers.
+template <int K>
+__device__ __noinline__ uint32_t gen_moves_cold(const DevConfig *cfg, uint8_t *warp_base, uint4 auxw, int me)
 {
-    const uint4 z = make_uint4(0, 0, 0, 0);
-    for (int i = lane_id(); i < (bytes >> 4); i += 32) reinterpret_cast<uint4 *>(p)[i] = z;
+    WarpMem m;
+    carve_warp(*cfg, warp_base, &m);
+    const uint32_t w[4] = {auxw.x, auxw.y, auxw.z, auxw.w};
+    Aux a;
+    aux_unpack(w, a);
+    LaneCells<K> lc;
+    lc.init(*cfg);
+    Blocked blk;
+    const bool any = gen_moves<K>(*cfg, m, a, me, false, lc, blk);
+    return (any ? 0x80000000u : 0u) | pack_blocked(blk);
 }
 
-template <int K>
-__global__ void __launch_bounds__(512) sx_fused_kernel(const __grid_constant__ KernelArgs args)
+// MODE fixes the op set at compile time so that each hot launch type carries only its own code (the
+// whole fused body is ~290 KB of SASS when everything is runtime-selected, far beyond the I-cache):
+enum { MODE_GENERIC = 0, MODE_STEP_PO_MASK = 1, MODE_STEP_PO_FO_MASK = 2, MODE_STEP_LEAN = 3 };
+constexpr uint32_t OPS_STEP_BASE = OP_STEP | OP_WRITE_STATE | OP_NEED_MOVES;
+
+__host__ __device__ constexpr uint32_t mode_ops(int mode)
+{
+    return mode == MODE_STEP_PO_MASK ? (OPS_STEP_BASE | OP_PO | OP_MASK)
+         : mode == MODE_STEP_PO_FO_MASK ? (OPS_STEP_BASE | OP_PO | OP_FO | OP_MASK)
+         : mode == MODE_STEP_LEAN ? OPS_STEP_BASE : 0u;
+}
+
+template <int K, int MODE>
+__global__ void __launch_bounds__(512, 1) sx_fused_kernel(const __grid_constant__ KernelArgs args)
 {
     extern __shared__ __align__(16) uint8_t smem[];
     const DevConfig &cfg = args.cfg;
     const int lane = lane_id(), warp = threadIdx.x >> 5, warps_per_block = blockDim.x >> 5;
-    const uint32_t ops = args.ops, flags = args.flags;
+    const uint32_t ops = MODE == MODE_GENERIC ? args.ops : mode_ops(MODE), flags = args.flags;
+    const int8_t *player_override = MODE == MODE_GENERIC ? args.player_override : nullptr;
+    uint8_t *warp_base = smem + args.tile_bytes + size_t(warp) * args.warp_bytes;
     WarpMem m;
-    carve(cfg, ops, smem + size_t(warp) * args.warp_bytes, &m);
+    carve_warp(cfg, warp_base, &m);
 
     const bool do_step = ops & OP_STEP, do_mask = ops & OP_MASK, do_po = ops & OP_PO, do_fo = ops & OP_FO;
+    const bool do_tile = do_mask || do_po || do_fo;
     const bool do_sample = (flags & SX_SAMPLE_NEXT) && args.out.next_action != nullptr;
     const bool allow_osc = flags & SX_ALLOW_OSCILLATION;
+    const bool need_moves = do_mask || do_sample || (ops & (OP_MASK_1D | OP_NEED_MOVES));
     const int mask_tile_bytes = round16(cfg.mask_bytes + 16);
     const ObsMap pom = po_map(), fom = fo_map();
+    LaneCells<K> lc;
+    lc.init(cfg);
 
-    if (do_po) fill_background(cfg, m.po, pom);
-    if (do_fo) fill_background(cfg, m.fo, fom);
-    if (do_mask) zero_bytes16(m.mask, mask_tile_bytes);
-    __syncwarp();
+    // the block's read-only background images
+    Tile bg;
+    carve_tile(cfg, ops, smem, &bg);
+    if (do_tile) {
+        if (do_po) fill_background(cfg, bg.po, pom, threadIdx.x, blockDim.x);
+        if (do_fo) fill_background(cfg, bg.fo, fom, threadIdx.x, blockDim.x);
+        if (do_mask)
+            for (int i = threadIdx.x; i < (mask_tile_bytes >> 4); i += blockDim.x)
+                reinterpret_cast<uint4 *>(bg.mask)[i] = make_uint4(0, 0, 0, 0);
+        fence_async_smem();  // generic-proxy writes above -> visible to the TMA engine (async proxy)
+    }
+    __syncthreads();
 
     long long n_games = 0, n_p1 = 0, n_p2 = 0, n_invalid = 0, n_illegal = 0;
     const long long total_warps = (long long)gridDim.x * warps_per_block;
     for (long long env = (long long)blockIdx.x * warps_per_block + warp; env < args.num_envs; env += total_warps) {
         const uint64_t gid = uint64_t(args.env_base + env);
+        // ---- start the background copies of this game's outputs; they drain while the rules run ------
+        if (do_tile) {
+            if (do_po) emit_tile(reinterpret_cast<uint8_t *>(args.out.partial_obs + env * cfg.po_floats),
+                                 reinterpret_cast<const uint8_t *>(bg.po), cfg.po_floats * 4);
+            if (do_fo) emit_tile(reinterpret_cast<uint8_t *>(args.out.full_obs + env * cfg.fo_floats),
+                                 reinterpret_cast<const uint8_t *>(bg.fo), cfg.fo_floats * 4);
+            if (do_mask) {
+                uint8_t *gmask = args.out.valid_mask + env * cfg.mask_bytes;
+                emit_tile(gmask, bg.mask + (reinterpret_cast<uintptr_t>(gmask) & 15), cfg.mask_bytes);
+            }
+            if (lane == 0) bulk_commit();
+        }
         // ---- stage the compact state in shared memory ------------------------------------------
         {
             const uint32_t *gb = reinterpret_cast<const uint32_t *>(args.board + env * cfg.board_stride);
@@ -126,49 +170,57 @@ __global__ void __launch_bounds__(512) sx_fused_kernel(const __grid_constant__ K
         __syncwarp();
 
         bool dirty = false;
-        ResetSource src{args.setups, args.n_setups, args.setup_idx ? args.setup_idx + env * 2 : nullptr,
-                        (flags & SX_RESET_RANDOM_SHUFFLE) != 0};
-        if ((ops & OP_RESET) && (args.reset_mask == nullptr || args.reset_mask[env] != 0)) {
-            reset_game(cfg, m, a, src, args.key, gid);
+        // out-of-line helpers take and return everything by value so that `a` never has to live in local memory
+        auto do_reset = [&]() {
+            __syncwarp();
+            const uint4 nw = reset_game(&cfg, warp_base, args.setups, args.n_setups,
+                                        args.setup_idx ? args.setup_idx + env * 2 : nullptr,
+                                        (flags & SX_RESET_RANDOM_SHUFFLE) != 0, args.key, gid, a.episode);
+            const uint32_t w[4] = {nw.x, nw.y, nw.z, nw.w};
+            aux_unpack(w, a);
+        };
+        auto regen_moves = [&](int me, Blocked &b) -> bool {
+            uint32_t w[4];
+            aux_pack(a, w);
+            __syncwarp();
+            const uint32_t r = gen_moves_cold<K>(&cfg, warp_base, make_uint4(w[0], w[1], w[2], w[3]), me);
+            b = unpack_blocked(r);
+            return (r >> 31) != 0;
+        };
+        if (MODE == MODE_GENERIC && (ops & OP_RESET) && (args.reset_mask == nullptr || args.reset_mask[env] != 0)) {
+            do_reset();
             dirty = true;
         }
 
         // ---- step: decode, validate, apply (impl:897-1028) ----------------------------------------
         StepStatus status = STEP_UNCHANGED;
         const int mover = a.to_move;
+        Blocked blk{-1, 0, 0};
         if (do_step) {
             const int action = args.actions[env];
             Move mv = args.action_format == SX_ACTION_SPATIAL ? decode_spatial(cfg, action, mover) : decode_1d(cfg, action);
             if (mv.noop && !mv.bad && !a.over) {  // impl:809-814
-                if (gen_moves<K>(cfg, m, a, mover, false, MarkNone{}, false)) mv.bad = true;
+                if (regen_moves(mover, blk)) mv.bad = true;
             }
             int attack;
             status = apply_move(cfg, m, a, mv, allow_osc, attack);
             dirty |= status != STEP_ILLEGAL;
         }
 
-        // ---- moves of the player the outputs are for ---------------------------------------------
+        // ---- move list of the player the outputs are for -------------------------------------------
         int viewer = a.to_move;
-        if (args.player_override) viewer = args.player_override[env] == 1 ? 0 : 1;
-        const int moff = do_mask ? int(reinterpret_cast<uintptr_t>(args.out.valid_mask + env * cfg.mask_bytes) & 15) : 0;
-        bool any = false, have_moves = false;
-        if (do_mask) {
-            any = gen_moves<K>(cfg, m, a, viewer, false, MarkSpatialSmem{m.mask + moff, cfg.A, cfg.R, cfg.C}, do_sample);
-            have_moves = true;
-        } else if ((ops & OP_MASK_1D) != 0) {
-            uint8_t *row = args.mask1d + env * cfg.action_size;
-            any = gen_moves<K>(cfg, m, a, viewer, false, Mark1DGlobal{row, cfg.N, cfg.R, cfg.C, viewer}, false);
-            if (!any && lane == 0) row[cfg.action_size - 1] = 1;  // impl:639-640
-            have_moves = true;
-        } else if ((ops & OP_NEED_MOVES) != 0 && (status == STEP_MOVED || !do_step)) {
-            any = gen_moves<K>(cfg, m, a, viewer, false, MarkNone{}, do_sample);
-            have_moves = true;
-        }
+        if (player_override) viewer = player_override[env] == 1 ? 0 : 1;
+        bool any = false;
+        const bool have_moves = need_moves && (status == STEP_MOVED || !do_step || do_mask || do_sample || (ops & OP_MASK_1D));
+        if (have_moves) any = gen_moves<K>(cfg, m, a, viewer, false, lc, blk);
 
-        bool timeout = false;
         if (status == STEP_MOVED) {
             if (have_moves && !any && !a.over) { a.over = 1; a.winner = mover == 0 ? 1 : -1; }  // impl:1031-1036
-            if (a.turn >= a.max_turns && !a.over) { a.over = 1; a.invalid = 1; timeout = true; }  // impl:1040-1043
+            if (a.turn >= a.max_turns && !a.over) {  // impl:1040-1043
+                a.over = 1;
+                a.invalid = 1;
+                if (have_moves && any) any = regen_moves(viewer, blk);  // terminal: noop only
+            }
         }
         const bool done = do_step && status != STEP_ILLEGAL && a.over;
         if (do_step) {
@@ -190,41 +242,17 @@ __global__ void __launch_bounds__(512) sx_fused_kernel(const __grid_constant__ K
         }
 
         if (done && (flags & SX_AUTO_RESET)) {
-            reset_game(cfg, m, a, src, args.key, gid);
+            do_reset();
             viewer = a.to_move;
-            if (do_mask) {
-                zero_bytes16(m.mask, mask_tile_bytes);
-                __syncwarp();
-                any = gen_moves<K>(cfg, m, a, viewer, false, MarkSpatialSmem{m.mask + moff, cfg.A, cfg.R, cfg.C}, do_sample);
-            } else if (do_sample) {
-                any = gen_moves<K>(cfg, m, a, viewer, false, MarkNone{}, true);
-            }
-        } else if (timeout && do_mask && any) {
-            // the game ended on the turn limit after its mask was generated: terminal masks are noop-only
-            __syncwarp();
-            zero_bytes16(m.mask, mask_tile_bytes);
-            any = false;
-            if (do_sample)
-                for (int k = 0; k < K; ++k)
-                    if (lane * K + k < cfg.N) m.reach[lane * K + k] = 0;
-            __syncwarp();
-        }
-        if (do_mask && !any && lane == 0) m.mask[moff + cfg.A - 1] = 1;  // [0,0,A-1], impl:514-515
-
-        // ---- render + emit -----------------------------------------------------------------------
-        if (do_po) patch_obs<K, true>(cfg, m, a, m.po, pom, viewer);
-        if (do_fo) patch_obs<K, true>(cfg, m, a, m.fo, fom, viewer);
-        if (do_po || do_fo || do_mask) {
-            fence_async_smem();  // make this thread's generic-proxy writes visible to the async proxy
-            __syncwarp();
-            if (do_po) emit_tile(reinterpret_cast<uint8_t *>(args.out.partial_obs + env * cfg.po_floats),
-                                 reinterpret_cast<const uint8_t *>(m.po), cfg.po_floats * 4);
-            if (do_fo) emit_tile(reinterpret_cast<uint8_t *>(args.out.full_obs + env * cfg.fo_floats),
-                                 reinterpret_cast<const uint8_t *>(m.fo), cfg.fo_floats * 4);
-            if (do_mask) emit_tile(args.out.valid_mask + env * cfg.mask_bytes, m.mask + moff, cfg.mask_bytes);
-            if (lane == 0) bulk_commit();
+            if (need_moves) any = regen_moves(viewer, blk);
         }
         if (args.out.player && lane == 0) args.out.player[env] = viewer == 0 ? 1 : -1;
+
+        if ((ops & OP_MASK_1D) != 0) {
+            uint8_t *row = args.mask1d + env * cfg.action_size;
+            mark_1d_global<K>(cfg, m, blk, lc, viewer, row);
+            if (!any && lane == 0) row[cfg.action_size - 1] = 1;  // impl:639-640
+        }
 
         if ((ops & OP_WRITE_STATE) && dirty) {
             uint32_t *gb = reinterpret_cast<uint32_t *>(args.board + env * cfg.board_stride);
@@ -240,22 +268,25 @@ __global__ void __launch_bounds__(512) sx_fused_kernel(const __grid_constant__ K
 
         if (do_sample) {
             const uint4 rnd = philox4x32_10(make_uint4(uint32_t(gid), uint32_t(gid >> 32), RNG_SAMPLE ^ uint32_t(a.turn), a.episode), args.key);
-            const int act = sample_move<K>(cfg, m, a, viewer, false, any, rnd.x);
+            const int act = sample_move<K>(cfg, m, blk, any, rnd.x);
             if (lane == 0) args.out.next_action[env] = act;
         }
 
-        // ---- restore the tiles once the TMA engine has read them ------------------------------------
-        if (do_po || do_fo || do_mask) {
-            if (lane == 0) bulk_wait_read();
+        // ---- render: sparse entries on top of the (by now written) background ---------------------------
+        if (do_tile) {
+            if (lane == 0) bulk_wait_all();  // this game's background is in global memory
             __syncwarp();
-            if (do_po) patch_obs<K, false>(cfg, m, a, m.po, pom, viewer);
-            if (do_fo) patch_obs<K, false>(cfg, m, a, m.fo, fom, viewer);
-            if (do_mask) zero_bytes16(m.mask, mask_tile_bytes);
+            if (do_po) patch_obs<K>(cfg, m, a, args.out.partial_obs + env * cfg.po_floats, pom, viewer);
+            if (do_fo) patch_obs<K>(cfg, m, a, args.out.full_obs + env * cfg.fo_floats, fom, viewer);
+            if (do_mask) {
+                uint8_t *gmask = args.out.valid_mask + env * cfg.mask_bytes;
+                mark_spatial<K>(cfg, m, blk, gmask);
+                if (!any && lane == 0) gmask[cfg.A - 1] = 1;  // [0,0,A-1], impl:514-515
+            }
         }
         __syncwarp();
     }
 
-    if ((do_po || do_fo || do_mask) && lane == 0) bulk_wait_all();  // global writes of the last tiles
     if (args.stats) {
         if (lane == 0) {  // all lanes carry identical counters; lane 0 publishes
             if (n_games) atomicAdd(reinterpret_cast<unsigned long long *>(args.stats + 0), (unsigned long long)n_games);
@@ -470,6 +501,9 @@ extern "C" int sx_config_create(const sx_config_desc *desc, sx_config **out)
     d.R = desc->rows; d.C = desc->cols; d.N = d.R * d.C;
     d.A = 2 * (d.R - 1) + 2 * (d.C - 1) + 1;
     d.mpa = d.R + d.C;
+    d.magic_C = uint32_t((1ull << 32) / uint64_t(d.C)) + 1u;
+    d.magic_A = uint32_t((1ull << 32) / uint64_t(d.A)) + 1u;
+    d.magic_mpa = uint32_t((1ull << 32) / uint64_t(d.mpa)) + 1u;
     d.action_size = d.N * d.mpa + 1;
     d.board_stride = (d.N + 15) & ~15;
     d.max_turns = desc->max_turns;
@@ -514,56 +548,83 @@ extern "C" int sx_config_layout(const sx_config *cfg, sx_layout *out)
 }
 
 typedef void (*fused_fn)(const KernelArgs);
-static fused_fn fused_for(int k)
+template <int K>
+static fused_fn fused_for_mode(int mode)
+{
+    switch (mode) {
+    case MODE_STEP_PO_MASK: return sx_fused_kernel<K, MODE_STEP_PO_MASK>;
+    case MODE_STEP_PO_FO_MASK: return sx_fused_kernel<K, MODE_STEP_PO_FO_MASK>;
+    case MODE_STEP_LEAN: return sx_fused_kernel<K, MODE_STEP_LEAN>;
+    default: return sx_fused_kernel<K, MODE_GENERIC>;
+    }
+}
+static fused_fn fused_for(int k, int mode)
 {
     switch (k) {
-    case 1: return sx_fused_kernel<1>;
-    case 2: return sx_fused_kernel<2>;
-    case 4: return sx_fused_kernel<4>;
-    default: return sx_fused_kernel<8>;
+    case 1: return fused_for_mode<1>(mode);
+    case 2: return fused_for_mode<2>(mode);
+    case 4: return fused_for_mode<4>(mode);
+    default: return fused_for_mode<8>(mode);
     }
+}
+
+// the specialised kernel for this launch, if one matches exactly
+static int mode_for(const KernelArgs &a)
+{
+    if (a.player_override || a.reset_mask || a.setup_idx || a.mask1d) return MODE_GENERIC;
+    for (int mode : {MODE_STEP_PO_MASK, MODE_STEP_PO_FO_MASK, MODE_STEP_LEAN})
+        if (a.ops == mode_ops(mode)) return mode;
+    return MODE_GENERIC;
 }
 
 struct LaunchPlan {
     int warps_per_block, blocks_per_sm, smem_per_block, num_sms, grid, regs;
+    int warp_bytes, tile_bytes;
 };
 
-// picks the block shape that maximises resident warps per SM for this variant's shared-memory slice
-static int plan_launch(const sx_config *cfg, uint32_t ops, long long num_envs, LaunchPlan *plan, int *warp_bytes_out)
+static int env_int(const char *name, int fallback)
 {
-    const int warp_bytes = carve(cfg->dev, ops, nullptr, nullptr);
-    fused_fn fn = fused_for(cfg->cells_per_lane);
+    const char *v = std::getenv(name);
+    return (v && *v) ? std::atoi(v) : fallback;
+}
+
+// Block shape: one block per SM with as many warps as the register file allows (SX_WARPS overrides; a
+// tuning aid); the block's shared memory is the background images plus one small slice per warp.
+static int plan_launch(const sx_config *cfg, uint32_t ops, int mode, long long num_envs, LaunchPlan *plan)
+{
+    const int warp_bytes = carve_warp(cfg->dev, nullptr, nullptr);
+    const int tile_bytes = carve_tile(cfg->dev, ops, nullptr, nullptr);
+    fused_fn fn = fused_for(cfg->cells_per_lane, mode);
     int device = 0;
     cudaError_t e = cudaGetDevice(&device);
     if (e != cudaSuccess) return cuda_fail("cudaGetDevice", e);
     int num_sms = 0, max_smem_optin = 0;
     cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, device);
     cudaDeviceGetAttribute(&max_smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device);
-    if (warp_bytes > max_smem_optin) return fail("variant does not fit in shared memory");
     e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem_optin);
     if (e != cudaSuccess) return cuda_fail("cudaFuncSetAttribute", e);
     cudaFuncAttributes attr;
     e = cudaFuncGetAttributes(&attr, fn);
     if (e != cudaSuccess) return cuda_fail("cudaFuncGetAttributes", e);
-    int best_w = 1, best_blocks = 0, best_warps = 0;
-    for (int w = 1; w <= 16; ++w) {
-        const long long smem = (long long)w * warp_bytes;
-        if (smem > max_smem_optin) break;
-        int blocks = 0;
-        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks, fn, w * 32, size_t(smem));
-        if (e != cudaSuccess) return cuda_fail("cudaOccupancyMaxActiveBlocksPerMultiprocessor", e);
-        if (blocks * w > best_warps) { best_warps = blocks * w; best_w = w; best_blocks = blocks; }
-    }
-    if (best_warps == 0) return fail("fused kernel cannot be resident on this device");
-    plan->warps_per_block = best_w;
-    plan->blocks_per_sm = best_blocks;
-    plan->smem_per_block = best_w * warp_bytes;
+    const int max_warps = std::max(1, std::min(attr.maxThreadsPerBlock / 32, 32));
+    int warps = std::min(max_warps, std::max(1, env_int("SX_WARPS", std::min(max_warps, 16))));
+    while (warps > 1 && tile_bytes + warps * warp_bytes > max_smem_optin) --warps;
+    const int smem = tile_bytes + warps * warp_bytes;
+    if (smem > max_smem_optin) return fail("variant does not fit in shared memory");
+    int blocks = 0;
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks, fn, warps * 32, size_t(smem));
+    if (e != cudaSuccess) return cuda_fail("cudaOccupancyMaxActiveBlocksPerMultiprocessor", e);
+    if (blocks < 1) return fail("fused kernel cannot be resident on this device");
+    plan->warps_per_block = warps;
+    plan->blocks_per_sm = blocks;
+    plan->smem_per_block = smem;
     plan->num_sms = num_sms;
     plan->regs = attr.numRegs;
-    long long grid = (long long)num_sms * best_blocks;
-    const long long needed = (num_envs + best_w - 1) / best_w;
+    plan->warp_bytes = warp_bytes;
+    plan->tile_bytes = tile_bytes;
+    const long long grid = (long long)num_sms * blocks;
+    const long long needed = (num_envs + warps - 1) / warps;
     plan->grid = int(std::max(1LL, std::min(grid, needed)));
-    *warp_bytes_out = warp_bytes;
     return 0;
 }
 
@@ -571,11 +632,12 @@ static int launch_fused(const sx_config *cfg, KernelArgs &args, cudaStream_t str
 {
     if (args.num_envs <= 0) return 0;
     LaunchPlan plan;
-    int warp_bytes = 0;
-    if (int rc = plan_launch(cfg, args.ops, args.num_envs, &plan, &warp_bytes)) return rc;
+    const int mode = mode_for(args);
+    if (int rc = plan_launch(cfg, args.ops, mode, args.num_envs, &plan)) return rc;
     args.cfg = cfg->dev;
-    args.warp_bytes = warp_bytes;
-    fused_for(cfg->cells_per_lane)<<<plan.grid, plan.warps_per_block * 32, plan.smem_per_block, stream>>>(args);
+    args.warp_bytes = plan.warp_bytes;
+    args.tile_bytes = plan.tile_bytes;
+    fused_for(cfg->cells_per_lane, mode)<<<plan.grid, plan.warps_per_block * 32, plan.smem_per_block, stream>>>(args);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return cuda_fail("sx fused kernel launch", e);
     return 0;
@@ -741,11 +803,14 @@ extern "C" int sx_step_all_launch_info(const sx_config *cfg, uint32_t obs_mask, 
     if (obs_mask & 2) ops |= OP_FO;
     if (obs_mask & 4) ops |= OP_MASK;
     LaunchPlan plan;
-    int warp_bytes = 0;
-    if (int rc = plan_launch(cfg, ops, 1LL << 40, &plan, &warp_bytes)) return rc;
+    KernelArgs probe;
+    std::memset(&probe, 0, sizeof(probe));
+    probe.ops = ops;
+    if (int rc = plan_launch(cfg, ops, mode_for(probe), 1LL << 40, &plan)) return rc;
     out->warps_per_block = plan.warps_per_block; out->blocks_per_sm = plan.blocks_per_sm;
     out->smem_bytes_per_block = plan.smem_per_block; out->num_sms = plan.num_sms; out->grid_blocks = plan.grid;
     out->regs_per_thread = plan.regs;
+    out->background_bytes = plan.tile_bytes;
     return 0;
 }
 

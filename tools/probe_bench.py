@@ -20,7 +20,7 @@ def main(version="barrage", B=262144, steps=30, full=False):
     eng.observe(st, out=out, partial=True, full=full, mask=True)
     actions = eng.sample_valid(out["valid_mask"], seed=1)
     stats = torch.zeros(8, dtype=torch.int64, device="cuda:0")
-    print(version, eng.launch_info(partial=True, full=full, mask=True))
+    print(version, eng.launch_info(partial=True, full=full, mask=True), flush=True)
     for phase, n in (("warm", 10), ("timed", steps)):
         torch.cuda.synchronize()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
