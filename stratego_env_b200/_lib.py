@@ -81,8 +81,8 @@ def load(build_if_missing: bool = True):
     global _lib
     if _lib is not None:
         return _lib
-    path = _build.LIB_PATH
-    if build_if_missing and _build.is_stale():
+    path = os.environ.get("SX_LIB") or _build.LIB_PATH  # SX_LIB: tuning aid (alternative builds)
+    if build_if_missing and path == _build.LIB_PATH and _build.is_stale():
         try:
             _build.build_extension()
         except Exception as exc:  # noqa: BLE001

@@ -12,7 +12,14 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+// K-loops of the hot functions: 1 keeps the fused loop small enough for the instruction cache
+#ifndef SX_UNROLL_K
+#define SX_UNROLL_K 1
+#endif
+
 namespace sx {
+
+constexpr int UNROLL_K = SX_UNROLL_K;
 
 // ---- piece codes (impl:145-163) -----------------------------------------------------------------
 constexpr int SP_SPY = 1, SP_SCOUT = 2, SP_MINER = 3, SP_MARSHAL = 10, SP_FLAG = 11, SP_BOMB = 12, SP_UNKNOWN = 13;
@@ -106,6 +113,7 @@ struct WarpMem {
     uint32_t *lines;   // [64] occupancy bit-lines: any[0..15 rows | 16..31 cols], enemy[32 + same]
     uint16_t *reach;   // [N] per-cell packed reach (4 x 4 bit): the move list of the player the outputs are for
     uint8_t *scratch;  // [>= 2 * setup_len] shuffle workspace
+    uint8_t *stage;    // [board_stride + cap bytes + 32] next game's state, action and aux, landed by cp.async
 };
 
 __host__ __device__ inline int round16(int v) { return (v + 15) & ~15; }
@@ -124,8 +132,23 @@ __host__ __device__ inline int carve_warp(const DevConfig &cfg, uint8_t *base, W
     off += round16(cfg.N * 2);
     if (m) m->scratch = base + off;
     off += round16(2 * cfg.setup_len);
+    if (m) m->stage = base + off;
+    off += cfg.board_stride + round16(cfg.cap_stride * 2) + 32;
     return off;
 }
+
+// ---- cp.async (LDGSTS): global -> shared without staging registers -----------------------------------
+__device__ __forceinline__ void cp_async16(void *sdst, const void *gsrc)
+{
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(uint32_t(__cvta_generic_to_shared(sdst))), "l"(gsrc)
+                 : "memory");
+}
+__device__ __forceinline__ void cp_async4(void *sdst, const void *gsrc)
+{
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(uint32_t(__cvta_generic_to_shared(sdst))), "l"(gsrc)
+                 : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
 
 // The block's read-only background images: what a game's outputs look like before the state-dependent
 // entries are added ("empty board" observation after normalisation; all-zero mask).
@@ -305,7 +328,7 @@ __device__ __forceinline__ bool gen_moves(const DevConfig &cfg, const WarpMem &m
     build_lines(cfg, m, me, flip);
     blk = blocked_move(cfg, m, a, me, flip, allow_osc);
     int found = 0;
-#pragma unroll
+#pragma unroll UNROLL_K
     for (int k = 0; k < K; ++k) {
         const int p = lane * K + k;
         uint32_t packed = 0;
@@ -313,7 +336,7 @@ __device__ __forceinline__ bool gen_moves(const DevConfig &cfg, const WarpMem &m
             const uint32_t b = m.board[view(p, flip, cfg.N)];
             const int rank = b & CELL_RANK;
             if (rank != 0 && rank <= SP_MARSHAL && int((b >> 4) & 1) == me) {  // impl:420
-                const int r = lc.r[k], c = lc.c[k];
+                const int r = fast_div(p, cfg.magic_C), c = p - r * cfg.C;
                 const uint32_t col_any = m.lines[16 + c], col_en = m.lines[48 + c];
                 const uint32_t row_any = m.lines[r], row_en = m.lines[32 + r];
                 int reach[4];
@@ -339,24 +362,33 @@ __device__ __forceinline__ bool gen_moves(const DevConfig &cfg, const WarpMem &m
 }
 
 // Expands m.reach into the spatial mask [cell][channel] (impl:292-311): stores a 1 at every move on top of
-// the zero background at `image` (global memory).
+// the zero background at `image` (global memory).  One-step moves (all but scouts) are four predicated
+// byte stores per cell; only scout rays loop.
 template <int K>
 __device__ __forceinline__ void mark_spatial(const DevConfig &cfg, const WarpMem &m, const Blocked &blk, uint8_t *image)
 {
     const int lane = lane_id();
-#pragma unroll
+    const int b1 = cfg.R - 1, b2 = 2 * b1, b3 = b2 + cfg.C - 1;
+#pragma unroll UNROLL_K
     for (int k = 0; k < K; ++k) {
         const int p = lane * K + k;
-        if (p < cfg.N) {
-            uint32_t packed = m.reach[p];
+        const uint32_t packed = p < cfg.N ? uint32_t(m.reach[p]) : 0u;
+        if (packed != 0) {
             uint8_t *cell = image + p * cfg.A;
+            const int skip = p == blk.cell ? blk.dir * 16 + blk.dist : -1;  // the move the two-square rule forbids
+            if ((packed & 0x000f) && skip != 1) cell[0] = 1;
+            if ((packed & 0x00f0) && skip != 17) cell[b1] = 1;
+            if ((packed & 0x0f00) && skip != 33) cell[b2] = 1;
+            if ((packed & 0xf000) && skip != 49) cell[b3] = 1;
+            if (packed & 0xeeee) {  // a scout ray longer than one square
 #pragma unroll 1
-            for (int d = 0; packed != 0; ++d, packed >>= 4) {
-                const int n = packed & 15;
-                uint8_t *ch = cell + dir_base(cfg, d) - 1;
+                for (int d = 0; d < 4; ++d) {
+                    const int n = (packed >> (4 * d)) & 15;
+                    uint8_t *ch = cell + (d == 0 ? 0 : d == 1 ? b1 : d == 2 ? b2 : b3) - 1;
 #pragma unroll 1
-                for (int t = 1; t <= n; ++t)
-                    if (!(p == blk.cell && d == blk.dir && t == blk.dist)) ch[t] = 1;
+                    for (int t = 2; t <= n; ++t)
+                        if (skip != d * 16 + t) ch[t] = 1;
+                }
             }
         }
     }
@@ -696,7 +728,7 @@ __device__ __forceinline__ void patch_obs(const DevConfig &cfg, const WarpMem &m
     constexpr bool SET = true;
     const int lane = lane_id(), flip = me, CH = om.channels;
     const float one = cfg.unit_lut[1];
-#pragma unroll
+#pragma unroll UNROLL_K
     for (int k = 0; k < K; ++k) {
         const int p = lane * K + k;
         if (p < cfg.N) {
@@ -743,7 +775,7 @@ __device__ __forceinline__ int sample_move(const DevConfig &cfg, const WarpMem &
     if (!any_moves) return cfg.A - 1;  // the noop entry [0,0,A-1]
     const int lane = lane_id();
     int mine = 0;
-#pragma unroll
+#pragma unroll UNROLL_K
     for (int k = 0; k < K; ++k) {
         const int p = lane * K + k;
         if (p < cfg.N) {

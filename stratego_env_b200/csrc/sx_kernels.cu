@@ -103,8 +103,11 @@ __host__ __device__ constexpr uint32_t mode_ops(int mode)
          : mode == MODE_STEP_LEAN ? OPS_STEP_BASE : 0u;
 }
 
+#ifndef SX_MAX_THREADS
+#define SX_MAX_THREADS 512
+#endif
 template <int K, int MODE>
-__global__ void __launch_bounds__(512, 1) sx_fused_kernel(const __grid_constant__ KernelArgs args)
+__global__ void __launch_bounds__(SX_MAX_THREADS, 1) sx_fused_kernel(const __grid_constant__ KernelArgs args)
 {
     extern __shared__ __align__(16) uint8_t smem[];
     const DevConfig &cfg = args.cfg;
@@ -138,10 +141,44 @@ __global__ void __launch_bounds__(512, 1) sx_fused_kernel(const __grid_constant_
     }
     __syncthreads();
 
+    // ---- state prefetch: the next game's board / captures / aux / action land in m.stage while this one runs
+    const int board16 = cfg.board_stride >> 4, cap16 = round16(cfg.cap_stride * 2) >> 4;
+    uint8_t *stage_cap = m.stage + cfg.board_stride, *stage_aux = stage_cap + (cap16 << 4), *stage_act = stage_aux + 16;
+    auto prefetch = [&](long long e) {
+        for (int c = lane; c < board16 + cap16 + 2; c += 32) {
+            if (c < board16) cp_async16(m.stage + (c << 4), args.board + e * cfg.board_stride + (c << 4));
+            else if (c < board16 + cap16)
+                cp_async16(stage_cap + ((c - board16) << 4),
+                           reinterpret_cast<const uint8_t *>(args.cap + e * cfg.cap_stride) + ((c - board16) << 4));
+            else if (c == board16 + cap16) cp_async16(stage_aux, args.aux + e * 8);
+            else if (do_step) cp_async4(stage_act, args.actions + e);
+        }
+    };
+
     long long n_games = 0, n_p1 = 0, n_p2 = 0, n_invalid = 0, n_illegal = 0;
     const long long total_warps = (long long)gridDim.x * warps_per_block;
-    for (long long env = (long long)blockIdx.x * warps_per_block + warp; env < args.num_envs; env += total_warps) {
+    long long env = (long long)blockIdx.x * warps_per_block + warp;
+    if (env < args.num_envs) prefetch(env);
+    for (; env < args.num_envs; env += total_warps) {
         const uint64_t gid = uint64_t(args.env_base + env);
+        // ---- this game's state has landed in m.stage: move it to the working slice, refill the stage ----
+        cp_async_wait_all();
+        __syncwarp();
+        for (int c = lane; c < board16 + cap16; c += 32) {
+            const uint4 v = reinterpret_cast<const uint4 *>(m.stage)[c];
+            if (c < board16) reinterpret_cast<uint4 *>(m.board)[c] = v;
+            else reinterpret_cast<uint4 *>(m.cap)[c - board16] = v;
+        }
+        const uint4 aw = *reinterpret_cast<const uint4 *>(stage_aux);
+        const int action = do_step ? *reinterpret_cast<const int *>(stage_act) : 0;
+        Aux a;
+        {
+            const uint32_t w[4] = {aw.x, aw.y, aw.z, aw.w};
+            aux_unpack(w, a);
+        }
+        __syncwarp();
+        if (env + total_warps < args.num_envs) prefetch(env + total_warps);
+        // (cp.async.wait_all above also waits for bulk copies in flight, so the TMA work is issued after it)
         // ---- start the background copies of this game's outputs; they drain while the rules run ------
         if (do_tile) {
             if (do_po) emit_tile(reinterpret_cast<uint8_t *>(args.out.partial_obs + env * cfg.po_floats),
@@ -154,20 +191,6 @@ __global__ void __launch_bounds__(512, 1) sx_fused_kernel(const __grid_constant_
             }
             if (lane == 0) bulk_commit();
         }
-        // ---- stage the compact state in shared memory ------------------------------------------
-        {
-            const uint32_t *gb = reinterpret_cast<const uint32_t *>(args.board + env * cfg.board_stride);
-            for (int i = lane; i < (cfg.board_stride >> 2); i += 32) reinterpret_cast<uint32_t *>(m.board)[i] = gb[i];
-            const uint32_t *gc = reinterpret_cast<const uint32_t *>(args.cap + env * cfg.cap_stride);
-            for (int i = lane; i < (cfg.cap_stride >> 1); i += 32) reinterpret_cast<uint32_t *>(m.cap)[i] = gc[i];
-        }
-        const uint4 aw = *reinterpret_cast<const uint4 *>(args.aux + env * 8);
-        Aux a;
-        {
-            const uint32_t w[4] = {aw.x, aw.y, aw.z, aw.w};
-            aux_unpack(w, a);
-        }
-        __syncwarp();
 
         bool dirty = false;
         // out-of-line helpers take and return everything by value so that `a` never has to live in local memory
@@ -197,7 +220,6 @@ __global__ void __launch_bounds__(512, 1) sx_fused_kernel(const __grid_constant_
         const int mover = a.to_move;
         Blocked blk{-1, 0, 0};
         if (do_step) {
-            const int action = args.actions[env];
             Move mv = args.action_format == SX_ACTION_SPATIAL ? decode_spatial(cfg, action, mover) : decode_1d(cfg, action);
             if (mv.noop && !mv.bad && !a.over) {  // impl:809-814
                 if (regen_moves(mover, blk)) mv.bad = true;
