@@ -51,6 +51,8 @@ typedef struct {
     const float *unit_lut;        /* [2] normalised 0 and 1 of the one-hot/obstacle/still channels */
     int32_t p2_rot180;            /* setup rows for player -1 are rotated 180 deg (util:33-53) instead of
                                      row-mirrored (human tables, util:241-275) */
+    int32_t capture_capacity;     /* capture-list entries per game; 0 = 2 * pieces per side (enough for any game
+                                     played from this variant's setups); the stateless facade passes rows*cols */
 } sx_config_desc;
 
 /* Byte/element strides of the device tensors for one variant. */
@@ -125,6 +127,12 @@ int sx_import_ref_state(const sx_config *cfg, sx_state st, int64_t num_envs, con
                         const int8_t *player_d, uint8_t *status_d, void *stream);
 int sx_export_ref_state(const sx_config *cfg, sx_state st, int64_t num_envs, int64_t *dense_d, int8_t *player_d,
                         void *stream);
+
+/* penv.get_state_from_player_perspective (penv:101 -> impl:646-675) on the device state: the dense state as
+ * viewer_d[b] sees it (player -1: player layers swapped, board rotated 180 degrees; NULL = absolute frame).
+ * This is what maenv puts in the observation dict under 'internal_state' (maenv:494-495). */
+int sx_export_perspective_state(const sx_config *cfg, sx_state st, int64_t num_envs, const int8_t *viewer_d,
+                                int64_t *dense_d, void *stream);
 
 /* impl:400-517 (spatial, in `player`'s frame) or impl:522-642 (1D, absolute frame): mask_d is
  * uint8 [num_envs][spatial_actions] or [num_envs][action_size].  player_d NULL = player to move. */

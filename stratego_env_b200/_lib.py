@@ -18,7 +18,7 @@ OBS_PO, OBS_FO, OBS_MASK = 1, 2, 4
 class SxConfigDesc(C.Structure):
     _fields_ = [("rows", _i32), ("cols", _i32), ("max_turns", _i32), ("usable_rows", _i32),
                 ("piece_amounts", _i32 * 13), ("obstacles", _vp), ("captured_lut", _vp), ("recent_lut", _vp),
-                ("unit_lut", _vp), ("p2_rot180", _i32)]
+                ("unit_lut", _vp), ("p2_rot180", _i32), ("capture_capacity", _i32)]
 
 
 class SxLayout(C.Structure):
@@ -51,6 +51,7 @@ SYMBOLS = {
     "sx_reset": (C.c_int, [_vp, SxState, _i64, _i64, _vp, _vp, _i32, _vp, _u64, _u32, _vp]),
     "sx_import_ref_state": (C.c_int, [_vp, SxState, _i64, _vp, _vp, _vp, _vp]),
     "sx_export_ref_state": (C.c_int, [_vp, SxState, _i64, _vp, _vp, _vp]),
+    "sx_export_perspective_state": (C.c_int, [_vp, SxState, _i64, _vp, _vp, _vp]),
     "sx_valid_mask": (C.c_int, [_vp, SxState, _i64, _vp, _i32, _vp, _vp]),
     "sx_observe": (C.c_int, [_vp, SxState, _i64, _vp, SxOutputs, _vp]),
     "sx_step": (C.c_int, [_vp, SxState, _i64, _vp, _i32, _u32, SxOutputs, _vp]),

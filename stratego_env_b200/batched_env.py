@@ -1,0 +1,152 @@
+"""``BatchedStrategoEnv``: the batched, device-resident variant of ``StrategoMultiAgentEnv``.
+
+``num_envs`` independent games live on one GPU in the compact struct-of-arrays layout; ``step`` is ONE
+launch of the fused sm_100a kernel (action decode -> move / combat -> outcome -> auto-reset -> next
+player's mask + observations [-> uniform valid-action sample]) and everything it returns is a torch CUDA
+tensor -- nothing crosses PCIe unless the caller asks.  Observation keys and layouts are the reference's
+(``ObservationComponents``; HWC float32 observations; the mask is uint8 instead of the reference's int64).
+
+Semantics that differ from the one-game API because many games advance at once:
+  * obs / mask / ``player`` are always for the player to move next in each game, in that player's frame;
+  * when a game ends during ``step`` the returned ``done`` / ``winner`` / ``game_result_was_invalid`` / rewards
+    describe the finished game, and (with ``auto_reset=True``) the observation is already the first
+    observation of the next game -- the terminal observations the reference hands to both players
+    (maenv:772-773) are available from ``observe(player=...)`` when auto-reset is off;
+  * an illegal action leaves that game untouched and sets ``illegal_action`` (the reference raises
+    ``ValueError``, impl:899-902); pass ``raise_on_illegal=True`` to get the exception (costs a host sync).
+"""
+from typing import Optional
+
+import torch
+
+from . import sharding
+from .config import HUMAN_INIT_TABLE, VERSION_CONFIGS, as_version
+from .engine import DeviceState, StrategoEngine, load_setup_table
+from .enums import GameVersions, ObservationComponents, ObservationModes
+from .stratego_multiagent_env import DEFAULT_CONFIG, with_base_config
+
+OC = ObservationComponents
+
+
+class BatchedStrategoEnv:
+    def __init__(self, env_config=None, num_envs: int = 1024, device=None, seed: int = 0, env_base: int = 0,
+                 auto_reset: bool = True, sample_actions: bool = False, raise_on_illegal: bool = False):
+        cfg = with_base_config(DEFAULT_CONFIG, env_config if env_config else {})
+        cfg['version'] = as_version(cfg['version'])
+        self.version = cfg['version']
+        version_config = VERSION_CONFIGS[self.version]
+        cfg = with_base_config(version_config, cfg)
+        for key in ('vs_human', 'vs_bot', 'curriculum_start_states_path', 'repeat_games_from_other_side',
+                    'random_player_assignment', 'same_start_pos_everytime'):
+            if cfg[key]:
+                raise NotImplementedError("%s is a single-game option (use StrategoMultiAgentEnv)" % key)
+        mode = cfg['observation_mode']
+        mode = mode if isinstance(mode, ObservationModes) else ObservationModes(mode)
+        self.observation_mode = mode
+        self._po = mode in (ObservationModes.PARTIALLY_OBSERVABLE, ObservationModes.BOTH_OBSERVATIONS)
+        self._fo = mode in (ObservationModes.FULLY_OBSERVABLE, ObservationModes.BOTH_OBSERVATIONS)
+        self.penalize_ties = bool(cfg['penalize_ties'])
+        self.include_internal_state = bool(cfg['observation_includes_internal_state'])
+        self.human_inits = bool(cfg['human_inits'])
+        if self.human_inits and self.version not in HUMAN_INIT_TABLE:
+            raise ValueError("Human inits not supported with {} game version".format(self.version.value))
+
+        self.num_envs, self.seed, self.env_base = int(num_envs), int(seed), int(env_base)
+        self.auto_reset, self.sample_actions, self.raise_on_illegal = auto_reset, sample_actions, raise_on_illegal
+        self.engine = StrategoEngine({k: cfg[k] for k in version_config}, device=device,
+                                     p2_rot180=not self.human_inits)
+        self.device = self.engine.device
+        self.rows, self.columns = self.engine.rows, self.engine.columns
+        self.spatial_action_size = self.engine.spatial_action_size
+        self.setups = (self.engine.upload_setups(load_setup_table(HUMAN_INIT_TABLE[self.version]))
+                       if self.human_inits else None)
+        self.state: DeviceState = self.engine.alloc_state(self.num_envs)
+        self.out = self.engine.alloc_outputs(self.num_envs, partial=self._po, full=self._fo, mask=True,
+                                             sample=sample_actions)
+        self.stats = torch.zeros(8, dtype=torch.int64, device=self.device)
+        self._spare_actions = torch.zeros(self.num_envs, dtype=torch.int32, device=self.device) if sample_actions else None
+
+    @classmethod
+    def from_distributed(cls, env_config=None, envs_per_rank: Optional[int] = None, global_envs: Optional[int] = None,
+                         **kwargs) -> "BatchedStrategoEnv":
+        """one process per GPU (torchrun): this rank's shard of the global batch on cuda:LOCAL_RANK"""
+        shard = sharding.current_shard(global_envs=global_envs, envs_per_rank=envs_per_rank)
+        env = cls(env_config, num_envs=shard.num_local, device=torch.device("cuda", shard.local_rank),
+                  env_base=shard.env_base, **kwargs)
+        env.shard = shard
+        return env
+
+    # ---- observation dict ---------------------------------------------------------------------------
+    def _obs(self) -> dict:
+        d = {OC.VALID_ACTIONS_MASK.value: self.out["valid_mask"], "player": self.out["player"]}
+        if self._po:
+            d[OC.PARTIAL_OBSERVATION.value] = self.out["partial_obs"]
+        if self._fo:
+            d[OC.FULL_OBSERVATION.value] = self.out["full_obs"]
+        if self.include_internal_state:
+            d[OC.INTERNAL_STATE.value] = self.engine.export_perspective_state(self.state, self.out["player"])
+        if self.sample_actions:
+            d["sampled_action"] = self.out["next_action"]
+        return d
+
+    def reset(self, reset_mask: Optional[torch.Tensor] = None) -> dict:
+        """(re)starts every game (or those with reset_mask[b] != 0) from freshly sampled setups"""
+        self.engine.reset(self.state, seed=self.seed, env_base=self.env_base, reset_mask=reset_mask,
+                          setups=self.setups, shuffle=self.setups is None)
+        self.engine.observe(self.state, out=self.out, partial=self._po, full=self._fo, mask=True)
+        if self.sample_actions:
+            self.out["next_action"] = self.engine.sample_valid(self.out["valid_mask"], seed=self.seed, step=0,
+                                                               env_base=self.env_base)
+        return self._obs()
+
+    def step(self, actions: torch.Tensor):
+        """actions: int32 [num_envs], flat index into (R, C, A) in the mover's frame (what maenv.step takes)."""
+        if actions.dtype != torch.int32:
+            actions = actions.to(torch.int32)
+        actions = actions.contiguous()
+        if self.sample_actions and actions.data_ptr() == self.out["next_action"].data_ptr():
+            # the caller plays the sampled actions: ping-pong so the kernel does not overwrite its own input
+            self.out["next_action"], self._spare_actions = self._spare_actions, self.out["next_action"]
+        self.engine.step_all(self.state, actions, self.out, env_base=self.env_base, auto_reset=self.auto_reset,
+                             sample_next=self.sample_actions, setups=self.setups, shuffle=self.setups is None,
+                             seed=self.seed, stats=self.stats)
+        out = self.out
+        if self.raise_on_illegal and bool(out["illegal"].any().item()):
+            bad = torch.nonzero(out["illegal"]).flatten().tolist()[:8]
+            raise ValueError("Couldn't get the next state because the move wasn't valid. (envs %s)" % bad)
+        reward_p1 = out["reward"]
+        if self.penalize_ties:  # maenv:803-805: both players get -0.5 for a tie
+            tie = (out["done"] != 0) & (out["winner"] == 0)
+            reward_p1 = torch.where(tie, torch.full_like(reward_p1, -0.5), reward_p1)
+            reward_p2 = torch.where(tie, torch.full_like(reward_p1, -0.5), -out["reward"])
+        else:
+            reward_p2 = -out["reward"]
+        rewards = {1: reward_p1, -1: reward_p2}
+        dones = out["done"]
+        infos = {"winner": out["winner"], "game_result_was_invalid": out["ending_invalid"],
+                 "illegal_action": out["illegal"]}
+        return self._obs(), rewards, dones, infos
+
+    def observe(self, player: Optional[torch.Tensor] = None, partial=True, full=True, mask=True) -> dict:
+        """mask + observations for an arbitrary viewer per game (+1 / -1; default: the player to move)"""
+        o = self.engine.observe(self.state, player, partial=partial, full=full, mask=mask)
+        d = {"player": o["player"]}
+        if mask:
+            d[OC.VALID_ACTIONS_MASK.value] = o["valid_mask"]
+        if partial:
+            d[OC.PARTIAL_OBSERVATION.value] = o["partial_obs"]
+        if full:
+            d[OC.FULL_OBSERVATION.value] = o["full_obs"]
+        return d
+
+    # ---- checkpoint / interop in the reference's dense layout ---------------------------------------------
+    def export_states(self):
+        """(int64 [B, 34, R, C], int8 [B] player to move) -- the reference's state layout (impl:16-60)"""
+        return self.engine.export_ref_state(self.state)
+
+    def import_states(self, dense: torch.Tensor, player: Optional[torch.Tensor] = None):
+        self.engine.import_ref_state(dense, player, state=self.state)
+
+    def reduce_stats(self) -> dict:
+        """end-of-run statistics summed over all ranks (the only collective this package issues)"""
+        return sharding.stats_dict(sharding.reduce_stats(self.stats.clone()))

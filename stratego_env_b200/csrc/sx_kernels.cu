@@ -322,12 +322,14 @@ __global__ void __launch_bounds__(SX_MAX_THREADS, 1) sx_fused_kernel(const __gri
 
 // ---- dense reference state <-> compact state (impl:16-60) -------------------------------------------
 __global__ void sx_export_kernel(DevConfig cfg, const uint8_t *board, const int16_t *aux, const uint16_t *cap,
-                                 long long num_envs, int64_t *dense, int8_t *player_out)
+                                 long long num_envs, const int8_t *viewer, int64_t *dense, int8_t *player_out)
 {
     const int lane = lane_id();
     const long long env = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (env >= num_envs) return;
     const int N = cfg.N;
+    // viewer -1: the state as that player sees it (impl:646-675): player layers swapped, board rotated 180 degrees
+    const int flip = (viewer && viewer[env] == -1) ? 1 : 0;
     int64_t *d = dense + env * (long long)SX_NUM_STATE_LAYERS * N;
     for (int i = lane; i < SX_NUM_STATE_LAYERS * N; i += 32) d[i] = 0;
     __syncwarp();
@@ -338,12 +340,12 @@ __global__ void sx_export_kernel(DevConfig cfg, const uint8_t *board, const int1
     const uint8_t *b = board + env * cfg.board_stride;
     for (int p = lane; p < N; p += 32) {
         const uint32_t c = b[p];
-        const int rank = c & CELL_RANK, owner = (c >> 4) & 1;
-        if (c & CELL_OBST) d[2 * N + p] = 1;
+        const int rank = c & CELL_RANK, owner = int((c >> 4) & 1) ^ flip, q = view(p, flip, N);
+        if (c & CELL_OBST) d[2 * N + q] = 1;
         if (rank) {
-            d[owner * N + p] = rank;
-            d[(3 + owner) * N + p] = (c & CELL_REVEALED) ? rank : SP_UNKNOWN;
-            if (c & CELL_STILL) d[(32 + owner) * N + p] = 1;
+            d[owner * N + q] = rank;
+            d[(3 + owner) * N + q] = (c & CELL_REVEALED) ? rank : SP_UNKNOWN;
+            if (c & CELL_STILL) d[(32 + owner) * N + q] = 1;
         }
     }
     if (lane == 0) {
@@ -353,16 +355,16 @@ __global__ void sx_export_kernel(DevConfig cfg, const uint8_t *board, const int1
         d[5 * N + cfg.C + 0] = a.max_turns;
         d[5 * N + cfg.C + 1] = a.invalid;
         for (int s = 0; s < 2; ++s) {
-            if (a.rfrom[s] != NO_CELL) d[(6 + s) * N + a.rfrom[s]] = 1;
-            if (a.rto[s] != NO_CELL) d[(6 + s) * N + a.rto[s]] = -a.rcode[s];
+            if (a.rfrom[s] != NO_CELL) d[(6 + (s ^ flip)) * N + view(a.rfrom[s], flip, N)] = 1;
+            if (a.rto[s] != NO_CELL) d[(6 + (s ^ flip)) * N + view(a.rto[s], flip, N)] = -a.rcode[s];
         }
         if (player_out) player_out[env] = a.to_move == 0 ? 1 : -1;
     }
     const uint16_t *ce = cap + env * cfg.cap_stride;
     for (int e = lane; e < a.ncap; e += 32) {
         const uint32_t ent = ce[e];
-        const int cell = ent & 0xff, owner = (ent >> 8) & 1, type0 = (ent >> 9) & 15, count = int(ent >> 13) + 1;
-        d[(8 + 12 * owner + type0) * N + cell] = count;
+        const int cell = ent & 0xff, owner = int((ent >> 8) & 1) ^ flip, type0 = (ent >> 9) & 15, count = int(ent >> 13) + 1;
+        d[(8 + 12 * owner + type0) * N + view(cell, flip, N)] = count;
     }
 }
 
@@ -542,7 +544,8 @@ extern "C" int sx_config_create(const sx_config_desc *desc, sx_config **out)
     }
     d.n_pieces = pieces;
     if (d.usable_rows < 1 || 2 * d.usable_rows > d.R || d.setup_len > 120 || pieces > d.setup_len) { delete c; return fail("pieces do not fit in the usable rows"); }
-    d.cap_stride = std::max(8, (2 * pieces + 7) & ~7);
+    if (desc->capture_capacity < 0 || desc->capture_capacity > 248) { delete c; return fail("capture_capacity out of range 0..248"); }
+    d.cap_stride = std::max(8, ((desc->capture_capacity > 0 ? desc->capture_capacity : 2 * pieces) + 7) & ~7);
     d.po_floats = d.N * SX_PO_CHANNELS;
     d.fo_floats = d.N * SX_FO_CHANNELS;
     d.mask_bytes = d.N * d.A;
@@ -709,17 +712,29 @@ extern "C" int sx_import_ref_state(const sx_config *cfg, sx_state st, int64_t nu
     return e == cudaSuccess ? 0 : cuda_fail("sx_import_kernel", e);
 }
 
-extern "C" int sx_export_ref_state(const sx_config *cfg, sx_state st, int64_t num_envs, int64_t *dense_d, int8_t *player_d,
-                                   void *stream)
+static int export_impl(const sx_config *cfg, sx_state st, int64_t num_envs, const int8_t *viewer_d, int64_t *dense_d,
+                       int8_t *player_d, void *stream, const char *who)
 {
-    if (int rc = check_state(cfg, st, "sx_export_ref_state")) return rc;
-    if (!dense_d) return fail("sx_export_ref_state: null dense state");
+    if (int rc = check_state(cfg, st, who)) return rc;
+    if (!dense_d) return fail(std::string(who) + ": null dense state");
     if (num_envs <= 0) return 0;
     const int wpb = 4;
     sx_export_kernel<<<unsigned((num_envs + wpb - 1) / wpb), wpb * 32, 0, static_cast<cudaStream_t>(stream)>>>(
-        cfg->dev, st.board, st.aux, st.captured, num_envs, dense_d, player_d);
+        cfg->dev, st.board, st.aux, st.captured, num_envs, viewer_d, dense_d, player_d);
     cudaError_t e = cudaGetLastError();
     return e == cudaSuccess ? 0 : cuda_fail("sx_export_kernel", e);
+}
+
+extern "C" int sx_export_ref_state(const sx_config *cfg, sx_state st, int64_t num_envs, int64_t *dense_d, int8_t *player_d,
+                                   void *stream)
+{
+    return export_impl(cfg, st, num_envs, nullptr, dense_d, player_d, stream, "sx_export_ref_state");
+}
+
+extern "C" int sx_export_perspective_state(const sx_config *cfg, sx_state st, int64_t num_envs, const int8_t *viewer_d,
+                                           int64_t *dense_d, void *stream)
+{
+    return export_impl(cfg, st, num_envs, viewer_d, dense_d, nullptr, stream, "sx_export_perspective_state");
 }
 
 extern "C" int sx_valid_mask(const sx_config *cfg, sx_state st, int64_t num_envs, const int8_t *player_d, int32_t format,

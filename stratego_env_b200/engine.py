@@ -56,7 +56,10 @@ def _stream():
 
 
 class StrategoEngine:
-    def __init__(self, game_version_config: dict, device=None, p2_rot180: bool = True):
+    def __init__(self, game_version_config: dict, device=None, p2_rot180: bool = True, normalize: bool = True,
+                 capture_capacity: int = 0):
+        """normalize=False: observations carry the raw channel values of the procedural layer (penv:157-173)
+        instead of the env-level [-1, 1] normalisation (maenv:499-508)."""
         if not torch.cuda.is_available():
             raise _lib.StrategoB200Error("StrategoEngine needs a CUDA device; there is no CPU fallback")
         self.lib = _lib.load()
@@ -73,14 +76,20 @@ class StrategoEngine:
         for i in range(13):
             desc.piece_amounts[i] = int(amounts[i])
         self._obst = np.ascontiguousarray(obstacle_map(cfg).reshape(-1), dtype=np.uint8)
-        self._cap_lut = np.ascontiguousarray(captured_lut(cfg['piece_amounts']), dtype=np.float32)
-        self._recent_lut = np.ascontiguousarray(recent_moves_lut(), dtype=np.float32)
-        self._unit_lut = np.ascontiguousarray(unit_channel_lut(), dtype=np.float32)
+        if normalize:
+            self._cap_lut = np.ascontiguousarray(captured_lut(cfg['piece_amounts']), dtype=np.float32)
+            self._recent_lut = np.ascontiguousarray(recent_moves_lut(), dtype=np.float32)
+            self._unit_lut = np.ascontiguousarray(unit_channel_lut(), dtype=np.float32)
+        else:
+            self._cap_lut = np.ascontiguousarray(np.tile(np.arange(9, dtype=np.float32), (12, 1)))
+            self._recent_lut = np.arange(-3, 2, dtype=np.float32)
+            self._unit_lut = np.asarray([0.0, 1.0], dtype=np.float32)
         desc.obstacles = self._obst.ctypes.data
         desc.captured_lut = self._cap_lut.ctypes.data
         desc.recent_lut = self._recent_lut.ctypes.data
         desc.unit_lut = self._unit_lut.ctypes.data
         desc.p2_rot180 = 1 if p2_rot180 else 0
+        desc.capture_capacity = int(capture_capacity)
         handle = C.c_void_p()
         _lib.check(self.lib.sx_config_create(C.byref(desc), C.byref(handle)), "sx_config_create")
         self._cfg = handle
@@ -183,6 +192,17 @@ class StrategoEngine:
             _lib.check(self.lib.sx_export_ref_state(self._cfg, state.as_struct(), B, dense.data_ptr(),
                                                     player.data_ptr(), _stream()), "sx_export_ref_state")
         return dense, player
+
+    def export_perspective_state(self, state: DeviceState, viewer: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """int64 [B, 34, R, C]: each game as `viewer[b]` (+1/-1; default: absolute frame) sees it (impl:646-675)."""
+        B = state.num_envs
+        dense = torch.empty((B, NUM_STATE_LAYERS, self.rows, self.columns), dtype=torch.int64, device=self.device)
+        if viewer is not None:
+            viewer = viewer.to(self.device, dtype=torch.int8).contiguous()
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.sx_export_perspective_state(self._cfg, state.as_struct(), B, _ptr(viewer),
+                                                            dense.data_ptr(), _stream()), "sx_export_perspective_state")
+        return dense
 
     def valid_mask(self, state: DeviceState, player: Optional[torch.Tensor] = None, one_d: bool = False) -> torch.Tensor:
         B = state.num_envs
