@@ -61,12 +61,15 @@ def measured_peak():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
-def recorded_traffic(workload):
-    """dram bytes per launch of the fused kernel from the committed ncu --set full capture, if any"""
+def recorded_traffic(workload, num_envs):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the fused kernel, scaled from the committed
+    `ncu --set full` capture (profiles/traffic.json holds bytes per env-step and the capture it came from)"""
     path = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(path):
         with open(path) as f:
-            return json.load(f).get(workload)
+            rec = json.load(f).get(workload)
+        if rec:
+            return rec["dram_bytes_per_env_step"] * num_envs
     return None
 
 
@@ -354,7 +357,7 @@ def run_gpu_arm(args):
                              (B * bytes_step / 1e9),
                        "dephase_steps": args.dephase if args.dephase is not None else w["dephase"]},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": recorded_traffic(args.workload), "peak_source": peak_src,
+                         "traffic": recorded_traffic(args.workload, B), "peak_source": peak_src,
                          "kernel": "sx_fused_kernel", "algorithmic_bytes_per_env_step": bytes_step,
                          "kernel_ms": kernel_ms, "launch": info},
             "e2e": e2e,
