@@ -12,6 +12,22 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+// L2 cache-hint use per access class (1 = hinted instruction form).  Measured on B200: keeping the state
+// evict_last and streaming the outputs evict_first changes Barrage by < 2 % and costs Standard 10 %, so
+// the hints are compiled out by default; the switches stay for future tuning.
+#ifndef SX_HINT_ST
+#define SX_HINT_ST 0
+#endif
+#ifndef SX_HINT_ST8
+#define SX_HINT_ST8 0
+#endif
+#ifndef SX_HINT_TMA
+#define SX_HINT_TMA 0
+#endif
+#ifndef SX_HINT_CPASYNC
+#define SX_HINT_CPASYNC 0  /* cp.async + L2::cache_hint raises "illegal instruction" on sm_100a (CUDA 12.9) */
+#endif
+
 // K-loops of the hot functions: 1 keeps the fused loop small enough for the instruction cache
 #ifndef SX_UNROLL_K
 #define SX_UNROLL_K 1
@@ -111,7 +127,7 @@ struct WarpMem {
     uint8_t *board;    // [board_stride]
     uint16_t *cap;     // [cap_stride]
     uint32_t *lines;   // [64] occupancy bit-lines: any[0..15 rows | 16..31 cols], enemy[32 + same]
-    uint16_t *reach;   // [N] per-cell packed reach (4 x 4 bit): the move list of the player the outputs are for
+    uint2 *moves;      // [N] per-cell 64-bit set of playable spatial channels: the move list the outputs are built from
     uint8_t *scratch;  // [>= 2 * setup_len] shuffle workspace
     uint8_t *stage;    // [board_stride + cap bytes + 32] next game's state, action and aux, landed by cp.async
 };
@@ -128,8 +144,8 @@ __host__ __device__ inline int carve_warp(const DevConfig &cfg, uint8_t *base, W
     off += round16(cfg.cap_stride * 2);
     if (m) m->lines = reinterpret_cast<uint32_t *>(base + off);
     off += 256;
-    if (m) m->reach = reinterpret_cast<uint16_t *>(base + off);
-    off += round16(cfg.N * 2);
+    if (m) m->moves = reinterpret_cast<uint2 *>(base + off);
+    off += round16(cfg.N * 8);
     if (m) m->scratch = base + off;
     off += round16(2 * cfg.setup_len);
     if (m) m->stage = base + off;
@@ -138,9 +154,14 @@ __host__ __device__ inline int carve_warp(const DevConfig &cfg, uint8_t *base, W
 }
 
 // ---- cp.async (LDGSTS): global -> shared without staging registers -----------------------------------
-__device__ __forceinline__ void cp_async16(void *sdst, const void *gsrc)
+__device__ __forceinline__ void cp_async16(void *sdst, const void *gsrc, uint64_t pol)
 {
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(uint32_t(__cvta_generic_to_shared(sdst))), "l"(gsrc)
+    if (!SX_HINT_CPASYNC) {
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(uint32_t(__cvta_generic_to_shared(sdst))), "l"(gsrc) : "memory");
+        return;
+    }
+    asm volatile("cp.async.cg.shared.global.L2::cache_hint [%0], [%1], 16, %2;" ::"r"(uint32_t(__cvta_generic_to_shared(sdst))),
+                 "l"(gsrc), "l"(pol)
                  : "memory");
 }
 __device__ __forceinline__ void cp_async4(void *sdst, const void *gsrc)
@@ -181,11 +202,51 @@ __device__ __forceinline__ int fast_div(int x, uint32_t magic) { return int(__um
 // flat cell index in `me`'s frame <-> absolute frame: a 180-degree rotation is index reversal
 __device__ __forceinline__ int view(int cell, int flip, int N) { return flip ? N - 1 - cell : cell; }
 
+// ---- L2 residency hints ------------------------------------------------------------------------------
+// The ~0.3 KB/game state is re-read every step and fits in the 126 MB L2 for hundreds of thousands of games;
+// the ~30 KB/game outputs are written once and stream to HBM.  Marking the former evict_last and the latter
+// evict_first keeps the state resident, so the write stream is not interrupted by DRAM reads.
+__device__ __forceinline__ uint64_t l2_policy(int kind)  // 0 normal, 1 evict_last (keep), 2 evict_first (stream)
+{
+    uint64_t p;
+    if (kind == 1) asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
+    else if (kind == 2) asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+    else asm volatile("createpolicy.fractional.L2::evict_normal.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
+__device__ __forceinline__ void st_hint(float *p, float v, uint64_t pol)
+{
+    if (!SX_HINT_ST) { *p = v; return; }
+    asm volatile("st.global.L2::cache_hint.f32 [%0], %1, %2;" ::"l"(p), "f"(v), "l"(pol) : "memory");
+}
+__device__ __forceinline__ void st_hint(uint8_t *p, uint32_t v, uint64_t pol)
+{
+    if (!SX_HINT_ST8) { *p = uint8_t(v); return; }
+    asm volatile("st.global.L2::cache_hint.u8 [%0], %1, %2;" ::"l"(p), "r"(v), "l"(pol) : "memory");
+}
+__device__ __forceinline__ void st_hint(uint32_t *p, uint32_t v, uint64_t pol)
+{
+    if (!SX_HINT_ST) { *p = v; return; }
+    asm volatile("st.global.L2::cache_hint.b32 [%0], %1, %2;" ::"l"(p), "r"(v), "l"(pol) : "memory");
+}
+__device__ __forceinline__ void st_hint(uint4 *p, uint4 v, uint64_t pol)
+{
+    if (!SX_HINT_ST) { *p = v; return; }
+    asm volatile("st.global.L2::cache_hint.v4.b32 [%0], {%1, %2, %3, %4}, %5;" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z),
+                 "r"(v.w), "l"(pol)
+                 : "memory");
+}
+
 // ---- TMA bulk copy shared -> global (SASS: UBLKCP), tracked by the issuing thread's bulk group -----
-__device__ __forceinline__ void bulk_store(void *gdst, const void *ssrc, uint32_t bytes)
+__device__ __forceinline__ void bulk_store(void *gdst, const void *ssrc, uint32_t bytes, uint64_t pol)
 {
     const uint32_t saddr = static_cast<uint32_t>(__cvta_generic_to_shared(ssrc));
-    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst), "r"(saddr), "r"(bytes)
+    if (!SX_HINT_TMA) {
+        asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst), "r"(saddr), "r"(bytes) : "memory");
+        return;
+    }
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group.L2::cache_hint [%0], [%1], %2, %3;" ::"l"(gdst), "r"(saddr),
+                 "r"(bytes), "l"(pol)
                  : "memory");
 }
 __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
@@ -197,7 +258,7 @@ __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.a
 // 16-byte aligned body goes out as one TMA bulk copy issued by lane 0 (caller commits/waits) and the
 // <16-byte head and tail as plain word stores; otherwise (odd-sized variants such as 5x5 and 15x15,
 // whose per-env byte counts are not multiples of 16) the tile is copied with plain stores.
-__device__ __noinline__ void emit_tile(uint8_t *gdst, const uint8_t *ssrc, int bytes)
+__device__ __noinline__ void emit_tile(uint8_t *gdst, const uint8_t *ssrc, int bytes, uint64_t pol)
 {
     const int lane = lane_id();
     const uintptr_t g = reinterpret_cast<uintptr_t>(gdst);
@@ -220,7 +281,7 @@ __device__ __noinline__ void emit_tile(uint8_t *gdst, const uint8_t *ssrc, int b
         const int off = head + body + ((lane - 8) << 2);
         *reinterpret_cast<uint32_t *>(gdst + off) = *reinterpret_cast<const uint32_t *>(ssrc + off);
     }
-    if (body > 0 && lane == 0) bulk_store(gdst + head, ssrc + head, uint32_t(body));
+    if (body > 0 && lane == 0) bulk_store(gdst + head, ssrc + head, uint32_t(body), pol);
 }
 
 // ---- occupancy bit-lines in `me`'s frame ------------------------------------------------------------
@@ -271,17 +332,6 @@ struct Blocked {
     int cell, dir, dist;  // in `me`'s frame; cell < 0 = nothing blocked
 };
 
-__device__ __forceinline__ uint32_t pack_blocked(const Blocked &b)
-{
-    return b.cell < 0 ? 0xffffu : (uint32_t(b.cell) | (uint32_t(b.dir) << 8) | (uint32_t(b.dist) << 10));
-}
-__device__ __forceinline__ Blocked unpack_blocked(uint32_t v)
-{
-    v &= 0xffffu;
-    if (v == 0xffffu) return Blocked{-1, 0, 0};
-    return Blocked{int(v & 0xff), int((v >> 8) & 3), int((v >> 10) & 15)};
-}
-
 __device__ __forceinline__ Blocked blocked_move(const DevConfig &cfg, const WarpMem &m, const Aux &a, int me, int flip,
                                                 bool allow_osc)
 {
@@ -299,124 +349,104 @@ __device__ __forceinline__ Blocked blocked_move(const DevConfig &cfg, const Warp
 }
 
 // ---- valid-move generation (impl:400-517 / impl:522-642) -------------------------------------------
-// Move generation produces, per cell, how far the piece on it can travel in each of the four directions
-// ("reach", 4 x 4 bit in m.reach).  The spatial mask image, the 1D mask and the uniform sampler are all
-// expansions of that list; the one move the two-square rule forbids (Blocked) is skipped on expansion.
+// Move generation produces, per cell, a 64-bit set over the spatial channels (bit ch = "the piece on this
+// cell may play channel ch", channel layout impl:292-311) in m.moves, with the one move the two-square rule
+// forbids already removed.  The spatial mask, the 1D mask and the uniform sampler are expansions of it.
 __device__ __forceinline__ int dir_base(const DevConfig &cfg, int dir)  // first channel of a direction, impl:292-311
 {
     return dir == 0 ? 0 : dir == 1 ? (cfg.R - 1) : dir == 2 ? 2 * (cfg.R - 1) : 2 * (cfg.R - 1) + (cfg.C - 1);
 }
 
-// Enumerates the moves of player index `me`, in `me`'s frame, into m.reach.  Returns (warp-uniform)
+// Enumerates the moves of player index `me`, in `me`'s frame, into m.moves.  Returns (warp-uniform)
 // whether any move exists.
 template <int K>
-__device__ __forceinline__ bool gen_moves(const DevConfig &cfg, const WarpMem &m, const Aux &a, int me, bool allow_osc,
-                                          const LaneCells<K> &lc, Blocked &blk)
+__device__ __forceinline__ bool gen_moves(const DevConfig &cfg, const WarpMem &m, const Aux &a, int me, bool allow_osc)
 {
-    blk = Blocked{-1, 0, 0};
     const int lane = lane_id();
     if (a.over) {  // impl:414
-#pragma unroll
+#pragma unroll UNROLL_K
         for (int k = 0; k < K; ++k) {
             const int p = lane * K + k;
-            if (p < cfg.N) m.reach[p] = 0;
+            if (p < cfg.N) m.moves[p] = make_uint2(0, 0);
         }
         __syncwarp();
         return false;
     }
     const int flip = me;  // player -1 sees the board rotated
     build_lines(cfg, m, me, flip);
-    blk = blocked_move(cfg, m, a, me, flip, allow_osc);
+    const Blocked blk = blocked_move(cfg, m, a, me, flip, allow_osc);
+    const int b1 = cfg.R - 1, b2 = 2 * b1, b3 = b2 + cfg.C - 1;
+    const int blocked_bit = blk.cell < 0 ? 0 : (blk.dir == 0 ? 0 : blk.dir == 1 ? b1 : blk.dir == 2 ? b2 : b3) + blk.dist - 1;
     int found = 0;
 #pragma unroll UNROLL_K
     for (int k = 0; k < K; ++k) {
         const int p = lane * K + k;
-        uint32_t packed = 0;
         if (p < cfg.N) {
+            unsigned long long bits = 0;
             const uint32_t b = m.board[view(p, flip, cfg.N)];
             const int rank = b & CELL_RANK;
             if (rank != 0 && rank <= SP_MARSHAL && int((b >> 4) & 1) == me) {  // impl:420
                 const int r = fast_div(p, cfg.magic_C), c = p - r * cfg.C;
                 const uint32_t col_any = m.lines[16 + c], col_en = m.lines[48 + c];
                 const uint32_t row_any = m.lines[r], row_en = m.lines[32 + r];
-                int reach[4];
-                reach[0] = ray_up(col_any, col_en, r, cfg.R);
-                reach[1] = ray_down(col_any, col_en, r);
-                reach[2] = ray_up(row_any, row_en, c, cfg.C);
-                reach[3] = ray_down(row_any, row_en, c);
-                int total = 0;
-#pragma unroll
-                for (int d = 0; d < 4; ++d) {
-                    if (rank != SP_SCOUT && reach[d] > 1) reach[d] = 1;  // impl:492-499
-                    packed |= uint32_t(reach[d]) << (4 * d);
-                    total += reach[d];
-                }
-                if (p == blk.cell && int((packed >> (4 * blk.dir)) & 15) >= blk.dist) total -= 1;  // impl:439-445
-                found |= total > 0;
+                int n0 = ray_up(col_any, col_en, r, cfg.R), n1 = ray_down(col_any, col_en, r);
+                int n2 = ray_up(row_any, row_en, c, cfg.C), n3 = ray_down(row_any, row_en, c);
+                if (rank != SP_SCOUT) { n0 = min(n0, 1); n1 = min(n1, 1); n2 = min(n2, 1); n3 = min(n3, 1); }  // impl:492-499
+                bits = (unsigned long long)((1u << n0) - 1u) | ((unsigned long long)((1u << n1) - 1u) << b1) |
+                       ((unsigned long long)((1u << n2) - 1u) << b2) | ((unsigned long long)((1u << n3) - 1u) << b3);
+                if (p == blk.cell) bits &= ~(1ull << blocked_bit);  // impl:439-445, 501-505
+                found |= bits != 0;
             }
-            m.reach[p] = uint16_t(packed);
+            m.moves[p] = make_uint2(uint32_t(bits), uint32_t(bits >> 32));
         }
     }
     __syncwarp();
     return __any_sync(FULL, found);
 }
 
-// Expands m.reach into the spatial mask [cell][channel] (impl:292-311): stores a 1 at every move on top of
-// the zero background at `image` (global memory).  One-step moves (all but scouts) are four predicated
-// byte stores per cell; only scout rays loop.
+// Expands m.moves into the spatial mask [cell][channel]: stores a 1 at every move on top of the zero
+// background at `image` (global memory).
 template <int K>
-__device__ __forceinline__ void mark_spatial(const DevConfig &cfg, const WarpMem &m, const Blocked &blk, uint8_t *image)
+__device__ __forceinline__ void mark_spatial(const DevConfig &cfg, const WarpMem &m, uint8_t *image, uint64_t pol)
 {
     const int lane = lane_id();
-    const int b1 = cfg.R - 1, b2 = 2 * b1, b3 = b2 + cfg.C - 1;
 #pragma unroll UNROLL_K
     for (int k = 0; k < K; ++k) {
         const int p = lane * K + k;
-        const uint32_t packed = p < cfg.N ? uint32_t(m.reach[p]) : 0u;
-        if (packed != 0) {
+        const uint2 bits = p < cfg.N ? m.moves[p] : make_uint2(0, 0);
+        if ((bits.x | bits.y) != 0) {
             uint8_t *cell = image + p * cfg.A;
-            const int skip = p == blk.cell ? blk.dir * 16 + blk.dist : -1;  // the move the two-square rule forbids
-            if ((packed & 0x000f) && skip != 1) cell[0] = 1;
-            if ((packed & 0x00f0) && skip != 17) cell[b1] = 1;
-            if ((packed & 0x0f00) && skip != 33) cell[b2] = 1;
-            if ((packed & 0xf000) && skip != 49) cell[b3] = 1;
-            if (packed & 0xeeee) {  // a scout ray longer than one square
 #pragma unroll 1
-                for (int d = 0; d < 4; ++d) {
-                    const int n = (packed >> (4 * d)) & 15;
-                    uint8_t *ch = cell + (d == 0 ? 0 : d == 1 ? b1 : d == 2 ? b2 : b3) - 1;
+            for (uint32_t w = bits.x; w != 0; w &= w - 1) st_hint(cell + __ffs(w) - 1, 1u, pol);
 #pragma unroll 1
-                    for (int t = 2; t <= n; ++t)
-                        if (skip != d * 16 + t) ch[t] = 1;
-                }
-            }
+            for (uint32_t w = bits.y; w != 0; w &= w - 1) st_hint(cell + 31 + __ffs(w), 1u, pol);
         }
     }
 }
 
-// Expands m.reach into a 1D mask row in global memory, absolute frame (impl:264-277); facade use only.
+// Expands m.moves into a 1D mask row in global memory, absolute frame (impl:264-277); facade use only.
 template <int K>
-__device__ __noinline__ void mark_1d_global(const DevConfig &cfg, const WarpMem &m, const Blocked &blk,
-                                               const LaneCells<K> &lc, int flip, uint8_t *row)
+__device__ __noinline__ void mark_1d_global(const DevConfig *cfgp, const uint2 *moves, int flip, uint8_t *row)
 {
+    const DevConfig &cfg = *cfgp;
     const int lane = lane_id();
-#pragma unroll
+    const int b1 = cfg.R - 1, b2 = 2 * b1, b3 = b2 + cfg.C - 1;
+#pragma unroll 1
     for (int k = 0; k < K; ++k) {
         const int p = lane * K + k;
-        if (p < cfg.N) {
-            const uint32_t packed = m.reach[p];
-            const int r = lc.r[k], c = lc.c[k];
-            const int s = view(p, flip, cfg.N);
-            for (int d = 0; d < 4; ++d) {
-                const int n = (packed >> (4 * d)) & 15;
-                for (int t = 1; t <= n; ++t) {
-                    if (p == blk.cell && d == blk.dir && t == blk.dist) continue;
-                    int er = r, ec = c;  // target in `me`'s frame
-                    if (d == 0) er += t; else if (d == 1) er -= t; else if (d == 2) ec += t; else ec -= t;
-                    if (flip) { er = cfg.R - 1 - er; ec = cfg.C - 1 - ec; }
-                    row[s * cfg.mpa + (d < 2 ? er : cfg.R + ec)] = 1;
-                }
-            }
+        if (p >= cfg.N) continue;
+        const int r = fast_div(p, cfg.magic_C), c = p - r * cfg.C;
+        const int s = view(p, flip, cfg.N);
+        unsigned long long bits = (unsigned long long)moves[p].x | ((unsigned long long)moves[p].y << 32);
+#pragma unroll 1
+        for (; bits != 0; bits &= bits - 1) {
+            const int ch = __ffsll((long long)bits) - 1;
+            const int d = ch >= b3 ? 3 : ch >= b2 ? 2 : ch >= b1 ? 1 : 0;
+            const int t = ch - (d == 0 ? 0 : d == 1 ? b1 : d == 2 ? b2 : b3) + 1;
+            int er = r, ec = c;  // target in `me`'s frame
+            if (d == 0) er += t; else if (d == 1) er -= t; else if (d == 2) ec += t; else ec -= t;
+            if (flip) { er = cfg.R - 1 - er; ec = cfg.C - 1 - ec; }
+            row[s * cfg.mpa + (d < 2 ? er : cfg.R + ec)] = 1;
         }
     }
 }
@@ -723,9 +753,8 @@ __device__ __noinline__ void fill_background(const DevConfig &cfg, float *tile, 
 // image at `tile` (global memory).
 template <int K>
 __device__ __forceinline__ void patch_obs(const DevConfig &cfg, const WarpMem &m, const Aux &a, float *tile,
-                                          const ObsMap om, int me)
+                                          const ObsMap om, int me, uint64_t pol)
 {
-    constexpr bool SET = true;
     const int lane = lane_id(), flip = me, CH = om.channels;
     const float one = cfg.unit_lut[1];
 #pragma unroll UNROLL_K
@@ -734,18 +763,18 @@ __device__ __forceinline__ void patch_obs(const DevConfig &cfg, const WarpMem &m
         if (p < cfg.N) {
             const uint32_t b = m.board[view(p, flip, cfg.N)];
             float *cell = tile + p * CH;
-            if (b & CELL_OBST) cell[om.obstacle] = one;
+            if (b & CELL_OBST) st_hint(cell + om.obstacle, one, pol);
             const int rank = b & CELL_RANK;
             if (rank) {
                 const int po = (b & CELL_REVEALED) ? rank : SP_UNKNOWN;
                 if (int((b >> 4) & 1) == me) {
-                    cell[om.own_true + rank - 1] = one;
-                    cell[om.own_po + po - 1] = one;
-                    if (b & CELL_STILL) cell[om.own_still] = one;
+                    st_hint(cell + om.own_true + rank - 1, one, pol);
+                    st_hint(cell + om.own_po + po - 1, one, pol);
+                    if (b & CELL_STILL) st_hint(cell + om.own_still, one, pol);
                 } else {
-                    if (om.enemy_true >= 0) cell[om.enemy_true + rank - 1] = one;
-                    cell[om.enemy_po + po - 1] = one;
-                    if (b & CELL_STILL) cell[om.enemy_still] = one;
+                    if (om.enemy_true >= 0) st_hint(cell + om.enemy_true + rank - 1, one, pol);
+                    st_hint(cell + om.enemy_po + po - 1, one, pol);
+                    if (b & CELL_STILL) st_hint(cell + om.enemy_still, one, pol);
                 }
             }
         }
@@ -755,22 +784,21 @@ __device__ __forceinline__ void patch_obs(const DevConfig &cfg, const WarpMem &m
         const int cell_abs = (lane & 1) ? a.rto[who] : a.rfrom[who];
         const int code = (lane & 1) ? -a.rcode[who] : 1;
         if (cell_abs != NO_CELL)
-            tile[view(cell_abs, flip, cfg.N) * CH + (lane < 2 ? om.own_recent : om.enemy_recent)] =
-                cfg.recent_lut[(SET ? code : 0) + 3];
+            st_hint(tile + view(cell_abs, flip, cfg.N) * CH + (lane < 2 ? om.own_recent : om.enemy_recent),
+                    cfg.recent_lut[code + 3], pol);
     }
     for (int e = lane; e < a.ncap; e += 32) {
         const uint32_t ent = m.cap[e];
         const int cell_abs = ent & 0xff, owner = (ent >> 8) & 1, type0 = (ent >> 9) & 15, count = int(ent >> 13) + 1;
-        tile[view(cell_abs, flip, cfg.N) * CH + (owner == me ? om.own_cap : om.enemy_cap) + type0] =
-            cfg.cap_lut[type0 * 9 + (SET ? count : 0)];
+        st_hint(tile + view(cell_abs, flip, cfg.N) * CH + (owner == me ? om.own_cap : om.enemy_cap) + type0,
+                cfg.cap_lut[type0 * 9 + count], pol);
     }
 }
 
 // ---- uniform draw over the generated moves (replaces maenv:830-834) ----------------------------------
-// Order = ascending flat spatial index (cell, then channel), which is the generation order.
+// Order = ascending flat spatial index (cell, then channel).
 template <int K>
-__device__ __forceinline__ int sample_move(const DevConfig &cfg, const WarpMem &m, const Blocked &blk, bool any_moves,
-                                           uint32_t rnd)
+__device__ __forceinline__ int sample_move(const DevConfig &cfg, const WarpMem &m, bool any_moves, uint32_t rnd)
 {
     if (!any_moves) return cfg.A - 1;  // the noop entry [0,0,A-1]
     const int lane = lane_id();
@@ -779,9 +807,8 @@ __device__ __forceinline__ int sample_move(const DevConfig &cfg, const WarpMem &
     for (int k = 0; k < K; ++k) {
         const int p = lane * K + k;
         if (p < cfg.N) {
-            const uint32_t packed = m.reach[p];
-            mine += int(packed & 15) + int((packed >> 4) & 15) + int((packed >> 8) & 15) + int((packed >> 12) & 15);
-            if (p == blk.cell && int((packed >> (4 * blk.dir)) & 15) >= blk.dist) mine -= 1;
+            const uint2 bits = m.moves[p];
+            mine += __popc(bits.x) + __popc(bits.y);
         }
     }
     int incl = mine;
@@ -791,30 +818,25 @@ __device__ __forceinline__ int sample_move(const DevConfig &cfg, const WarpMem &
         if (lane >= off) incl += v;
     }
     const int total = __shfl_sync(FULL, incl, 31);
-    int t = int(__umulhi(rnd, uint32_t(total)));
+    const int t = int(__umulhi(rnd, uint32_t(total)));
     int action = 0;
     const bool owner = t >= incl - mine && t < incl;
     if (owner) {
         int left = t - (incl - mine);
-        bool found = false;
 #pragma unroll 1
-        for (int k = 0; k < K && !found; ++k) {
+        for (int k = 0; k < K; ++k) {
             const int p = lane * K + k;
-            uint32_t packed = p < cfg.N ? uint32_t(m.reach[p]) : 0u;
+            const uint2 bits = p < cfg.N ? m.moves[p] : make_uint2(0, 0);
+            const int c0 = __popc(bits.x), c1 = __popc(bits.y);
+            if (left < c0 + c1) {
+                uint32_t w = left < c0 ? bits.x : bits.y;
+                int skip = left < c0 ? left : left - c0;
 #pragma unroll 1
-            for (int d = 0; packed != 0; ++d, packed >>= 4) {
-                const int reach = packed & 15;
-                const bool skip = p == blk.cell && d == blk.dir && reach >= blk.dist;
-                const int n = reach - (skip ? 1 : 0);
-                if (left < n) {
-                    int dist = left + 1;
-                    if (skip && dist >= blk.dist) dist += 1;
-                    action = p * cfg.A + dir_base(cfg, d) + dist - 1;
-                    found = true;
-                    break;
-                }
-                left -= n;
+                for (; skip > 0; --skip) w &= w - 1;
+                action = p * cfg.A + (left < c0 ? 0 : 32) + __ffs(w) - 1;
+                break;
             }
+            left -= c0 + c1;
         }
     }
     const uint32_t who = __ballot_sync(FULL, owner);

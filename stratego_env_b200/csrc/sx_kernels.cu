@@ -74,21 +74,16 @@ __host__ __device__ inline int carve_tile(const DevConfig &cfg, uint32_t ops, ui
 // three instructions) at the top of the iteration, the warp runs the rule logic while the copy drains,
 // and the sparse entries are then stored straight to global memory, where they merge with the freshly
 // written lines in L2.  No warp owns a 30 KB tile, so shared memory no longer limits residency.
-// Arguments and result by value (bit 31 = any move, low 16 bits = packed Blocked) so that the caller's
-// state stays in registers.
+// Arguments and result by value so that the caller's state stays in registers.
 template <int K>
-__device__ __noinline__ uint32_t gen_moves_cold(const DevConfig *cfg, uint8_t *warp_base, uint4 auxw, int me)
+__device__ __noinline__ bool gen_moves_cold(const DevConfig *cfg, uint8_t *warp_base, uint4 auxw, int me)
 {
     WarpMem m;
     carve_warp(*cfg, warp_base, &m);
     const uint32_t w[4] = {auxw.x, auxw.y, auxw.z, auxw.w};
     Aux a;
     aux_unpack(w, a);
-    LaneCells<K> lc;
-    lc.init(*cfg);
-    Blocked blk;
-    const bool any = gen_moves<K>(*cfg, m, a, me, false, lc, blk);
-    return (any ? 0x80000000u : 0u) | pack_blocked(blk);
+    return gen_moves<K>(*cfg, m, a, me, false);
 }
 
 // MODE fixes the op set at compile time so that each hot launch type carries only its own code (the
@@ -107,7 +102,7 @@ __host__ __device__ constexpr uint32_t mode_ops(int mode)
 #define SX_MAX_THREADS 512
 #endif
 template <int K, int MODE>
-__global__ void __launch_bounds__(SX_MAX_THREADS, 1) sx_fused_kernel(const __grid_constant__ KernelArgs args)
+__global__ void __launch_bounds__(K <= 2 ? 1024 : SX_MAX_THREADS, 1) sx_fused_kernel(const __grid_constant__ KernelArgs args)
 {
     extern __shared__ __align__(16) uint8_t smem[];
     const DevConfig &cfg = args.cfg;
@@ -125,8 +120,6 @@ __global__ void __launch_bounds__(SX_MAX_THREADS, 1) sx_fused_kernel(const __gri
     const bool need_moves = do_mask || do_sample || (ops & (OP_MASK_1D | OP_NEED_MOVES));
     const int mask_tile_bytes = round16(cfg.mask_bytes + 16);
     const ObsMap pom = po_map(), fom = fo_map();
-    LaneCells<K> lc;
-    lc.init(cfg);
 
     // the block's read-only background images
     Tile bg;
@@ -141,16 +134,18 @@ __global__ void __launch_bounds__(SX_MAX_THREADS, 1) sx_fused_kernel(const __gri
     }
     __syncthreads();
 
+    const bool hints = !(flags & 0x40000u);
+    const uint64_t pol_keep = l2_policy(hints ? 1 : 0), pol_stream = l2_policy(hints ? 2 : 0);
     // ---- state prefetch: the next game's board / captures / aux / action land in m.stage while this one runs
     const int board16 = cfg.board_stride >> 4, cap16 = round16(cfg.cap_stride * 2) >> 4;
     uint8_t *stage_cap = m.stage + cfg.board_stride, *stage_aux = stage_cap + (cap16 << 4), *stage_act = stage_aux + 16;
     auto prefetch = [&](long long e) {
         for (int c = lane; c < board16 + cap16 + 2; c += 32) {
-            if (c < board16) cp_async16(m.stage + (c << 4), args.board + e * cfg.board_stride + (c << 4));
+            if (c < board16) cp_async16(m.stage + (c << 4), args.board + e * cfg.board_stride + (c << 4), pol_keep);
             else if (c < board16 + cap16)
                 cp_async16(stage_cap + ((c - board16) << 4),
-                           reinterpret_cast<const uint8_t *>(args.cap + e * cfg.cap_stride) + ((c - board16) << 4));
-            else if (c == board16 + cap16) cp_async16(stage_aux, args.aux + e * 8);
+                           reinterpret_cast<const uint8_t *>(args.cap + e * cfg.cap_stride) + ((c - board16) << 4), pol_keep);
+            else if (c == board16 + cap16) cp_async16(stage_aux, args.aux + e * 8, pol_keep);
             else if (do_step) cp_async4(stage_act, args.actions + e);
         }
     };
@@ -180,14 +175,14 @@ __global__ void __launch_bounds__(SX_MAX_THREADS, 1) sx_fused_kernel(const __gri
         if (env + total_warps < args.num_envs) prefetch(env + total_warps);
         // (cp.async.wait_all above also waits for bulk copies in flight, so the TMA work is issued after it)
         // ---- start the background copies of this game's outputs; they drain while the rules run ------
-        if (do_tile) {
+        if (do_tile && !(flags & 0x10000u)) {
             if (do_po) emit_tile(reinterpret_cast<uint8_t *>(args.out.partial_obs + env * cfg.po_floats),
-                                 reinterpret_cast<const uint8_t *>(bg.po), cfg.po_floats * 4);
+                                 reinterpret_cast<const uint8_t *>(bg.po), cfg.po_floats * 4, pol_stream);
             if (do_fo) emit_tile(reinterpret_cast<uint8_t *>(args.out.full_obs + env * cfg.fo_floats),
-                                 reinterpret_cast<const uint8_t *>(bg.fo), cfg.fo_floats * 4);
+                                 reinterpret_cast<const uint8_t *>(bg.fo), cfg.fo_floats * 4, pol_stream);
             if (do_mask) {
                 uint8_t *gmask = args.out.valid_mask + env * cfg.mask_bytes;
-                emit_tile(gmask, bg.mask + (reinterpret_cast<uintptr_t>(gmask) & 15), cfg.mask_bytes);
+                emit_tile(gmask, bg.mask + (reinterpret_cast<uintptr_t>(gmask) & 15), cfg.mask_bytes, pol_stream);
             }
             if (lane == 0) bulk_commit();
         }
@@ -202,13 +197,11 @@ __global__ void __launch_bounds__(SX_MAX_THREADS, 1) sx_fused_kernel(const __gri
             const uint32_t w[4] = {nw.x, nw.y, nw.z, nw.w};
             aux_unpack(w, a);
         };
-        auto regen_moves = [&](int me, Blocked &b) -> bool {
+        auto regen_moves = [&](int me) -> bool {
             uint32_t w[4];
             aux_pack(a, w);
             __syncwarp();
-            const uint32_t r = gen_moves_cold<K>(&cfg, warp_base, make_uint4(w[0], w[1], w[2], w[3]), me);
-            b = unpack_blocked(r);
-            return (r >> 31) != 0;
+            return gen_moves_cold<K>(&cfg, warp_base, make_uint4(w[0], w[1], w[2], w[3]), me);
         };
         if (MODE == MODE_GENERIC && (ops & OP_RESET) && (args.reset_mask == nullptr || args.reset_mask[env] != 0)) {
             do_reset();
@@ -218,11 +211,10 @@ __global__ void __launch_bounds__(SX_MAX_THREADS, 1) sx_fused_kernel(const __gri
         // ---- step: decode, validate, apply (impl:897-1028) ----------------------------------------
         StepStatus status = STEP_UNCHANGED;
         const int mover = a.to_move;
-        Blocked blk{-1, 0, 0};
         if (do_step) {
             Move mv = args.action_format == SX_ACTION_SPATIAL ? decode_spatial(cfg, action, mover) : decode_1d(cfg, action);
             if (mv.noop && !mv.bad && !a.over) {  // impl:809-814
-                if (regen_moves(mover, blk)) mv.bad = true;
+                if (regen_moves(mover)) mv.bad = true;
             }
             int attack;
             status = apply_move(cfg, m, a, mv, allow_osc, attack);
@@ -234,14 +226,14 @@ __global__ void __launch_bounds__(SX_MAX_THREADS, 1) sx_fused_kernel(const __gri
         if (player_override) viewer = player_override[env] == 1 ? 0 : 1;
         bool any = false;
         const bool have_moves = need_moves && (status == STEP_MOVED || !do_step || do_mask || do_sample || (ops & OP_MASK_1D));
-        if (have_moves) any = gen_moves<K>(cfg, m, a, viewer, false, lc, blk);
+        if (have_moves) any = gen_moves<K>(cfg, m, a, viewer, false);
 
         if (status == STEP_MOVED) {
             if (have_moves && !any && !a.over) { a.over = 1; a.winner = mover == 0 ? 1 : -1; }  // impl:1031-1036
             if (a.turn >= a.max_turns && !a.over) {  // impl:1040-1043
                 a.over = 1;
                 a.invalid = 1;
-                if (have_moves && any) any = regen_moves(viewer, blk);  // terminal: noop only
+                if (have_moves && any) any = regen_moves(viewer);  // terminal: noop only
             }
         }
         const bool done = do_step && status != STEP_ILLEGAL && a.over;
@@ -266,44 +258,46 @@ __global__ void __launch_bounds__(SX_MAX_THREADS, 1) sx_fused_kernel(const __gri
         if (done && (flags & SX_AUTO_RESET)) {
             do_reset();
             viewer = a.to_move;
-            if (need_moves) any = regen_moves(viewer, blk);
+            if (need_moves) any = regen_moves(viewer);
         }
         if (args.out.player && lane == 0) args.out.player[env] = viewer == 0 ? 1 : -1;
 
         if ((ops & OP_MASK_1D) != 0) {
             uint8_t *row = args.mask1d + env * cfg.action_size;
-            mark_1d_global<K>(cfg, m, blk, lc, viewer, row);
+            mark_1d_global<K>(&cfg, m.moves, viewer, row);
             if (!any && lane == 0) row[cfg.action_size - 1] = 1;  // impl:639-640
         }
 
         if ((ops & OP_WRITE_STATE) && dirty) {
             uint32_t *gb = reinterpret_cast<uint32_t *>(args.board + env * cfg.board_stride);
-            for (int i = lane; i < (cfg.board_stride >> 2); i += 32) gb[i] = reinterpret_cast<const uint32_t *>(m.board)[i];
+            for (int i = lane; i < (cfg.board_stride >> 2); i += 32)
+                st_hint(gb + i, reinterpret_cast<const uint32_t *>(m.board)[i], pol_keep);
             uint32_t *gc = reinterpret_cast<uint32_t *>(args.cap + env * cfg.cap_stride);
-            for (int i = lane; i < (cfg.cap_stride >> 1); i += 32) gc[i] = reinterpret_cast<const uint32_t *>(m.cap)[i];
+            for (int i = lane; i < (cfg.cap_stride >> 1); i += 32)
+                st_hint(gc + i, reinterpret_cast<const uint32_t *>(m.cap)[i], pol_keep);
             if (lane == 0) {
                 uint32_t w[4];
                 aux_pack(a, w);
-                *reinterpret_cast<uint4 *>(args.aux + env * 8) = make_uint4(w[0], w[1], w[2], w[3]);
+                st_hint(reinterpret_cast<uint4 *>(args.aux + env * 8), make_uint4(w[0], w[1], w[2], w[3]), pol_keep);
             }
         }
 
         if (do_sample) {
             const uint4 rnd = philox4x32_10(make_uint4(uint32_t(gid), uint32_t(gid >> 32), RNG_SAMPLE ^ uint32_t(a.turn), a.episode), args.key);
-            const int act = sample_move<K>(cfg, m, blk, any, rnd.x);
+            const int act = sample_move<K>(cfg, m, any, rnd.x);
             if (lane == 0) args.out.next_action[env] = act;
         }
 
         // ---- render: sparse entries on top of the (by now written) background ---------------------------
-        if (do_tile) {
+        if (do_tile && !(flags & 0x20000u)) {
             if (lane == 0) bulk_wait_all();  // this game's background is in global memory
             __syncwarp();
-            if (do_po) patch_obs<K>(cfg, m, a, args.out.partial_obs + env * cfg.po_floats, pom, viewer);
-            if (do_fo) patch_obs<K>(cfg, m, a, args.out.full_obs + env * cfg.fo_floats, fom, viewer);
+            if (do_po) patch_obs<K>(cfg, m, a, args.out.partial_obs + env * cfg.po_floats, pom, viewer, pol_stream);
+            if (do_fo) patch_obs<K>(cfg, m, a, args.out.full_obs + env * cfg.fo_floats, fom, viewer, pol_stream);
             if (do_mask) {
                 uint8_t *gmask = args.out.valid_mask + env * cfg.mask_bytes;
-                mark_spatial<K>(cfg, m, blk, gmask);
-                if (!any && lane == 0) gmask[cfg.A - 1] = 1;  // [0,0,A-1], impl:514-515
+                mark_spatial<K>(cfg, m, gmask, pol_stream);
+                if (!any && lane == 0) st_hint(gmask + cfg.A - 1, 1u, pol_stream);  // [0,0,A-1], impl:514-515
             }
         }
         __syncwarp();
@@ -632,7 +626,10 @@ static int plan_launch(const sx_config *cfg, uint32_t ops, int mode, long long n
     e = cudaFuncGetAttributes(&attr, fn);
     if (e != cudaSuccess) return cuda_fail("cudaFuncGetAttributes", e);
     const int max_warps = std::max(1, std::min(attr.maxThreadsPerBlock / 32, 32));
-    int warps = std::min(max_warps, std::max(1, env_int("SX_WARPS", std::min(max_warps, 16))));
+    // Measured on B200: throughput peaks when ~0.4 MB of output per SM is in flight and falls beyond it (more
+    // resident warps only lengthen the TMA completion queue), so fewer warps for bigger per-game outputs.
+    const int preferred = tile_bytes <= 8 * 1024 ? 32 : tile_bytes <= 32 * 1024 ? 12 : tile_bytes <= 64 * 1024 ? 8 : 6;
+    int warps = std::min(max_warps, std::max(1, env_int("SX_WARPS", std::min(max_warps, preferred))));
     while (warps > 1 && tile_bytes + warps * warp_bytes > max_smem_optin) --warps;
     const int smem = tile_bytes + warps * warp_bytes;
     if (smem > max_smem_optin) return fail("variant does not fit in shared memory");
@@ -640,6 +637,7 @@ static int plan_launch(const sx_config *cfg, uint32_t ops, int mode, long long n
     e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks, fn, warps * 32, size_t(smem));
     if (e != cudaSuccess) return cuda_fail("cudaOccupancyMaxActiveBlocksPerMultiprocessor", e);
     if (blocks < 1) return fail("fused kernel cannot be resident on this device");
+    blocks = std::max(1, std::min(blocks, env_int("SX_BLOCKS", tile_bytes > 8 * 1024 ? 1 : blocks)));
     plan->warps_per_block = warps;
     plan->blocks_per_sm = blocks;
     plan->smem_per_block = smem;
@@ -811,7 +809,7 @@ extern "C" int sx_step_all(const sx_config *cfg, sx_state st, int64_t num_envs, 
     KernelArgs a;
     base_args(a, st, num_envs, env_base);
     a.actions = actions_d; a.action_format = action_format;
-    a.flags = flags;
+    a.flags = flags | (uint32_t(env_int("SX_DEBUG", 0)) << 16);  // SX_DEBUG: 1 = skip TMA, 2 = skip sparse stores (experiments)
     a.out = out;
     a.ops = step_all_ops(out, flags);
     a.setups = setups_d; a.n_setups = n_setups;

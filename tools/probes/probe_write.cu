@@ -49,6 +49,30 @@ __global__ void k_tma(uint8_t *p, size_t n_tiles, int tile) {
         asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
     }
 }
+// the engine's output layout: per game a 26 800 B observation (16 B aligned) and a 3 700 B mask row (4 B aligned),
+// written with the same TMA bulk + head/tail word stores, nothing else (no logic, no sparse entries)
+__global__ void k_layout(uint8_t *obs, uint8_t *mask, size_t n_envs, int obs_bytes, int mask_bytes, int wait_read) {
+    extern __shared__ __align__(128) uint8_t smem[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, wpb = blockDim.x >> 5;
+    for (int i = threadIdx.x * 16; i < obs_bytes + mask_bytes + 32; i += blockDim.x * 16) *reinterpret_cast<uint4 *>(smem + i) = make_uint4(0, 0, 0, 0);
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    __syncthreads();
+    const uint32_t s_obs = (uint32_t)__cvta_generic_to_shared(smem), s_mask = s_obs + ((obs_bytes + 15) & ~15);
+    for (size_t e = blockIdx.x * (size_t)wpb + warp; e < n_envs; e += (size_t)gridDim.x * wpb) {
+        uint8_t *go = obs + e * obs_bytes, *gm = mask + e * mask_bytes;
+        const int head = int((16 - (reinterpret_cast<uintptr_t>(gm) & 15)) & 15), body = (mask_bytes - head) & ~15, tail = mask_bytes - head - body;
+        if (lane < (head >> 2)) reinterpret_cast<uint32_t *>(gm)[lane] = 0;
+        if (lane >= 8 && lane - 8 < (tail >> 2)) *reinterpret_cast<uint32_t *>(gm + head + body + ((lane - 8) << 2)) = 0;
+        if (lane == 0) {
+            asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(go), "r"(s_obs), "r"(obs_bytes) : "memory");
+            asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gm + head), "r"(s_mask), "r"(body) : "memory");
+            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+            if (wait_read) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+            else asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+        }
+        __syncwarp();
+    }
+}
 __global__ void k_copy(const uint4 *a, uint4 *b, size_t n) {
     for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) b[i] = a[i];
 }
@@ -83,6 +107,16 @@ int main() {
             RUN(nm, (double)(bytes / tile) * tile, (k_tma<false><<<148, wpb * 32, wpb * tile>>>(a, bytes / tile, tile)));
             snprintf(nm, 64, "TMA bulk evict_first tile=%d warps/SM=%d", tile, wpb);
             RUN(nm, (double)(bytes / tile) * tile, (k_tma<true><<<148, wpb * 32, wpb * tile>>>(a, bytes / tile, tile)));
+        }
+    }
+    {
+        const int ob = 26800, mb = 3700;
+        const size_t n_envs = 262144;
+        uint8_t *mask = b;
+        cudaFuncSetAttribute(k_layout, cudaFuncAttributeMaxDynamicSharedMemorySize, 40000);
+        for (int wpb : {4, 8, 12, 16}) for (int wr : {1, 0}) {
+            char nm[96]; snprintf(nm, 96, "engine layout obs26800+mask3700 W=%d wait=%s", wpb, wr ? "read" : "full");
+            RUN(nm, (double)n_envs * (ob + mb), (k_layout<<<148, wpb * 32, 32768>>>(a, mask, n_envs, ob, mb, wr)));
         }
     }
     RUN("copy ld.v4/st.v4 grid=148x8", 2.0 * bytes, (k_copy<<<148 * 8, 256>>>((const uint4 *)a, (uint4 *)b, n16)));
