@@ -129,7 +129,6 @@ struct WarpMem {
     uint32_t *lines;   // [64] occupancy bit-lines: any[0..15 rows | 16..31 cols], enemy[32 + same]
     uint2 *moves;      // [N] per-cell 64-bit set of playable spatial channels: the move list the outputs are built from
     uint8_t *scratch;  // [>= 2 * setup_len] shuffle workspace
-    uint8_t *stage;    // [board_stride + cap bytes + 32] next game's state, action and aux, landed by cp.async
 };
 
 __host__ __device__ inline int round16(int v) { return (v + 15) & ~15; }
@@ -148,8 +147,6 @@ __host__ __device__ inline int carve_warp(const DevConfig &cfg, uint8_t *base, W
     off += round16(cfg.N * 8);
     if (m) m->scratch = base + off;
     off += round16(2 * cfg.setup_len);
-    if (m) m->stage = base + off;
-    off += cfg.board_stride + round16(cfg.cap_stride * 2) + 32;
     return off;
 }
 
@@ -252,6 +249,7 @@ __device__ __forceinline__ void bulk_store(void *gdst, const void *ssrc, uint32_
 __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_but_one() { asm volatile("cp.async.bulk.wait_group 1;" ::: "memory"); }
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
 // Emits `bytes` from shared memory to global memory.  When src and dst are congruent mod 16 the

@@ -136,56 +136,71 @@ __global__ void __launch_bounds__(K <= 2 ? 1024 : SX_MAX_THREADS, 1) sx_fused_ke
 
     const bool hints = !(flags & 0x40000u);
     const uint64_t pol_keep = l2_policy(hints ? 1 : 0), pol_stream = l2_policy(hints ? 2 : 0);
-    // ---- state prefetch: the next game's board / captures / aux / action land in m.stage while this one runs
-    const int board16 = cfg.board_stride >> 4, cap16 = round16(cfg.cap_stride * 2) >> 4;
-    uint8_t *stage_cap = m.stage + cfg.board_stride, *stage_aux = stage_cap + (cap16 << 4), *stage_act = stage_aux + 16;
-    auto prefetch = [&](long long e) {
-        for (int c = lane; c < board16 + cap16 + 2; c += 32) {
-            if (c < board16) cp_async16(m.stage + (c << 4), args.board + e * cfg.board_stride + (c << 4), pol_keep);
-            else if (c < board16 + cap16)
-                cp_async16(stage_cap + ((c - board16) << 4),
-                           reinterpret_cast<const uint8_t *>(args.cap + e * cfg.cap_stride) + ((c - board16) << 4), pol_keep);
-            else if (c == board16 + cap16) cp_async16(stage_aux, args.aux + e * 8, pol_keep);
-            else if (do_step) cp_async4(stage_act, args.actions + e);
+
+    // ---- software pipeline -----------------------------------------------------------------------------
+    // While game i runs, (1) game i+1's state / action loads are in flight in registers and (2) game i+1's
+    // background images are already on their way to HBM: they are issued BEFORE waiting for game i's copy,
+    // so a warp keeps up to two bulk groups in flight and never idles on TMA completion.
+    struct Prefetched {
+        uint32_t board[2], cap[4];
+        uint4 aux;
+        int action;
+    };
+    const int board_words = cfg.board_stride >> 2, cap_words = cfg.cap_stride >> 1;
+    auto load_state = [&](long long e, Prefetched &pf) {
+        const uint32_t *gb = reinterpret_cast<const uint32_t *>(args.board + e * cfg.board_stride);
+        const uint32_t *gc = reinterpret_cast<const uint32_t *>(args.cap + e * cfg.cap_stride);
+#pragma unroll
+        for (int j = 0; j < 2; ++j) pf.board[j] = lane + 32 * j < board_words ? gb[lane + 32 * j] : 0u;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) pf.cap[j] = lane + 32 * j < cap_words ? gc[lane + 32 * j] : 0u;
+        pf.aux = *reinterpret_cast<const uint4 *>(args.aux + e * 8);
+        pf.action = do_step ? args.actions[e] : 0;
+    };
+    auto issue_background = [&](long long e) {
+        if (flags & 0x10000u) return;  // experiment switch
+        if (do_po) emit_tile(reinterpret_cast<uint8_t *>(args.out.partial_obs + e * cfg.po_floats),
+                             reinterpret_cast<const uint8_t *>(bg.po), cfg.po_floats * 4, pol_stream);
+        if (do_fo) emit_tile(reinterpret_cast<uint8_t *>(args.out.full_obs + e * cfg.fo_floats),
+                             reinterpret_cast<const uint8_t *>(bg.fo), cfg.fo_floats * 4, pol_stream);
+        if (do_mask) {
+            uint8_t *gmask = args.out.valid_mask + e * cfg.mask_bytes;
+            emit_tile(gmask, bg.mask + (reinterpret_cast<uintptr_t>(gmask) & 15), cfg.mask_bytes, pol_stream);
         }
+        if (lane == 0) bulk_commit();
     };
 
     long long n_games = 0, n_p1 = 0, n_p2 = 0, n_invalid = 0, n_illegal = 0;
     const long long total_warps = (long long)gridDim.x * warps_per_block;
     long long env = (long long)blockIdx.x * warps_per_block + warp;
-    if (env < args.num_envs) prefetch(env);
+    Prefetched pf;
+    // Where a game's background copy is issued.  The sparse entries must reach L2 while the background lines
+    // are still resident there (otherwise every 4-byte store becomes a DRAM read-modify-write), so the copy is
+    // issued late: after the rules, right before the (short) wait.  SX_DEBUG bits 4-5 select the point for
+    // experiments: 0 = late (default), 1 = after the outcome / before write-back and sampling, 2 = top of the game.
+    const int issue_at = (flags >> 20) & 3;
+    if (env < args.num_envs) load_state(env, pf);
     for (; env < args.num_envs; env += total_warps) {
         const uint64_t gid = uint64_t(args.env_base + env);
-        // ---- this game's state has landed in m.stage: move it to the working slice, refill the stage ----
-        cp_async_wait_all();
+        // ---- this game's state has arrived in registers: move it to the working slice, request the next ----
         __syncwarp();
-        for (int c = lane; c < board16 + cap16; c += 32) {
-            const uint4 v = reinterpret_cast<const uint4 *>(m.stage)[c];
-            if (c < board16) reinterpret_cast<uint4 *>(m.board)[c] = v;
-            else reinterpret_cast<uint4 *>(m.cap)[c - board16] = v;
-        }
-        const uint4 aw = *reinterpret_cast<const uint4 *>(stage_aux);
-        const int action = do_step ? *reinterpret_cast<const int *>(stage_act) : 0;
+#pragma unroll
+        for (int j = 0; j < 2; ++j)
+            if (lane + 32 * j < board_words) reinterpret_cast<uint32_t *>(m.board)[lane + 32 * j] = pf.board[j];
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+            if (lane + 32 * j < cap_words) reinterpret_cast<uint32_t *>(m.cap)[lane + 32 * j] = pf.cap[j];
+        const int action = pf.action;
         Aux a;
         {
-            const uint32_t w[4] = {aw.x, aw.y, aw.z, aw.w};
+            const uint32_t w[4] = {pf.aux.x, pf.aux.y, pf.aux.z, pf.aux.w};
             aux_unpack(w, a);
         }
         __syncwarp();
-        if (env + total_warps < args.num_envs) prefetch(env + total_warps);
-        // (cp.async.wait_all above also waits for bulk copies in flight, so the TMA work is issued after it)
-        // ---- start the background copies of this game's outputs; they drain while the rules run ------
-        if (do_tile && !(flags & 0x10000u)) {
-            if (do_po) emit_tile(reinterpret_cast<uint8_t *>(args.out.partial_obs + env * cfg.po_floats),
-                                 reinterpret_cast<const uint8_t *>(bg.po), cfg.po_floats * 4, pol_stream);
-            if (do_fo) emit_tile(reinterpret_cast<uint8_t *>(args.out.full_obs + env * cfg.fo_floats),
-                                 reinterpret_cast<const uint8_t *>(bg.fo), cfg.fo_floats * 4, pol_stream);
-            if (do_mask) {
-                uint8_t *gmask = args.out.valid_mask + env * cfg.mask_bytes;
-                emit_tile(gmask, bg.mask + (reinterpret_cast<uintptr_t>(gmask) & 15), cfg.mask_bytes, pol_stream);
-            }
-            if (lane == 0) bulk_commit();
-        }
+        const long long next_env = env + total_warps;
+        const bool has_next = next_env < args.num_envs;
+        if (has_next) load_state(next_env, pf);
+        if (do_tile && issue_at == 2) issue_background(env);
 
         bool dirty = false;
         // out-of-line helpers take and return everything by value so that `a` never has to live in local memory
@@ -261,6 +276,7 @@ __global__ void __launch_bounds__(K <= 2 ? 1024 : SX_MAX_THREADS, 1) sx_fused_ke
             if (need_moves) any = regen_moves(viewer);
         }
         if (args.out.player && lane == 0) args.out.player[env] = viewer == 0 ? 1 : -1;
+        if (do_tile && issue_at == 1) issue_background(env);
 
         if ((ops & OP_MASK_1D) != 0) {
             uint8_t *row = args.mask1d + env * cfg.action_size;
@@ -289,9 +305,11 @@ __global__ void __launch_bounds__(K <= 2 ? 1024 : SX_MAX_THREADS, 1) sx_fused_ke
         }
 
         // ---- render: sparse entries on top of the (by now written) background ---------------------------
+        if (do_tile && issue_at == 0) issue_background(env);
         if (do_tile && !(flags & 0x20000u)) {
             if (lane == 0) bulk_wait_all();  // this game's background is in global memory
             __syncwarp();
+            if (flags & 0x80000u) continue;  // experiment: wait but skip the sparse stores
             if (do_po) patch_obs<K>(cfg, m, a, args.out.partial_obs + env * cfg.po_floats, pom, viewer, pol_stream);
             if (do_fo) patch_obs<K>(cfg, m, a, args.out.full_obs + env * cfg.fo_floats, fom, viewer, pol_stream);
             if (do_mask) {
@@ -628,7 +646,8 @@ static int plan_launch(const sx_config *cfg, uint32_t ops, int mode, long long n
     const int max_warps = std::max(1, std::min(attr.maxThreadsPerBlock / 32, 32));
     // Measured on B200: throughput peaks when ~0.4 MB of output per SM is in flight and falls beyond it (more
     // resident warps only lengthen the TMA completion queue), so fewer warps for bigger per-game outputs.
-    const int preferred = tile_bytes <= 8 * 1024 ? 32 : tile_bytes <= 32 * 1024 ? 12 : tile_bytes <= 64 * 1024 ? 8 : 6;
+    const int preferred = tile_bytes <= 8 * 1024 ? 32 : tile_bytes <= 32 * 1024 ? (2 * cfg->dev.n_pieces <= 24 ? 10 : 12)
+                          : tile_bytes <= 64 * 1024 ? 6 : 4;
     int warps = std::min(max_warps, std::max(1, env_int("SX_WARPS", std::min(max_warps, preferred))));
     while (warps > 1 && tile_bytes + warps * warp_bytes > max_smem_optin) --warps;
     const int smem = tile_bytes + warps * warp_bytes;
@@ -809,7 +828,11 @@ extern "C" int sx_step_all(const sx_config *cfg, sx_state st, int64_t num_envs, 
     KernelArgs a;
     base_args(a, st, num_envs, env_base);
     a.actions = actions_d; a.action_format = action_format;
-    a.flags = flags | (uint32_t(env_int("SX_DEBUG", 0)) << 16);  // SX_DEBUG: 1 = skip TMA, 2 = skip sparse stores (experiments)
+    // bits 16+: tuning / experiment switches (SX_DEBUG overrides): 1 skip TMA, 2 skip wait + sparse stores, 4 plain L2
+    // policy, 8 skip sparse stores, 16/32 background issue point.  Sparse boards (Barrage-like) gain from issuing the
+    // background at the top of the game; dense boards need it late so the sparse stores still hit L2 (see kernel).
+    const int tune = env_int("SX_DEBUG", 2 * cfg->dev.n_pieces <= 24 ? 32 : 0);
+    a.flags = (flags & 0xffffu) | (uint32_t(tune) << 16);
     a.out = out;
     a.ops = step_all_ops(out, flags);
     a.setups = setups_d; a.n_setups = n_setups;
