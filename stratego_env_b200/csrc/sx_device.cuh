@@ -150,23 +150,6 @@ __host__ __device__ inline int carve_warp(const DevConfig &cfg, uint8_t *base, W
     return off;
 }
 
-// ---- cp.async (LDGSTS): global -> shared without staging registers -----------------------------------
-__device__ __forceinline__ void cp_async16(void *sdst, const void *gsrc, uint64_t pol)
-{
-    if (!SX_HINT_CPASYNC) {
-        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(uint32_t(__cvta_generic_to_shared(sdst))), "l"(gsrc) : "memory");
-        return;
-    }
-    asm volatile("cp.async.cg.shared.global.L2::cache_hint [%0], [%1], 16, %2;" ::"r"(uint32_t(__cvta_generic_to_shared(sdst))),
-                 "l"(gsrc), "l"(pol)
-                 : "memory");
-}
-__device__ __forceinline__ void cp_async4(void *sdst, const void *gsrc)
-{
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(uint32_t(__cvta_generic_to_shared(sdst))), "l"(gsrc)
-                 : "memory");
-}
-__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
 
 // The block's read-only background images: what a game's outputs look like before the state-dependent
 // entries are added ("empty board" observation after normalisation; all-zero mask).
@@ -174,23 +157,6 @@ struct Tile {
     float *po;      // [N*67] partial observation
     float *fo;      // [N*79] full observation
     uint8_t *mask;  // [mask_bytes + 16] zeros; copies start at mask + (global address & 15)
-};
-
-// row/column of the K consecutive cells a lane owns, computed once per warp (no divisions in the game loop)
-template <int K>
-struct LaneCells {
-    int8_t r[K], c[K];
-    __device__ __forceinline__ void init(const DevConfig &cfg)
-    {
-#pragma unroll
-        for (int k = 0; k < K; ++k) {
-            const int p = lane_id_() * K + k;
-            const int rr = int(__umulhi(uint32_t(p), cfg.magic_C));
-            r[k] = int8_t(rr);
-            c[k] = int8_t(p - rr * cfg.C);
-        }
-    }
-    static __device__ __forceinline__ int lane_id_() { return threadIdx.x & 31; }
 };
 
 __device__ __forceinline__ int lane_id() { return threadIdx.x & 31; }

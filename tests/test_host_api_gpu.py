@@ -257,3 +257,56 @@ def test_illegal_action_flag_and_exception():
     with pytest.raises(ValueError):
         env.step(bad)
     assert torch.equal(env.export_states()[0], before)  # untouched
+
+
+@pytest.mark.parametrize("version,human,chunks", [("barrage", True, 5), ("micro", False, 16), ("fives", False, 1)])
+def test_host_buffer_env_matches_device_path(version, human, chunks):
+    """sx_host_env_* (host actions in, host outputs back, chunked over streams) == the device-resident path"""
+    from stratego_env_b200 import BatchedStrategoEnv, GameVersions, ObservationModes
+    from stratego_env_b200.config import HUMAN_INIT_TABLE
+    from stratego_env_b200.engine import load_setup_table
+    from stratego_env_b200.host_env import HostBufferEnv
+    B = 333  # deliberately not a multiple of the chunk count or the warp count
+    dev = BatchedStrategoEnv({"version": GameVersions(version), "human_inits": human,
+                              "observation_mode": ObservationModes.PARTIALLY_OBSERVABLE},
+                             num_envs=B, seed=77, env_base=4096, auto_reset=True)
+    table = load_setup_table(HUMAN_INIT_TABLE[GameVersions(version)]) if human else None
+    host_env = HostBufferEnv(dev.engine, B, setups=table, seed=77, env_base=4096, n_chunks=chunks)
+    host = host_env.reset()
+    obs = dev.reset()
+    assert np.array_equal(host["valid_mask"].numpy(), obs["valid_actions_mask"].cpu().numpy())
+    assert np.array_equal(_bits(host["partial_obs"].numpy()), _bits(obs["partial_observation"].cpu().numpy()))
+    for _ in range(40):
+        actions = host["next_action"].clone()
+        host = host_env.step(actions)
+        obs, rewards, dones, infos = dev.step(actions.to(dev.device))
+        assert int(host["illegal"].sum()) == 0
+        assert np.array_equal(host["valid_mask"].numpy(), obs["valid_actions_mask"].cpu().numpy())
+        assert np.array_equal(_bits(host["partial_obs"].numpy()), _bits(obs["partial_observation"].cpu().numpy()))
+        assert np.array_equal(host["player"].numpy(), obs["player"].cpu().numpy())
+        assert np.array_equal(host["done"].numpy(), dones.cpu().numpy())
+        assert np.array_equal(host["winner"].numpy(), infos["winner"].cpu().numpy())
+        assert np.array_equal(_bits(host["reward"].numpy()), _bits(rewards[1].cpu().numpy()))
+    host_env.close()
+
+
+@pytest.mark.parametrize("num_envs", [1, 31, 4097])
+def test_odd_batch_sizes(num_envs):
+    """grid tail handling: batch sizes around the warp / block granularity, checked against the oracle"""
+    from oracle.binding import OracleEnvLogic
+    from stratego_env_b200 import BatchedStrategoEnv, GameVersions, ObservationModes
+    from stratego_env_b200.config import VERSION_CONFIGS
+    env = BatchedStrategoEnv({"version": GameVersions.OCTA_BARRAGE, "observation_mode": ObservationModes.BOTH_OBSERVATIONS},
+                             num_envs=num_envs, seed=3, sample_actions=True)
+    cfg = VERSION_CONFIGS[GameVersions.OCTA_BARRAGE]
+    orc = OracleEnvLogic(cfg["rows"], cfg["columns"], cfg["piece_amounts"])
+    obs = env.reset()
+    for _ in range(6):
+        obs, _, _, infos = env.step(obs["sampled_action"])
+    assert not infos["illegal_action"].any().item()
+    dense, player = (x.cpu().numpy() for x in env.export_states())
+    mask, po, fo = (obs[k].cpu().numpy() for k in ("valid_actions_mask", "partial_observation", "full_observation"))
+    for b in sorted({0, num_envs // 2, num_envs - 1}):
+        m_o, po_o, fo_o = orc.current_obs(dense[b], int(player[b]), 3)
+        assert np.array_equal(mask[b], m_o)
+        assert np.array_equal(_bits(po[b]), _bits(po_o)) and np.array_equal(_bits(fo[b]), _bits(fo_o))
