@@ -310,3 +310,36 @@ def test_odd_batch_sizes(num_envs):
         m_o, po_o, fo_o = orc.current_obs(dense[b], int(player[b]), 3)
         assert np.array_equal(mask[b], m_o)
         assert np.array_equal(_bits(po[b]), _bits(po_o)) and np.array_equal(_bits(fo[b]), _bits(fo_o))
+
+
+@pytest.mark.parametrize("version,B", [("barrage", 262144), ("standard", 131072)])
+def test_full_size_step_every_game_vs_oracle(version, B):
+    """BASELINE config 3 size (262 144 Barrage games): after de-phasing, one fused step under full load is
+    re-derived game by game by the oracle -- every mask byte and every observation float.  This is the test
+    that would catch an ordering problem between the TMA background copies and the sparse stores."""
+    from oracle.binding import OracleEnvLogic
+    from stratego_env_b200 import BatchedStrategoEnv, GameVersions, ObservationModes
+    from stratego_env_b200.config import VERSION_CONFIGS
+    env = BatchedStrategoEnv({"version": GameVersions(version), "human_inits": True,
+                              "observation_mode": ObservationModes.PARTIALLY_OBSERVABLE},
+                             num_envs=B, seed=2026, auto_reset=True, sample_actions=True)
+    cfg = VERSION_CONFIGS[GameVersions(version)]
+    orc = OracleEnvLogic(cfg["rows"], cfg["columns"], cfg["piece_amounts"])
+    obs = env.reset()
+    for _ in range(60):
+        obs, _, _, infos = env.step(obs["sampled_action"])
+    assert not infos["illegal_action"].any().item()
+    torch.cuda.synchronize()
+    mask = obs["valid_actions_mask"].cpu().numpy()
+    po = obs["partial_observation"].cpu().numpy().view(np.uint32)
+    chunk = 16384
+    checked = 0
+    for lo in range(0, B, chunk):
+        dense, player = env.engine.export_ref_state(env.state.select(lo, lo + chunk))
+        dense, player = dense.cpu().numpy(), player.cpu().numpy()
+        for b in range(chunk):
+            m_o, po_o, _ = orc.current_obs(dense[b], int(player[b]), 1)
+            if not (np.array_equal(mask[lo + b], m_o) and np.array_equal(po[lo + b], po_o.view(np.uint32))):
+                raise AssertionError("game %d differs from the oracle" % (lo + b))
+            checked += 1
+    assert checked == B
