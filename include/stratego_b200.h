@@ -159,6 +159,17 @@ int sx_step_all(const sx_config *cfg, sx_state st, int64_t num_envs, int64_t env
 int sx_sample_valid(const uint8_t *mask_d, int64_t num_envs, int32_t mask_len, int64_t env_base, uint64_t seed,
                     uint32_t step, int32_t *actions_d, void *stream);
 
+/* Masked-logit action sampling, the step right upstream of sx_step_all in a rollout (replaces the CPU chooser
+ * of examples/basic_game_loop.py:6-32 / README.md:38-65: softmax(logits + log(mask + 1e-8)) + np.random.choice).
+ * Draws actions_d[b] ~ softmax(logits[b] / temperature) restricted to mask[b] != 0 (Gumbel-max, Philox4x32-10
+ * keyed by (seed, env_base + b, step, entry)); invalid entries have probability exactly 0.  logits_d is
+ * [num_envs][n_actions] of logits_dtype; logprob_d (optional) receives log p(action).  actions_d[b] = -1 when a
+ * mask row has no valid entry. */
+enum { SX_DTYPE_F32 = 0, SX_DTYPE_BF16 = 1, SX_DTYPE_F16 = 2 };
+int sx_sample_logits(const void *logits_d, int32_t logits_dtype, const uint8_t *mask_d, int64_t num_envs,
+                     int32_t n_actions, int64_t env_base, uint64_t seed, uint32_t step, float temperature,
+                     int32_t *actions_d, float *logprob_d, void *stream);
+
 /* Kernel/launch facts for the benchmark's roofline accounting. */
 typedef struct {
     int32_t warps_per_block, blocks_per_sm, smem_bytes_per_block, num_sms, grid_blocks, regs_per_thread;

@@ -57,6 +57,7 @@ SYMBOLS = {
     "sx_step": (C.c_int, [_vp, SxState, _i64, _vp, _i32, _u32, SxOutputs, _vp]),
     "sx_step_all": (C.c_int, [_vp, SxState, _i64, _i64, _vp, _i32, _u32, _vp, _i32, _u64, SxOutputs, _vp, _vp]),
     "sx_sample_valid": (C.c_int, [_vp, _i64, _i32, _i64, _u64, _u32, _vp, _vp]),
+    "sx_sample_logits": (C.c_int, [_vp, _i32, _vp, _i64, _i32, _i64, _u64, _u32, C.c_float, _vp, _vp, _vp]),
     "sx_step_all_launch_info": (C.c_int, [_vp, _u32, C.POINTER(SxLaunchInfo)]),
     "sx_host_env_create": (C.c_int, [_vp, _i64, _i64, _u32, _u32, _vp, _i32, _u64, _i32, C.POINTER(_vp)]),
     "sx_host_env_destroy": (None, [_vp]),

@@ -127,6 +127,14 @@ class BatchedStrategoEnv:
                  "illegal_action": out["illegal"]}
         return self._obs(), rewards, dones, infos
 
+    def sample_actions_from_logits(self, logits: torch.Tensor, temperature: float = 1.0, return_logprob: bool = False):
+        """masked-logit sampling for the current observation's mask (one kernel; the policy's logits stay on the
+        GPU).  logits: [num_envs, R*C*A] or [num_envs, R, C, A], float32 / bfloat16 / float16."""
+        self._policy_step = getattr(self, "_policy_step", 0) + 1
+        return self.engine.sample_logits(logits, self.out["valid_mask"], seed=self.seed, step=self._policy_step,
+                                         env_base=self.env_base, temperature=temperature,
+                                         return_logprob=return_logprob)
+
     def observe(self, player: Optional[torch.Tensor] = None, partial=True, full=True, mask=True) -> dict:
         """mask + observations for an arbitrary viewer per game (+1 / -1; default: the player to move)"""
         o = self.engine.observe(self.state, player, partial=partial, full=full, mask=mask)

@@ -222,7 +222,7 @@ __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.a
 // 16-byte aligned body goes out as one TMA bulk copy issued by lane 0 (caller commits/waits) and the
 // <16-byte head and tail as plain word stores; otherwise (odd-sized variants such as 5x5 and 15x15,
 // whose per-env byte counts are not multiples of 16) the tile is copied with plain stores.
-__device__ __noinline__ void emit_tile(uint8_t *gdst, const uint8_t *ssrc, int bytes, uint64_t pol)
+static __device__ __noinline__ void emit_tile(uint8_t *gdst, const uint8_t *ssrc, int bytes, uint64_t pol)
 {
     const int lane = lane_id();
     const uintptr_t g = reinterpret_cast<uintptr_t>(gdst);
@@ -390,7 +390,7 @@ __device__ __forceinline__ void mark_spatial(const DevConfig &cfg, const WarpMem
 
 // Expands m.moves into a 1D mask row in global memory, absolute frame (impl:264-277); facade use only.
 template <int K>
-__device__ __noinline__ void mark_1d_global(const DevConfig *cfgp, const uint2 *moves, int flip, uint8_t *row)
+static __device__ __noinline__ void mark_1d_global(const DevConfig *cfgp, const uint2 *moves, int flip, uint8_t *row)
 {
     const DevConfig &cfg = *cfgp;
     const int lane = lane_id();
@@ -514,7 +514,7 @@ __device__ __forceinline__ void add_capture_inl(const DevConfig &cfg, const Warp
 
 // Out-of-line entry (attacks are 2-4 % of moves): arguments and result by value so that the caller's
 // Aux stays in registers.
-__device__ __noinline__ int add_capture(const DevConfig *cfg, uint16_t *cap, int ncap, int cell, int owner, int type)
+static __device__ __noinline__ int add_capture(const DevConfig *cfg, uint16_t *cap, int ncap, int cell, int owner, int type)
 {
     WarpMem m{};
     m.cap = cap;
@@ -675,7 +675,7 @@ __device__ __forceinline__ void reset_game_inl(const DevConfig &cfg, const WarpM
 }
 
 // Out-of-line entry: re-sets the game staged in the warp slice at `warp_base`, returns the packed aux words.
-__device__ __noinline__ uint4 reset_game(const DevConfig *cfg, uint8_t *warp_base, const uint8_t *setups, int n_setups,
+static __device__ __noinline__ uint4 reset_game(const DevConfig *cfg, uint8_t *warp_base, const uint8_t *setups, int n_setups,
                                          const int32_t *setup_idx, int shuffle, uint2 key, uint64_t gid, uint32_t episode)
 {
     WarpMem m;
@@ -699,7 +699,7 @@ __device__ __forceinline__ ObsMap po_map() { return ObsMap{67, 0, -1, 12, 25, 38
 __device__ __forceinline__ ObsMap fo_map() { return ObsMap{79, 0, 12, 24, 37, 50, 51, 52, 53, 65, 77, 78}; }
 
 // fills a tile with what an empty board looks like after normalisation
-__device__ __noinline__ void fill_background(const DevConfig &cfg, float *tile, const ObsMap om, int first, int stride)
+static __device__ __noinline__ void fill_background(const DevConfig &cfg, float *tile, const ObsMap om, int first, int stride)
 {
     const int total = cfg.N * om.channels;
 #pragma unroll 1

@@ -518,6 +518,7 @@ static int fail(const std::string &msg)
     g_error = msg;
     return -1;
 }
+int sx_set_error(const std::string &msg) { return fail(msg); }  // for the other translation units of the library
 static int cuda_fail(const char *what, cudaError_t e) { return fail(std::string(what) + ": " + cudaGetErrorString(e)); }
 
 extern "C" const char *sx_last_error(void) { return g_error.c_str(); }

@@ -269,6 +269,26 @@ class StrategoEngine:
                                                 step & 0xffffffff, actions.data_ptr(), _stream()), "sx_sample_valid")
         return actions
 
+    def sample_logits(self, logits: torch.Tensor, mask: torch.Tensor, seed: int = 0, step: int = 0, env_base: int = 0,
+                      temperature: float = 1.0, return_logprob: bool = False):
+        """Masked categorical sampling: actions[b] ~ softmax(logits[b] / temperature) over mask[b] != 0
+        (replaces the CPU chooser of examples/basic_game_loop.py:6-32).  logits: float32 / bfloat16 / float16
+        [B, n_actions] (any trailing shape that flattens to it); mask: uint8, same number of entries."""
+        B = mask.shape[0]
+        flat_mask = mask.reshape(B, -1)
+        flat_logits = logits.reshape(B, -1)
+        assert flat_mask.dtype == torch.uint8 and flat_mask.is_contiguous() and flat_logits.is_contiguous()
+        assert flat_logits.shape == flat_mask.shape, (flat_logits.shape, flat_mask.shape)
+        dtype = {torch.float32: 0, torch.bfloat16: 1, torch.float16: 2}[flat_logits.dtype]
+        actions = torch.empty(B, dtype=torch.int32, device=self.device)
+        logprob = torch.empty(B, dtype=torch.float32, device=self.device) if return_logprob else None
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.sx_sample_logits(flat_logits.data_ptr(), dtype, flat_mask.data_ptr(), B,
+                                                 flat_mask.shape[1], env_base, seed & (2 ** 64 - 1), step & 0xffffffff,
+                                                 float(temperature), actions.data_ptr(), _ptr(logprob), _stream()),
+                       "sx_sample_logits")
+        return (actions, logprob) if return_logprob else actions
+
     def launch_info(self, partial=True, full=False, mask=True) -> dict:
         info = _lib.SxLaunchInfo()
         obs = (1 if partial else 0) | (2 if full else 0) | (4 if mask else 0)
