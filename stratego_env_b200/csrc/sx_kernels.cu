@@ -88,14 +88,16 @@ __device__ __noinline__ bool gen_moves_cold(const DevConfig *cfg, uint8_t *warp_
 
 // MODE fixes the op set at compile time so that each hot launch type carries only its own code (the
 // whole fused body is ~290 KB of SASS when everything is runtime-selected, far beyond the I-cache):
-enum { MODE_GENERIC = 0, MODE_STEP_PO_MASK = 1, MODE_STEP_PO_FO_MASK = 2, MODE_STEP_LEAN = 3 };
+enum { MODE_GENERIC = 0, MODE_STEP_PO_MASK = 1, MODE_STEP_PO_FO_MASK = 2, MODE_STEP_LEAN = 3, MODE_MASK = 4, MODE_OBSERVE_PO_MASK = 5 };
 constexpr uint32_t OPS_STEP_BASE = OP_STEP | OP_WRITE_STATE | OP_NEED_MOVES;
 
 __host__ __device__ constexpr uint32_t mode_ops(int mode)
 {
     return mode == MODE_STEP_PO_MASK ? (OPS_STEP_BASE | OP_PO | OP_MASK)
          : mode == MODE_STEP_PO_FO_MASK ? (OPS_STEP_BASE | OP_PO | OP_FO | OP_MASK)
-         : mode == MODE_STEP_LEAN ? OPS_STEP_BASE : 0u;
+         : mode == MODE_STEP_LEAN ? OPS_STEP_BASE
+         : mode == MODE_MASK ? uint32_t(OP_MASK)
+         : mode == MODE_OBSERVE_PO_MASK ? (OP_MASK | OP_PO) : 0u;
 }
 
 #ifndef SX_MAX_THREADS
@@ -108,7 +110,8 @@ __global__ void __launch_bounds__(K <= 2 ? 1024 : SX_MAX_THREADS, 1) sx_fused_ke
     const DevConfig &cfg = args.cfg;
     const int lane = lane_id(), warp = threadIdx.x >> 5, warps_per_block = blockDim.x >> 5;
     const uint32_t ops = MODE == MODE_GENERIC ? args.ops : mode_ops(MODE), flags = args.flags;
-    const int8_t *player_override = MODE == MODE_GENERIC ? args.player_override : nullptr;
+    const int8_t *player_override =
+        (MODE == MODE_GENERIC || MODE == MODE_MASK || MODE == MODE_OBSERVE_PO_MASK) ? args.player_override : nullptr;
     uint8_t *warp_base = smem + args.tile_bytes + size_t(warp) * args.warp_bytes;
     WarpMem m;
     carve_warp(cfg, warp_base, &m);
@@ -593,6 +596,8 @@ static fused_fn fused_for_mode(int mode)
     case MODE_STEP_PO_MASK: return sx_fused_kernel<K, MODE_STEP_PO_MASK>;
     case MODE_STEP_PO_FO_MASK: return sx_fused_kernel<K, MODE_STEP_PO_FO_MASK>;
     case MODE_STEP_LEAN: return sx_fused_kernel<K, MODE_STEP_LEAN>;
+    case MODE_MASK: return sx_fused_kernel<K, MODE_MASK>;
+    case MODE_OBSERVE_PO_MASK: return sx_fused_kernel<K, MODE_OBSERVE_PO_MASK>;
     default: return sx_fused_kernel<K, MODE_GENERIC>;
     }
 }
@@ -609,7 +614,10 @@ static fused_fn fused_for(int k, int mode)
 // the specialised kernel for this launch, if one matches exactly
 static int mode_for(const KernelArgs &a)
 {
-    if (a.player_override || a.reset_mask || a.setup_idx || a.mask1d) return MODE_GENERIC;
+    if (a.reset_mask || a.setup_idx || a.mask1d) return MODE_GENERIC;
+    for (int mode : {MODE_MASK, MODE_OBSERVE_PO_MASK})
+        if (a.ops == mode_ops(mode) && !(a.flags & SX_SAMPLE_NEXT)) return mode;
+    if (a.player_override) return MODE_GENERIC;
     for (int mode : {MODE_STEP_PO_MASK, MODE_STEP_PO_FO_MASK, MODE_STEP_LEAN})
         if (a.ops == mode_ops(mode)) return mode;
     return MODE_GENERIC;
