@@ -345,6 +345,25 @@ def run_gpu_arm(args):
             "clocks": clocks,
             "games_finished": int(stats[0].item()),
         }
+        if world == 1 and args.also:
+            # the other single-GPU configurations of BASELINE.json (configs[1] micro, configs[3] standard): short
+            # device-resident runs in a child process, summarised here so one line shows every workload
+            torch.cuda.empty_cache()
+            line["other_workloads"] = {}
+            for name in [n for n in args.also.split(",") if n and n != args.workload]:
+                try:
+                    child = subprocess.run([sys.executable, os.path.abspath(__file__), "--workload", name, "--steps",
+                                            str(min(args.steps, 30)), "--warmup", str(args.warmup), "--no-e2e",
+                                            "--no-cpu", "--also", ""], capture_output=True, text=True, timeout=600)
+                    d = json.loads(child.stdout.strip().splitlines()[-1])
+                    line["other_workloads"][name] = {
+                        "value": d["value"], "unit": UNIT, "ms_per_step": d["ms_per_step"],
+                        "envs_per_gpu": d["config"]["envs_per_gpu"], "roofline_frac": d["roofline"]["frac"],
+                        "achieved_GBps": d["roofline"]["achieved"],
+                        "algorithmic_bytes_per_env_step": d["roofline"]["algorithmic_bytes_per_env_step"],
+                        "description": d["config"]["description"]}
+                except Exception as exc:  # noqa: BLE001
+                    line["other_workloads"][name] = {"error": str(exc)[:200]}
         if world == 1 and not args.no_cpu:
             line["cpu_baseline"] = {k: v for k, v in cpu_selfplay(args.workload, args.cpu_seconds).items()
                                     if k not in ("seconds", "steps")}
@@ -368,6 +387,8 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=8)
     ap.add_argument("--e2e-envs", type=int, default=None)
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
+    ap.add_argument("--also", default="micro,standard",
+                    help="other workloads summarised in the same line at N=1 (comma list, '' = none)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()
