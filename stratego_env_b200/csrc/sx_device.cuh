@@ -160,6 +160,29 @@ struct Tile {
 };
 
 __device__ __forceinline__ int lane_id() { return threadIdx.x & 31; }
+
+// ---- games per warp ------------------------------------------------------------------------------------
+// A 10x10 board uses all 32 lanes of a warp; the toy variants (3x4 ... 5x5) would leave most lanes idle and
+// replicate the scalar rule logic 32 times for 12-25 cells.  For those, G = 2 or 4 games share a warp: each
+// game owns a contiguous group of L = 32 / G lanes, every warp-level primitive below is restricted to the
+// group's lane mask, and the (identical) instruction stream advances G games at once.
+template <int G>
+struct Grp {
+    static constexpr int GAMES = G;
+    static constexpr int L = 32 / G;  // lanes per game
+    static constexpr int H = L / 2;   // lanes building row lines; the other half builds column lines
+    static __device__ __forceinline__ int lane() { return threadIdx.x & (L - 1); }
+    static __device__ __forceinline__ int index() { return (threadIdx.x & 31) / L; }
+    static __device__ __forceinline__ uint32_t mask()
+    {
+        return G == 1 ? FULL : ((G == 2 ? 0xffffu : 0xffu) << (index() * L));
+    }
+    static __device__ __forceinline__ void sync() { __syncwarp(mask()); }
+    static __device__ __forceinline__ bool any(int pred) { return __any_sync(mask(), pred) != 0; }
+    static __device__ __forceinline__ uint32_t ballot(int pred) { return __ballot_sync(mask(), pred) >> (index() * L); }
+    static __device__ __forceinline__ int shfl(int v, int src) { return __shfl_sync(mask(), v, src, L); }
+    static __device__ __forceinline__ int shfl_up(int v, int delta) { return __shfl_up_sync(mask(), v, delta, L); }
+};
 __device__ __forceinline__ int fast_div(int x, uint32_t magic) { return int(__umulhi(uint32_t(x), magic)); }
 
 // flat cell index in `me`'s frame <-> absolute frame: a 180-degree rotation is index reversal
@@ -222,17 +245,18 @@ __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.a
 // 16-byte aligned body goes out as one TMA bulk copy issued by lane 0 (caller commits/waits) and the
 // <16-byte head and tail as plain word stores; otherwise (odd-sized variants such as 5x5 and 15x15,
 // whose per-env byte counts are not multiples of 16) the tile is copied with plain stores.
+template <class GT>
 static __device__ __noinline__ void emit_tile(uint8_t *gdst, const uint8_t *ssrc, int bytes, uint64_t pol)
 {
-    const int lane = lane_id();
+    const int lane = GT::lane();
     const uintptr_t g = reinterpret_cast<uintptr_t>(gdst);
     const uint32_t s = static_cast<uint32_t>(__cvta_generic_to_shared(ssrc));
     if (((g | s | uint32_t(bytes)) & 3) != 0) {
-        for (int i = lane; i < bytes; i += 32) gdst[i] = ssrc[i];
+        for (int i = lane; i < bytes; i += GT::L) gdst[i] = ssrc[i];
         return;
     }
     if (((g ^ s) & 15) != 0) {
-        for (int i = lane; i < (bytes >> 2); i += 32)
+        for (int i = lane; i < (bytes >> 2); i += GT::L)
             reinterpret_cast<uint32_t *>(gdst)[i] = reinterpret_cast<const uint32_t *>(ssrc)[i];
         return;
     }
@@ -241,21 +265,23 @@ static __device__ __noinline__ void emit_tile(uint8_t *gdst, const uint8_t *ssrc
     const int body = (bytes - head) & ~15;
     const int tail = bytes - head - body;
     if (lane < (head >> 2)) reinterpret_cast<uint32_t *>(gdst)[lane] = reinterpret_cast<const uint32_t *>(ssrc)[lane];
-    if (lane >= 8 && lane - 8 < (tail >> 2)) {
-        const int off = head + body + ((lane - 8) << 2);
+    if (lane >= 4 && lane - 4 < (tail >> 2)) {
+        const int off = head + body + ((lane - 4) << 2);
         *reinterpret_cast<uint32_t *>(gdst + off) = *reinterpret_cast<const uint32_t *>(ssrc + off);
     }
     if (body > 0 && lane == 0) bulk_store(gdst + head, ssrc + head, uint32_t(body), pol);
 }
 
 // ---- occupancy bit-lines in `me`'s frame ------------------------------------------------------------
-// lanes 0..15 build one row each (bit c), lanes 16..31 one column each (bit r); "any" marks pieces and
-// lakes, "enemy" marks the opponent's pieces.  Replaces the per-square ray walk of impl:426-490.
+// the first half of a game's lanes build one row each (bit c), the second half one column each (bit r);
+// "any" marks pieces and lakes, "enemy" marks the opponent's pieces.  Replaces the per-square ray walk of
+// impl:426-490.  Layout of m.lines: any[0..H) rows, any[H..L) columns, enemy at L + the same.
+template <class GT>
 __device__ __forceinline__ void build_lines(const DevConfig &cfg, const WarpMem &m, int me, int flip)
 {
-    const int lane = lane_id();
-    const bool is_row = lane < 16;
-    const int idx = is_row ? lane : lane - 16;
+    const int lane = GT::lane();
+    const bool is_row = lane < GT::H;
+    const int idx = is_row ? lane : lane - GT::H;
     const int count = is_row ? cfg.C : cfg.R;
     const int stride = is_row ? 1 : cfg.C;
     const int base = is_row ? idx * cfg.C : idx;
@@ -269,8 +295,8 @@ __device__ __forceinline__ void build_lines(const DevConfig &cfg, const WarpMem 
         }
     }
     m.lines[lane] = any;
-    m.lines[32 + lane] = enemy;
-    __syncwarp();
+    m.lines[GT::L + lane] = enemy;
+    GT::sync();
 }
 
 // distance a sliding piece can travel from bit `pos` towards higher / lower bits of a line; the last
@@ -323,21 +349,21 @@ __device__ __forceinline__ int dir_base(const DevConfig &cfg, int dir)  // first
 
 // Enumerates the moves of player index `me`, in `me`'s frame, into m.moves.  Returns (warp-uniform)
 // whether any move exists.
-template <int K>
+template <int K, class GT>
 __device__ __forceinline__ bool gen_moves(const DevConfig &cfg, const WarpMem &m, const Aux &a, int me, bool allow_osc)
 {
-    const int lane = lane_id();
+    const int lane = GT::lane();
     if (a.over) {  // impl:414
 #pragma unroll UNROLL_K
         for (int k = 0; k < K; ++k) {
             const int p = lane * K + k;
             if (p < cfg.N) m.moves[p] = make_uint2(0, 0);
         }
-        __syncwarp();
+        GT::sync();
         return false;
     }
     const int flip = me;  // player -1 sees the board rotated
-    build_lines(cfg, m, me, flip);
+    build_lines<GT>(cfg, m, me, flip);
     const Blocked blk = blocked_move(cfg, m, a, me, flip, allow_osc);
     const int b1 = cfg.R - 1, b2 = 2 * b1, b3 = b2 + cfg.C - 1;
     const int blocked_bit = blk.cell < 0 ? 0 : (blk.dir == 0 ? 0 : blk.dir == 1 ? b1 : blk.dir == 2 ? b2 : b3) + blk.dist - 1;
@@ -351,8 +377,8 @@ __device__ __forceinline__ bool gen_moves(const DevConfig &cfg, const WarpMem &m
             const int rank = b & CELL_RANK;
             if (rank != 0 && rank <= SP_MARSHAL && int((b >> 4) & 1) == me) {  // impl:420
                 const int r = fast_div(p, cfg.magic_C), c = p - r * cfg.C;
-                const uint32_t col_any = m.lines[16 + c], col_en = m.lines[48 + c];
-                const uint32_t row_any = m.lines[r], row_en = m.lines[32 + r];
+                const uint32_t col_any = m.lines[GT::H + c], col_en = m.lines[GT::L + GT::H + c];
+                const uint32_t row_any = m.lines[r], row_en = m.lines[GT::L + r];
                 int n0 = ray_up(col_any, col_en, r, cfg.R), n1 = ray_down(col_any, col_en, r);
                 int n2 = ray_up(row_any, row_en, c, cfg.C), n3 = ray_down(row_any, row_en, c);
                 if (rank != SP_SCOUT) { n0 = min(n0, 1); n1 = min(n1, 1); n2 = min(n2, 1); n3 = min(n3, 1); }  // impl:492-499
@@ -364,16 +390,16 @@ __device__ __forceinline__ bool gen_moves(const DevConfig &cfg, const WarpMem &m
             m.moves[p] = make_uint2(uint32_t(bits), uint32_t(bits >> 32));
         }
     }
-    __syncwarp();
-    return __any_sync(FULL, found);
+    GT::sync();
+    return GT::any(found);
 }
 
 // Expands m.moves into the spatial mask [cell][channel]: stores a 1 at every move on top of the zero
 // background at `image` (global memory).
-template <int K>
+template <int K, class GT>
 __device__ __forceinline__ void mark_spatial(const DevConfig &cfg, const WarpMem &m, uint8_t *image, uint64_t pol)
 {
-    const int lane = lane_id();
+    const int lane = GT::lane();
 #pragma unroll UNROLL_K
     for (int k = 0; k < K; ++k) {
         const int p = lane * K + k;
@@ -389,11 +415,11 @@ __device__ __forceinline__ void mark_spatial(const DevConfig &cfg, const WarpMem
 }
 
 // Expands m.moves into a 1D mask row in global memory, absolute frame (impl:264-277); facade use only.
-template <int K>
+template <int K, class GT>
 static __device__ __noinline__ void mark_1d_global(const DevConfig *cfgp, const uint2 *moves, int flip, uint8_t *row)
 {
     const DevConfig &cfg = *cfgp;
-    const int lane = lane_id();
+    const int lane = GT::lane();
     const int b1 = cfg.R - 1, b2 = 2 * b1, b3 = b2 + cfg.C - 1;
 #pragma unroll 1
     for (int k = 0; k < K; ++k) {
@@ -495,37 +521,40 @@ __device__ __forceinline__ bool move_is_legal(const DevConfig &cfg, const WarpMe
 }
 
 // records one captured piece (impl:999-1009) in the capture list; lanes search entries in parallel
+template <class GT>
 __device__ __forceinline__ void add_capture_inl(const DevConfig &cfg, const WarpMem &m, Aux &a, int cell, int owner, int type)
 {
     const uint32_t key = cap_key(cell, owner, type);
-    const int lane = lane_id();
+    const int lane = GT::lane();
     int hit = -1;
-    for (int e = lane; e < a.ncap; e += 32)
+    for (int e = lane; e < a.ncap; e += GT::L)
         if ((uint32_t(m.cap[e]) & 0x1fffu) == key) hit = e;
-    const uint32_t vote = __ballot_sync(FULL, hit >= 0);
+    const bool vote = GT::any(hit >= 0);
     if (vote) {
         if (hit >= 0 && (m.cap[hit] >> 13) < 7) m.cap[hit] = uint16_t(m.cap[hit] + (1u << 13));
     } else if (a.ncap < cfg.cap_stride) {
         if (lane == 0) m.cap[a.ncap] = uint16_t(key);
         a.ncap += 1;
     }
-    __syncwarp();
+    GT::sync();
 }
 
 // Out-of-line entry (attacks are 2-4 % of moves): arguments and result by value so that the caller's
 // Aux stays in registers.
+template <class GT>
 static __device__ __noinline__ int add_capture(const DevConfig *cfg, uint16_t *cap, int ncap, int cell, int owner, int type)
 {
     WarpMem m{};
     m.cap = cap;
     Aux a{};
     a.ncap = ncap;
-    add_capture_inl(*cfg, m, a, cell, owner, type);
+    add_capture_inl<GT>(*cfg, m, a, cell, owner, type);
     return a.ncap;
 }
 
 // impl:897-1028: applies a decoded move for the player to move.  The opponent-stuck and max-turn
 // checks (impl:1031-1043) need the next player's move list and are done by the caller.
+template <class GT>
 __device__ __forceinline__ StepStatus apply_move(const DevConfig &cfg, const WarpMem &m, Aux &a, const Move &mv,
                                                  bool allow_osc, int &attack)
 {
@@ -565,12 +594,12 @@ __device__ __forceinline__ StepStatus apply_move(const DevConfig &cfg, const War
         else if (tie) new_end = 0;
         else new_end = (eb & (CELL_RANK | CELL_OWNER)) | CELL_REVEALED;
     }
-    __syncwarp();
-    if (lane_id() == 0) { m.board[mv.start] = uint8_t(new_start); m.board[mv.end] = uint8_t(new_end); }
-    __syncwarp();
+    GT::sync();
+    if (GT::lane() == 0) { m.board[mv.start] = uint8_t(new_start); m.board[mv.end] = uint8_t(new_end); }
+    GT::sync();
     if (defender != 0) {  // impl:999-1009
-        if (!wins) a.ncap = add_capture(&cfg, m.cap, a.ncap, mv.end, me, rank);
-        if (wins || tie) a.ncap = add_capture(&cfg, m.cap, a.ncap, mv.end, me ^ 1, defender);
+        if (!wins) a.ncap = add_capture<GT>(&cfg, m.cap, a.ncap, mv.end, me, rank);
+        if (wins || tie) a.ncap = add_capture<GT>(&cfg, m.cap, a.ncap, mv.end, me ^ 1, defender);
     }
     // impl:1013-1028: the mover's recent-move record is rebuilt from scratch
     if (defender == 0) {
@@ -588,9 +617,10 @@ __device__ __forceinline__ StepStatus apply_move(const DevConfig &cfg, const War
 
 // ---- setups / reset (impl:213-249, util:13-53, util:241-319) ---------------------------------------
 // own_map[i], i < setup_len: piece code at own-frame cell i (row-major over the usable rows).
+template <class GT>
 __device__ __forceinline__ void place_side(const DevConfig &cfg, const WarpMem &m, const uint8_t *own_map, int side)
 {
-    for (int i = lane_id(); i < cfg.setup_len; i += 32) {
+    for (int i = GT::lane(); i < cfg.setup_len; i += GT::L) {
         const int code = own_map[i];
         if (code == 0) continue;
         const int r = i / cfg.C, c = i - r * cfg.C;
@@ -602,14 +632,15 @@ __device__ __forceinline__ void place_side(const DevConfig &cfg, const WarpMem &
     }
 }
 
+template <class GT>
 __device__ __forceinline__ void shuffle_side(const DevConfig &cfg, const WarpMem &m, uint8_t *perm, uint8_t *own_map,
                                              uint2 key, uint64_t gid, uint32_t episode, int side)
 {
     // util:13-30: shuffle the usable cells, then deal pieces in piece-code order
     const int n = cfg.setup_len;
-    for (int i = lane_id(); i < n; i += 32) { perm[i] = uint8_t(i); own_map[i] = 0; }
-    __syncwarp();
-    if (lane_id() == 0) {
+    for (int i = GT::lane(); i < n; i += GT::L) { perm[i] = uint8_t(i); own_map[i] = 0; }
+    GT::sync();
+    if (GT::lane() == 0) {
         uint4 rnd = make_uint4(0, 0, 0, 0);
         int have = 0;
         uint32_t block = 0;
@@ -626,7 +657,7 @@ __device__ __forceinline__ void shuffle_side(const DevConfig &cfg, const WarpMem
         }
         for (int k = 0; k < cfg.n_pieces; ++k) own_map[perm[k]] = cfg.piece_seq[k];
     }
-    __syncwarp();
+    GT::sync();
 }
 
 struct ResetSource {
@@ -636,20 +667,21 @@ struct ResetSource {
     bool shuffle;
 };
 
+template <class GT>
 __device__ __forceinline__ void reset_game_inl(const DevConfig &cfg, const WarpMem &m, Aux &a, const ResetSource &src,
                                                uint2 key, uint64_t gid)
 {
-    const int lane = lane_id();
-    __syncwarp();
-    for (int i = lane; i < cfg.board_stride; i += 32) m.board[i] = (i < cfg.N && cfg.obstacles[i]) ? uint8_t(CELL_OBST) : uint8_t(0);
-    __syncwarp();
+    const int lane = GT::lane();
+    GT::sync();
+    for (int i = lane; i < cfg.board_stride; i += GT::L) m.board[i] = (i < cfg.N && cfg.obstacles[i]) ? uint8_t(CELL_OBST) : uint8_t(0);
+    GT::sync();
     const uint32_t episode = a.episode;
     if (src.shuffle || src.setups == nullptr) {
         uint8_t *perm = m.scratch, *own_map = m.scratch + cfg.setup_len;
         for (int side = 0; side < 2; ++side) {
-            shuffle_side(cfg, m, perm, own_map, key, gid, episode, side);
-            place_side(cfg, m, own_map, side);
-            __syncwarp();
+            shuffle_side<GT>(cfg, m, perm, own_map, key, gid, episode, side);
+            place_side<GT>(cfg, m, own_map, side);
+            GT::sync();
         }
     } else {
         int i0, i1;
@@ -659,10 +691,10 @@ __device__ __forceinline__ void reset_game_inl(const DevConfig &cfg, const WarpM
             i0 = int(__umulhi(rnd.x, uint32_t(src.n_setups)));  // util:313-314: two independent uniform draws
             i1 = int(__umulhi(rnd.y, uint32_t(src.n_setups)));
         }
-        place_side(cfg, m, src.setups + size_t(i0) * cfg.setup_len, 0);
-        place_side(cfg, m, src.setups + size_t(i1) * cfg.setup_len, 1);
+        place_side<GT>(cfg, m, src.setups + size_t(i0) * cfg.setup_len, 0);
+        place_side<GT>(cfg, m, src.setups + size_t(i1) * cfg.setup_len, 1);
     }
-    __syncwarp();
+    GT::sync();
     a.turn = 0;
     a.max_turns = cfg.max_turns;  // impl:247
     a.over = 0; a.invalid = 0; a.winner = 0;
@@ -675,6 +707,7 @@ __device__ __forceinline__ void reset_game_inl(const DevConfig &cfg, const WarpM
 }
 
 // Out-of-line entry: re-sets the game staged in the warp slice at `warp_base`, returns the packed aux words.
+template <class GT>
 static __device__ __noinline__ uint4 reset_game(const DevConfig *cfg, uint8_t *warp_base, const uint8_t *setups, int n_setups,
                                          const int32_t *setup_idx, int shuffle, uint2 key, uint64_t gid, uint32_t episode)
 {
@@ -683,7 +716,7 @@ static __device__ __noinline__ uint4 reset_game(const DevConfig *cfg, uint8_t *w
     Aux a{};
     a.episode = episode;
     const ResetSource src{setups, n_setups, setup_idx, shuffle != 0};
-    reset_game_inl(*cfg, m, a, src, key, gid);
+    reset_game_inl<GT>(*cfg, m, a, src, key, gid);
     uint32_t w[4];
     aux_pack(a, w);
     return make_uint4(w[0], w[1], w[2], w[3]);
@@ -701,7 +734,7 @@ __device__ __forceinline__ ObsMap fo_map() { return ObsMap{79, 0, 12, 24, 37, 50
 // fills a tile with what an empty board looks like after normalisation
 static __device__ __noinline__ void fill_background(const DevConfig &cfg, float *tile, const ObsMap om, int first, int stride)
 {
-    const int total = cfg.N * om.channels;
+    const int total = (cfg.N + 3) * om.channels;  // + 3 cell rows of alignment slack (see carve_tile)
 #pragma unroll 1
     for (int i = first; i < total; i += stride) {
         const int ch = i % om.channels;
@@ -715,11 +748,11 @@ static __device__ __noinline__ void fill_background(const DevConfig &cfg, float 
 
 // Writes the sparse, state-dependent entries of observer `me`'s observation on top of the background
 // image at `tile` (global memory).
-template <int K>
+template <int K, class GT>
 __device__ __forceinline__ void patch_obs(const DevConfig &cfg, const WarpMem &m, const Aux &a, float *tile,
                                           const ObsMap om, int me, uint64_t pol)
 {
-    const int lane = lane_id(), flip = me, CH = om.channels;
+    const int lane = GT::lane(), flip = me, CH = om.channels;
     const float one = cfg.unit_lut[1];
 #pragma unroll UNROLL_K
     for (int k = 0; k < K; ++k) {
@@ -751,7 +784,7 @@ __device__ __forceinline__ void patch_obs(const DevConfig &cfg, const WarpMem &m
             st_hint(tile + view(cell_abs, flip, cfg.N) * CH + (lane < 2 ? om.own_recent : om.enemy_recent),
                     cfg.recent_lut[code + 3], pol);
     }
-    for (int e = lane; e < a.ncap; e += 32) {
+    for (int e = lane; e < a.ncap; e += GT::L) {
         const uint32_t ent = m.cap[e];
         const int cell_abs = ent & 0xff, owner = (ent >> 8) & 1, type0 = (ent >> 9) & 15, count = int(ent >> 13) + 1;
         st_hint(tile + view(cell_abs, flip, cfg.N) * CH + (owner == me ? om.own_cap : om.enemy_cap) + type0,
@@ -761,11 +794,11 @@ __device__ __forceinline__ void patch_obs(const DevConfig &cfg, const WarpMem &m
 
 // ---- uniform draw over the generated moves (replaces maenv:830-834) ----------------------------------
 // Order = ascending flat spatial index (cell, then channel).
-template <int K>
+template <int K, class GT>
 __device__ __forceinline__ int sample_move(const DevConfig &cfg, const WarpMem &m, bool any_moves, uint32_t rnd)
 {
     if (!any_moves) return cfg.A - 1;  // the noop entry [0,0,A-1]
-    const int lane = lane_id();
+    const int lane = GT::lane();
     int mine = 0;
 #pragma unroll UNROLL_K
     for (int k = 0; k < K; ++k) {
@@ -777,11 +810,11 @@ __device__ __forceinline__ int sample_move(const DevConfig &cfg, const WarpMem &
     }
     int incl = mine;
 #pragma unroll
-    for (int off = 1; off < 32; off <<= 1) {
-        const int v = __shfl_up_sync(FULL, incl, off);
+    for (int off = 1; off < GT::L; off <<= 1) {
+        const int v = GT::shfl_up(incl, off);
         if (lane >= off) incl += v;
     }
-    const int total = __shfl_sync(FULL, incl, 31);
+    const int total = GT::shfl(incl, GT::L - 1);
     const int t = int(__umulhi(rnd, uint32_t(total)));
     int action = 0;
     const bool owner = t >= incl - mine && t < incl;
@@ -803,8 +836,8 @@ __device__ __forceinline__ int sample_move(const DevConfig &cfg, const WarpMem &
             left -= c0 + c1;
         }
     }
-    const uint32_t who = __ballot_sync(FULL, owner);
-    return __shfl_sync(FULL, action, __ffs(who) - 1);
+    const uint32_t who = GT::ballot(owner);
+    return GT::shfl(action, __ffs(who) - 1);
 }
 
 }  // namespace sx

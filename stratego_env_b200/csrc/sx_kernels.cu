@@ -58,9 +58,12 @@ __host__ __device__ inline int carve_tile(const DevConfig &cfg, uint32_t ops, ui
 {
     int off = 0;
     if (t) t->po = reinterpret_cast<float *>(base + off);
-    off += (ops & OP_PO) ? round16(cfg.po_floats * 4) : 0;
+    // three extra cell rows: the image is periodic in the cell (67 or 79 floats = 12 mod 16 bytes), so starting the
+    // copy k rows in gives a source congruent mod 16 to ANY 4-byte aligned destination (5x5 and 15x15 observations
+    // are not multiples of 16 bytes, so their rows in the output tensor are 4-, 8- or 12-byte misaligned)
+    off += (ops & OP_PO) ? round16((cfg.N + 3) * SX_PO_CHANNELS * 4) : 0;
     if (t) t->fo = reinterpret_cast<float *>(base + off);
-    off += (ops & OP_FO) ? round16(cfg.fo_floats * 4) : 0;
+    off += (ops & OP_FO) ? round16((cfg.N + 3) * SX_FO_CHANNELS * 4) : 0;
     if (t) t->mask = base + off;
     off += (ops & OP_MASK) ? round16(cfg.mask_bytes + 16) : 0;
     return off;
@@ -75,7 +78,7 @@ __host__ __device__ inline int carve_tile(const DevConfig &cfg, uint32_t ops, ui
 // and the sparse entries are then stored straight to global memory, where they merge with the freshly
 // written lines in L2.  No warp owns a 30 KB tile, so shared memory no longer limits residency.
 // Arguments and result by value so that the caller's state stays in registers.
-template <int K>
+template <int K, class GT>
 __device__ __noinline__ bool gen_moves_cold(const DevConfig *cfg, uint8_t *warp_base, uint4 auxw, int me)
 {
     WarpMem m;
@@ -83,7 +86,7 @@ __device__ __noinline__ bool gen_moves_cold(const DevConfig *cfg, uint8_t *warp_
     const uint32_t w[4] = {auxw.x, auxw.y, auxw.z, auxw.w};
     Aux a;
     aux_unpack(w, a);
-    return gen_moves<K>(*cfg, m, a, me, false);
+    return gen_moves<K, GT>(*cfg, m, a, me, false);
 }
 
 // MODE fixes the op set at compile time so that each hot launch type carries only its own code (the
@@ -103,12 +106,15 @@ __host__ __device__ constexpr uint32_t mode_ops(int mode)
 #ifndef SX_MAX_THREADS
 #define SX_MAX_THREADS 512
 #endif
-template <int K, int MODE>
+// K = board cells per lane, G = games per warp (Grp<G>): 10x10 -> K 4, G 1; 3x4 / 4x4 -> K 2, G 4.
+template <int K, int MODE, int G>
 __global__ void __launch_bounds__(K <= 2 ? 1024 : SX_MAX_THREADS, 1) sx_fused_kernel(const __grid_constant__ KernelArgs args)
 {
+    using GT = Grp<G>;
     extern __shared__ __align__(16) uint8_t smem[];
     const DevConfig &cfg = args.cfg;
-    const int lane = lane_id(), warp = threadIdx.x >> 5, warps_per_block = blockDim.x >> 5;
+    // `lane` is the lane within this game's group and `warp` the game slot within the block
+    const int lane = GT::lane(), warp = (threadIdx.x >> 5) * G + GT::index(), warps_per_block = (blockDim.x >> 5) * G;
     const uint32_t ops = MODE == MODE_GENERIC ? args.ops : mode_ops(MODE), flags = args.flags;
     const int8_t *player_override =
         (MODE == MODE_GENERIC || MODE == MODE_MASK || MODE == MODE_OBSERVE_PO_MASK) ? args.player_override : nullptr;
@@ -154,21 +160,29 @@ __global__ void __launch_bounds__(K <= 2 ? 1024 : SX_MAX_THREADS, 1) sx_fused_ke
         const uint32_t *gb = reinterpret_cast<const uint32_t *>(args.board + e * cfg.board_stride);
         const uint32_t *gc = reinterpret_cast<const uint32_t *>(args.cap + e * cfg.cap_stride);
 #pragma unroll
-        for (int j = 0; j < 2; ++j) pf.board[j] = lane + 32 * j < board_words ? gb[lane + 32 * j] : 0u;
+        for (int j = 0; j < 2; ++j) pf.board[j] = lane + GT::L * j < board_words ? gb[lane + GT::L * j] : 0u;
 #pragma unroll
-        for (int j = 0; j < 4; ++j) pf.cap[j] = lane + 32 * j < cap_words ? gc[lane + 32 * j] : 0u;
+        for (int j = 0; j < 4; ++j) pf.cap[j] = lane + GT::L * j < cap_words ? gc[lane + GT::L * j] : 0u;
         pf.aux = *reinterpret_cast<const uint4 *>(args.aux + e * 8);
         pf.action = do_step ? args.actions[e] : 0;
     };
     auto issue_background = [&](long long e) {
         if (flags & 0x10000u) return;  // experiment switch
-        if (do_po) emit_tile(reinterpret_cast<uint8_t *>(args.out.partial_obs + e * cfg.po_floats),
-                             reinterpret_cast<const uint8_t *>(bg.po), cfg.po_floats * 4, pol_stream);
-        if (do_fo) emit_tile(reinterpret_cast<uint8_t *>(args.out.full_obs + e * cfg.fo_floats),
-                             reinterpret_cast<const uint8_t *>(bg.fo), cfg.fo_floats * 4, pol_stream);
+        if (do_po) {
+            float *g = args.out.partial_obs + e * cfg.po_floats;
+            const int k = (4 - int((reinterpret_cast<uintptr_t>(g) >> 2) & 3)) & 3;  // k * 12 == misalignment (mod 16)
+            emit_tile<GT>(reinterpret_cast<uint8_t *>(g), reinterpret_cast<const uint8_t *>(bg.po + k * SX_PO_CHANNELS),
+                          cfg.po_floats * 4, pol_stream);
+        }
+        if (do_fo) {
+            float *g = args.out.full_obs + e * cfg.fo_floats;
+            const int k = (4 - int((reinterpret_cast<uintptr_t>(g) >> 2) & 3)) & 3;
+            emit_tile<GT>(reinterpret_cast<uint8_t *>(g), reinterpret_cast<const uint8_t *>(bg.fo + k * SX_FO_CHANNELS),
+                          cfg.fo_floats * 4, pol_stream);
+        }
         if (do_mask) {
             uint8_t *gmask = args.out.valid_mask + e * cfg.mask_bytes;
-            emit_tile(gmask, bg.mask + (reinterpret_cast<uintptr_t>(gmask) & 15), cfg.mask_bytes, pol_stream);
+            emit_tile<GT>(gmask, bg.mask + (reinterpret_cast<uintptr_t>(gmask) & 15), cfg.mask_bytes, pol_stream);
         }
         if (lane == 0) bulk_commit();
     };
@@ -186,20 +200,20 @@ __global__ void __launch_bounds__(K <= 2 ? 1024 : SX_MAX_THREADS, 1) sx_fused_ke
     for (; env < args.num_envs; env += total_warps) {
         const uint64_t gid = uint64_t(args.env_base + env);
         // ---- this game's state has arrived in registers: move it to the working slice, request the next ----
-        __syncwarp();
+        GT::sync();
 #pragma unroll
         for (int j = 0; j < 2; ++j)
-            if (lane + 32 * j < board_words) reinterpret_cast<uint32_t *>(m.board)[lane + 32 * j] = pf.board[j];
+            if (lane + GT::L * j < board_words) reinterpret_cast<uint32_t *>(m.board)[lane + GT::L * j] = pf.board[j];
 #pragma unroll
         for (int j = 0; j < 4; ++j)
-            if (lane + 32 * j < cap_words) reinterpret_cast<uint32_t *>(m.cap)[lane + 32 * j] = pf.cap[j];
+            if (lane + GT::L * j < cap_words) reinterpret_cast<uint32_t *>(m.cap)[lane + GT::L * j] = pf.cap[j];
         const int action = pf.action;
         Aux a;
         {
             const uint32_t w[4] = {pf.aux.x, pf.aux.y, pf.aux.z, pf.aux.w};
             aux_unpack(w, a);
         }
-        __syncwarp();
+        GT::sync();
         const long long next_env = env + total_warps;
         const bool has_next = next_env < args.num_envs;
         if (has_next) load_state(next_env, pf);
@@ -208,8 +222,8 @@ __global__ void __launch_bounds__(K <= 2 ? 1024 : SX_MAX_THREADS, 1) sx_fused_ke
         bool dirty = false;
         // out-of-line helpers take and return everything by value so that `a` never has to live in local memory
         auto do_reset = [&]() {
-            __syncwarp();
-            const uint4 nw = reset_game(&cfg, warp_base, args.setups, args.n_setups,
+            GT::sync();
+            const uint4 nw = reset_game<GT>(&cfg, warp_base, args.setups, args.n_setups,
                                         args.setup_idx ? args.setup_idx + env * 2 : nullptr,
                                         (flags & SX_RESET_RANDOM_SHUFFLE) != 0, args.key, gid, a.episode);
             const uint32_t w[4] = {nw.x, nw.y, nw.z, nw.w};
@@ -218,8 +232,8 @@ __global__ void __launch_bounds__(K <= 2 ? 1024 : SX_MAX_THREADS, 1) sx_fused_ke
         auto regen_moves = [&](int me) -> bool {
             uint32_t w[4];
             aux_pack(a, w);
-            __syncwarp();
-            return gen_moves_cold<K>(&cfg, warp_base, make_uint4(w[0], w[1], w[2], w[3]), me);
+            GT::sync();
+            return gen_moves_cold<K, GT>(&cfg, warp_base, make_uint4(w[0], w[1], w[2], w[3]), me);
         };
         if (MODE == MODE_GENERIC && (ops & OP_RESET) && (args.reset_mask == nullptr || args.reset_mask[env] != 0)) {
             do_reset();
@@ -235,7 +249,7 @@ __global__ void __launch_bounds__(K <= 2 ? 1024 : SX_MAX_THREADS, 1) sx_fused_ke
                 if (regen_moves(mover)) mv.bad = true;
             }
             int attack;
-            status = apply_move(cfg, m, a, mv, allow_osc, attack);
+            status = apply_move<GT>(cfg, m, a, mv, allow_osc, attack);
             dirty |= status != STEP_ILLEGAL;
         }
 
@@ -244,7 +258,7 @@ __global__ void __launch_bounds__(K <= 2 ? 1024 : SX_MAX_THREADS, 1) sx_fused_ke
         if (player_override) viewer = player_override[env] == 1 ? 0 : 1;
         bool any = false;
         const bool have_moves = need_moves && (status == STEP_MOVED || !do_step || do_mask || do_sample || (ops & OP_MASK_1D));
-        if (have_moves) any = gen_moves<K>(cfg, m, a, viewer, false);
+        if (have_moves) any = gen_moves<K, GT>(cfg, m, a, viewer, false);
 
         if (status == STEP_MOVED) {
             if (have_moves && !any && !a.over) { a.over = 1; a.winner = mover == 0 ? 1 : -1; }  // impl:1031-1036
@@ -283,16 +297,16 @@ __global__ void __launch_bounds__(K <= 2 ? 1024 : SX_MAX_THREADS, 1) sx_fused_ke
 
         if ((ops & OP_MASK_1D) != 0) {
             uint8_t *row = args.mask1d + env * cfg.action_size;
-            mark_1d_global<K>(&cfg, m.moves, viewer, row);
+            mark_1d_global<K, GT>(&cfg, m.moves, viewer, row);
             if (!any && lane == 0) row[cfg.action_size - 1] = 1;  // impl:639-640
         }
 
         if ((ops & OP_WRITE_STATE) && dirty) {
             uint32_t *gb = reinterpret_cast<uint32_t *>(args.board + env * cfg.board_stride);
-            for (int i = lane; i < (cfg.board_stride >> 2); i += 32)
+            for (int i = lane; i < (cfg.board_stride >> 2); i += GT::L)
                 st_hint(gb + i, reinterpret_cast<const uint32_t *>(m.board)[i], pol_keep);
             uint32_t *gc = reinterpret_cast<uint32_t *>(args.cap + env * cfg.cap_stride);
-            for (int i = lane; i < (cfg.cap_stride >> 1); i += 32)
+            for (int i = lane; i < (cfg.cap_stride >> 1); i += GT::L)
                 st_hint(gc + i, reinterpret_cast<const uint32_t *>(m.cap)[i], pol_keep);
             if (lane == 0) {
                 uint32_t w[4];
@@ -303,7 +317,7 @@ __global__ void __launch_bounds__(K <= 2 ? 1024 : SX_MAX_THREADS, 1) sx_fused_ke
 
         if (do_sample) {
             const uint4 rnd = philox4x32_10(make_uint4(uint32_t(gid), uint32_t(gid >> 32), RNG_SAMPLE ^ uint32_t(a.turn), a.episode), args.key);
-            const int act = sample_move<K>(cfg, m, any, rnd.x);
+            const int act = sample_move<K, GT>(cfg, m, any, rnd.x);
             if (lane == 0) args.out.next_action[env] = act;
         }
 
@@ -311,17 +325,17 @@ __global__ void __launch_bounds__(K <= 2 ? 1024 : SX_MAX_THREADS, 1) sx_fused_ke
         if (do_tile && issue_at == 0) issue_background(env);
         if (do_tile && !(flags & 0x20000u)) {
             if (lane == 0) bulk_wait_all();  // this game's background is in global memory
-            __syncwarp();
+            GT::sync();
             if (flags & 0x80000u) continue;  // experiment: wait but skip the sparse stores
-            if (do_po) patch_obs<K>(cfg, m, a, args.out.partial_obs + env * cfg.po_floats, pom, viewer, pol_stream);
-            if (do_fo) patch_obs<K>(cfg, m, a, args.out.full_obs + env * cfg.fo_floats, fom, viewer, pol_stream);
+            if (do_po) patch_obs<K, GT>(cfg, m, a, args.out.partial_obs + env * cfg.po_floats, pom, viewer, pol_stream);
+            if (do_fo) patch_obs<K, GT>(cfg, m, a, args.out.full_obs + env * cfg.fo_floats, fom, viewer, pol_stream);
             if (do_mask) {
                 uint8_t *gmask = args.out.valid_mask + env * cfg.mask_bytes;
-                mark_spatial<K>(cfg, m, gmask, pol_stream);
+                mark_spatial<K, GT>(cfg, m, gmask, pol_stream);
                 if (!any && lane == 0) st_hint(gmask + cfg.A - 1, 1u, pol_stream);  // [0,0,A-1], impl:514-515
             }
         }
-        __syncwarp();
+        GT::sync();
     }
 
     if (args.stats) {
@@ -513,6 +527,7 @@ struct sx_config {
     DevConfig dev;
     sx_layout layout;
     int cells_per_lane;  // K
+    int games_per_warp;  // G
 };
 
 static thread_local std::string g_error;
@@ -523,6 +538,12 @@ static int fail(const std::string &msg)
 }
 int sx_set_error(const std::string &msg) { return fail(msg); }  // for the other translation units of the library
 static int cuda_fail(const char *what, cudaError_t e) { return fail(std::string(what) + ": " + cudaGetErrorString(e)); }
+
+static int env_int(const char *name, int fallback)
+{
+    const char *v = std::getenv(name);
+    return (v && *v) ? std::atoi(v) : fallback;
+}
 
 extern "C" const char *sx_last_error(void) { return g_error.c_str(); }
 extern "C" int sx_version(void) { return 1; }
@@ -569,8 +590,13 @@ extern "C" int sx_config_create(const sx_config_desc *desc, sx_config **out)
     std::memcpy(d.recent_lut, desc->recent_lut, sizeof(d.recent_lut));
     std::memcpy(d.unit_lut, desc->unit_lut, sizeof(d.unit_lut));
     for (int i = 0; i < d.N; ++i) d.obstacles[i] = desc->obstacles[i] ? 1 : 0;
-    const int k = (d.N + 31) / 32;
-    c->cells_per_lane = k <= 1 ? 1 : k <= 2 ? 2 : k <= 4 ? 4 : 8;
+    // games per warp: small boards share a warp (each game needs max(R, C) <= lanes / 2 and N <= 2 * lanes)
+    const int side = std::max(d.R, d.C);
+    c->games_per_warp = (side <= 4 && d.N <= 16) ? 4 : (side <= 8 && d.N <= 32) ? 2 : 1;
+    if (env_int("SX_GAMES_PER_WARP", 0) == 1) c->games_per_warp = 1;  // tuning / A-B switch
+    const int lanes = 32 / c->games_per_warp;
+    const int k = (d.N + lanes - 1) / lanes;
+    c->cells_per_lane = k <= 2 ? 2 : k <= 4 ? 4 : 8;
     sx_layout &l = c->layout;
     l.rows = d.R; l.cols = d.C; l.cells = d.N; l.spatial_channels = d.A; l.spatial_actions = d.mask_bytes;
     l.action_size = d.action_size; l.board_stride = d.board_stride; l.aux_stride = 8; l.captured_stride = d.cap_stride;
@@ -589,25 +615,29 @@ extern "C" int sx_config_layout(const sx_config *cfg, sx_layout *out)
 }
 
 typedef void (*fused_fn)(const KernelArgs);
-template <int K>
+template <int K, int G>
 static fused_fn fused_for_mode(int mode)
 {
     switch (mode) {
-    case MODE_STEP_PO_MASK: return sx_fused_kernel<K, MODE_STEP_PO_MASK>;
-    case MODE_STEP_PO_FO_MASK: return sx_fused_kernel<K, MODE_STEP_PO_FO_MASK>;
-    case MODE_STEP_LEAN: return sx_fused_kernel<K, MODE_STEP_LEAN>;
-    case MODE_MASK: return sx_fused_kernel<K, MODE_MASK>;
-    case MODE_OBSERVE_PO_MASK: return sx_fused_kernel<K, MODE_OBSERVE_PO_MASK>;
-    default: return sx_fused_kernel<K, MODE_GENERIC>;
+    case MODE_STEP_PO_MASK: return sx_fused_kernel<K, MODE_STEP_PO_MASK, G>;
+    case MODE_STEP_PO_FO_MASK: return sx_fused_kernel<K, MODE_STEP_PO_FO_MASK, G>;
+    case MODE_STEP_LEAN: return sx_fused_kernel<K, MODE_STEP_LEAN, G>;
+    case MODE_MASK: return sx_fused_kernel<K, MODE_MASK, G>;
+    case MODE_OBSERVE_PO_MASK: return sx_fused_kernel<K, MODE_OBSERVE_PO_MASK, G>;
+    default: return sx_fused_kernel<K, MODE_GENERIC, G>;
     }
 }
-static fused_fn fused_for(int k, int mode)
+// (cells per lane, games per warp) instantiations: (2,4) boards up to 4x4, (2,2) up to 5x5 (both dimensions must fit
+// in half a group's lanes), (2,1) up to 64 cells, (4,1) 10x10, (8,1) 15x15
+static fused_fn fused_for(const sx_config *cfg, int mode)
 {
+    const int k = cfg->cells_per_lane, g = cfg->games_per_warp;
+    if (g == 4) return fused_for_mode<2, 4>(mode);
+    if (g == 2) return fused_for_mode<2, 2>(mode);
     switch (k) {
-    case 1: return fused_for_mode<1>(mode);
-    case 2: return fused_for_mode<2>(mode);
-    case 4: return fused_for_mode<4>(mode);
-    default: return fused_for_mode<8>(mode);
+    case 2: return fused_for_mode<2, 1>(mode);
+    case 4: return fused_for_mode<4, 1>(mode);
+    default: return fused_for_mode<8, 1>(mode);
     }
 }
 
@@ -628,11 +658,6 @@ struct LaunchPlan {
     int warp_bytes, tile_bytes;
 };
 
-static int env_int(const char *name, int fallback)
-{
-    const char *v = std::getenv(name);
-    return (v && *v) ? std::atoi(v) : fallback;
-}
 
 // Block shape: one block per SM with as many warps as the register file allows (SX_WARPS overrides; a
 // tuning aid); the block's shared memory is the background images plus one small slice per warp.
@@ -640,7 +665,7 @@ static int plan_launch(const sx_config *cfg, uint32_t ops, int mode, long long n
 {
     const int warp_bytes = carve_warp(cfg->dev, nullptr, nullptr);
     const int tile_bytes = carve_tile(cfg->dev, ops, nullptr, nullptr);
-    fused_fn fn = fused_for(cfg->cells_per_lane, mode);
+    fused_fn fn = fused_for(cfg, mode);
     int device = 0;
     cudaError_t e = cudaGetDevice(&device);
     if (e != cudaSuccess) return cuda_fail("cudaGetDevice", e);
@@ -658,8 +683,9 @@ static int plan_launch(const sx_config *cfg, uint32_t ops, int mode, long long n
     const int preferred = tile_bytes <= 8 * 1024 ? 32 : tile_bytes <= 32 * 1024 ? (2 * cfg->dev.n_pieces <= 24 ? 10 : 12)
                           : tile_bytes <= 64 * 1024 ? 6 : 4;
     int warps = std::min(max_warps, std::max(1, env_int("SX_WARPS", std::min(max_warps, preferred))));
-    while (warps > 1 && tile_bytes + warps * warp_bytes > max_smem_optin) --warps;
-    const int smem = tile_bytes + warps * warp_bytes;
+    const int games = cfg->games_per_warp;  // each game of a warp has its own slice
+    while (warps > 1 && tile_bytes + warps * games * warp_bytes > max_smem_optin) --warps;
+    const int smem = tile_bytes + warps * games * warp_bytes;
     if (smem > max_smem_optin) return fail("variant does not fit in shared memory");
     int blocks = 0;
     e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks, fn, warps * 32, size_t(smem));
@@ -674,7 +700,7 @@ static int plan_launch(const sx_config *cfg, uint32_t ops, int mode, long long n
     plan->warp_bytes = warp_bytes;
     plan->tile_bytes = tile_bytes;
     const long long grid = (long long)num_sms * blocks;
-    const long long needed = (num_envs + warps - 1) / warps;
+    const long long needed = (num_envs + warps * games - 1) / (warps * games);
     plan->grid = int(std::max(1LL, std::min(grid, needed)));
     return 0;
 }
@@ -688,7 +714,7 @@ static int launch_fused(const sx_config *cfg, KernelArgs &args, cudaStream_t str
     args.cfg = cfg->dev;
     args.warp_bytes = plan.warp_bytes;
     args.tile_bytes = plan.tile_bytes;
-    fused_for(cfg->cells_per_lane, mode)<<<plan.grid, plan.warps_per_block * 32, plan.smem_per_block, stream>>>(args);
+    fused_for(cfg, mode)<<<plan.grid, plan.warps_per_block * 32, plan.smem_per_block, stream>>>(args);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return cuda_fail("sx fused kernel launch", e);
     return 0;
@@ -840,7 +866,7 @@ extern "C" int sx_step_all(const sx_config *cfg, sx_state st, int64_t num_envs, 
     // bits 16+: tuning / experiment switches (SX_DEBUG overrides): 1 skip TMA, 2 skip wait + sparse stores, 4 plain L2
     // policy, 8 skip sparse stores, 16/32 background issue point.  Sparse boards (Barrage-like) gain from issuing the
     // background at the top of the game; dense boards need it late so the sparse stores still hit L2 (see kernel).
-    const int tune = env_int("SX_DEBUG", 2 * cfg->dev.n_pieces <= 24 ? 32 : 0);
+    const int tune = env_int("SX_DEBUG", (cfg->dev.N >= 64 && 2 * cfg->dev.n_pieces <= 24) ? 32 : 0);
     a.flags = (flags & 0xffffu) | (uint32_t(tune) << 16);
     a.out = out;
     a.ops = step_all_ops(out, flags);
