@@ -301,7 +301,7 @@ __global__ void __launch_bounds__(K <= 2 ? 1024 : SX_MAX_THREADS, 1) sx_fused_ke
             if (!any && lane == 0) row[cfg.action_size - 1] = 1;  // impl:639-640
         }
 
-        if ((ops & OP_WRITE_STATE) && dirty) {
+        if ((ops & OP_WRITE_STATE) && dirty && !(flags & 0x400000u)) {  // (0x400000: experiment, no state write-back)
             uint32_t *gb = reinterpret_cast<uint32_t *>(args.board + env * cfg.board_stride);
             for (int i = lane; i < (cfg.board_stride >> 2); i += GT::L)
                 st_hint(gb + i, reinterpret_cast<const uint32_t *>(m.board)[i], pol_keep);
