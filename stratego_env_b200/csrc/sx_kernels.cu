@@ -218,6 +218,12 @@ __global__ void __launch_bounds__(K <= 2 ? 1024 : SX_MAX_THREADS, 1) sx_fused_ke
         const bool has_next = next_env < args.num_envs;
         if (has_next) load_state(next_env, pf);
         if (do_tile && issue_at == 2) issue_background(env);
+        if (flags & 0x800000u) {  // experiment: output skeleton only (no rules): background copy + wait
+            if (do_tile && issue_at != 2) issue_background(env);
+            if (lane == 0) bulk_wait_all();
+            GT::sync();
+            continue;
+        }
 
         bool dirty = false;
         // out-of-line helpers take and return everything by value so that `a` never has to live in local memory
@@ -714,6 +720,10 @@ static int launch_fused(const sx_config *cfg, KernelArgs &args, cudaStream_t str
     args.cfg = cfg->dev;
     args.warp_bytes = plan.warp_bytes;
     args.tile_bytes = plan.tile_bytes;
+    // (Tried and removed: marking the state range as persisting in L2 with an access-policy window.  A pure store
+    // stream loses ~8 % when the ~0.2 KB/game state reads come from DRAM (tools/probes/probe_write.cu), but any L2
+    // set-aside large enough to hold the state takes capacity from the output lines that wait for their sparse
+    // stores: 25-30 % of the maximum was neutral, 35 % and more cost 15-35 %.)
     fused_for(cfg, mode)<<<plan.grid, plan.warps_per_block * 32, plan.smem_per_block, stream>>>(args);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return cuda_fail("sx fused kernel launch", e);

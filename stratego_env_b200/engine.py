@@ -111,10 +111,15 @@ class StrategoEngine:
 
     # ---- buffers -------------------------------------------------------------------------------
     def alloc_state(self, num_envs: int) -> DeviceState:
+        """the three state tensors are views of ONE allocation (one contiguous range to checkpoint or copy)"""
         d, lay = self.device, self.layout
-        return DeviceState(torch.zeros((num_envs, lay.board_stride), dtype=torch.uint8, device=d),
-                           torch.zeros((num_envs, lay.aux_stride), dtype=torch.int16, device=d),
-                           torch.zeros((num_envs, lay.captured_stride), dtype=torch.int16, device=d))
+        board_b, aux_b, cap_b = num_envs * lay.board_stride, num_envs * lay.aux_stride * 2, num_envs * lay.captured_stride * 2
+        pad = lambda n: (n + 255) // 256 * 256  # noqa: E731
+        buf = torch.zeros(pad(board_b) + pad(aux_b) + pad(cap_b), dtype=torch.uint8, device=d)
+        board = buf[:board_b].view(num_envs, lay.board_stride)
+        aux = buf[pad(board_b):pad(board_b) + aux_b].view(torch.int16).view(num_envs, lay.aux_stride)
+        cap = buf[pad(board_b) + pad(aux_b):pad(board_b) + pad(aux_b) + cap_b].view(torch.int16).view(num_envs, lay.captured_stride)
+        return DeviceState(board, aux, cap)
 
     def alloc_outputs(self, num_envs: int, partial=True, full=False, mask=True, sample=False) -> dict:
         d, R, Cc = self.device, self.rows, self.columns

@@ -51,14 +51,16 @@ __global__ void k_tma(uint8_t *p, size_t n_tiles, int tile) {
 }
 // the engine's output layout: per game a 26 800 B observation (16 B aligned) and a 3 700 B mask row (4 B aligned),
 // written with the same TMA bulk + head/tail word stores, nothing else (no logic, no sparse entries)
-__global__ void k_layout(uint8_t *obs, uint8_t *mask, size_t n_envs, int obs_bytes, int mask_bytes, int wait_read) {
+__global__ void k_layout(uint8_t *obs, uint8_t *mask, size_t n_envs, int obs_bytes, int mask_bytes, int wait_read, const uint32_t *state = nullptr, uint32_t *sink = nullptr) {
     extern __shared__ __align__(128) uint8_t smem[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, wpb = blockDim.x >> 5;
     for (int i = threadIdx.x * 16; i < obs_bytes + mask_bytes + 32; i += blockDim.x * 16) *reinterpret_cast<uint4 *>(smem + i) = make_uint4(0, 0, 0, 0);
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     __syncthreads();
     const uint32_t s_obs = (uint32_t)__cvta_generic_to_shared(smem), s_mask = s_obs + ((obs_bytes + 15) & ~15);
+    uint32_t acc = 0;
     for (size_t e = blockIdx.x * (size_t)wpb + warp; e < n_envs; e += (size_t)gridDim.x * wpb) {
+        if (state) acc += state[e * 40 + lane] + state[n_envs * 40 + e * 4 + (lane & 3)];  // ~176 B of per-game state reads
         uint8_t *go = obs + e * obs_bytes, *gm = mask + e * mask_bytes;
         const int head = int((16 - (reinterpret_cast<uintptr_t>(gm) & 15)) & 15), body = (mask_bytes - head) & ~15, tail = mask_bytes - head - body;
         if (lane < (head >> 2)) reinterpret_cast<uint32_t *>(gm)[lane] = 0;
@@ -72,6 +74,7 @@ __global__ void k_layout(uint8_t *obs, uint8_t *mask, size_t n_envs, int obs_byt
         }
         __syncwarp();
     }
+    if (sink && acc == 0x12345678u) sink[0] = acc;
 }
 __global__ void k_copy(const uint4 *a, uint4 *b, size_t n) {
     for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) b[i] = a[i];
@@ -117,6 +120,10 @@ int main() {
         for (int wpb : {4, 8, 12, 16}) for (int wr : {1, 0}) {
             char nm[96]; snprintf(nm, 96, "engine layout obs26800+mask3700 W=%d wait=%s", wpb, wr ? "read" : "full");
             RUN(nm, (double)n_envs * (ob + mb), (k_layout<<<148, wpb * 32, 32768>>>(a, mask, n_envs, ob, mb, wr)));
+            if (!wr) {
+                snprintf(nm, 96, "  + 176 B/game state reads        W=%d", wpb);
+                RUN(nm, (double)n_envs * (ob + mb), (k_layout<<<148, wpb * 32, 32768>>>(a, mask, n_envs, ob, mb, wr, (const uint32_t *)(b + (4ull << 30)), (uint32_t *)(b + (6ull << 30)))));
+            }
         }
     }
     RUN("copy ld.v4/st.v4 grid=148x8", 2.0 * bytes, (k_copy<<<148 * 8, 256>>>((const uint4 *)a, (uint4 *)b, n16)));
