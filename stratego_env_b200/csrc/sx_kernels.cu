@@ -1,10 +1,11 @@
 // sx_kernels.cu -- sm_100a kernels and C ABI of the B200 Stratego engine (include/stratego_b200.h).
 //
-// One persistent warp per game.  The fused kernel stages a game's compact state in shared memory,
-// applies the action, generates the next player's move mask with occupancy bit-lines, renders the
-// observation as "constant background tile + sparse patches" in shared memory and hands the tile to
-// the TMA engine (cp.async.bulk shared->global), so the ~30 KB per env-step of output costs one
-// instruction instead of ~1900 vector stores.  No tensor cores, no CPU fallback.
+// One persistent warp (or lane group, for the toy boards) per game.  The fused kernel stages a game's compact
+// state in shared memory, applies the action, generates the next player's moves with occupancy bit-lines, and
+// renders the outputs as "constant background image + sparse entries": the block's read-only background images
+// go to HBM through the TMA engine (cp.async.bulk shared->global, ~30 KB per game for three instructions), the
+// 50-250 state-dependent entries follow as plain stores that merge in L2.  No tensor cores, no CPU fallback.
+// DESIGN.md section 3 has the design, the measurements behind each choice and the dead ends.
 #include <cuda_runtime.h>
 
 #include <algorithm>
@@ -22,7 +23,7 @@ namespace sx {
 
 enum : uint32_t {
     OP_STEP = 1,         // decode + apply args.actions
-    OP_MASK = 2,         // spatial mask tile -> out.valid_mask
+    OP_MASK = 2,         // spatial mask -> out.valid_mask
     OP_PO = 4,           // partial observation -> out.partial_obs
     OP_FO = 8,           // full observation -> out.full_obs
     OP_RESET = 16,       // re-set envs selected by reset_mask before anything else
@@ -40,7 +41,7 @@ struct KernelArgs {
     const int32_t *actions;
     int action_format;
     const int8_t *player_override;
-    uint32_t flags, ops;
+    uint32_t flags, ops;  // flags: SX_* of the header in the low 16 bits, tuning / experiment switches above (sx_step_all)
     sx_outputs out;
     uint8_t *mask1d;
     const uint8_t *setups;
@@ -49,7 +50,7 @@ struct KernelArgs {
     const uint8_t *reset_mask;
     uint2 key;
     long long *stats;
-    int warp_bytes;  // shared-memory slice of one warp (game state + scratch)
+    int warp_bytes;  // shared-memory slice of one game (state + move sets + scratch)
     int tile_bytes;  // the block's background images (0 = this launch renders nothing)
 };
 
