@@ -188,9 +188,16 @@ void sx_host_env_destroy(sx_host_env *env);
 /* host pointers; pinned memory recommended.  reset fills the outputs for the first player. */
 int sx_host_env_reset(sx_host_env *env, sx_outputs host_out);
 int sx_host_env_step(sx_host_env *env, const int32_t *actions_host, sx_outputs host_out);
+/* same with an explicit action format (SX_ACTION_1D for maenv.step(..., is_spatial_index=False)) and per-call
+ * flags (e.g. SX_ALLOW_OSCILLATION) instead of the ones given at creation */
+int sx_host_env_step_ex(sx_host_env *env, const int32_t *actions_host, int32_t action_format, uint32_t flags,
+                        sx_outputs host_out);
 /* device-resident variant used for the kernel-only measurement: no host copies */
 int sx_host_env_step_device(sx_host_env *env, int32_t use_sampled_actions);
 int sx_host_env_sync(sx_host_env *env);
+/* device pointers of the object's state (for sx_import_ref_state / sx_export_ref_state / sx_observe on it, e.g.
+ * maenv's initial_state_override) and, optionally, of its device-side output buffers */
+int sx_host_env_state(sx_host_env *env, sx_state *state_out, sx_outputs *device_outputs_out);
 
 #ifdef __cplusplus
 }

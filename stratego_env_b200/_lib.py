@@ -63,8 +63,10 @@ SYMBOLS = {
     "sx_host_env_destroy": (None, [_vp]),
     "sx_host_env_reset": (C.c_int, [_vp, SxOutputs]),
     "sx_host_env_step": (C.c_int, [_vp, _vp, SxOutputs]),
+    "sx_host_env_step_ex": (C.c_int, [_vp, _vp, _i32, _u32, SxOutputs]),
     "sx_host_env_step_device": (C.c_int, [_vp, _i32]),
     "sx_host_env_sync": (C.c_int, [_vp]),
+    "sx_host_env_state": (C.c_int, [_vp, C.POINTER(SxState), C.POINTER(SxOutputs)]),
 }
 
 _lib = None

@@ -12,6 +12,8 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <map>
+#include <mutex>
 #include <new>
 #include <string>
 #include <vector>
@@ -530,11 +532,20 @@ __global__ void sx_sample_kernel(const uint8_t *mask, long long num_envs, int ma
 // =====================================================================================================
 using namespace sx;
 
+struct LaunchPlan {
+    int warps_per_block, blocks_per_sm, smem_per_block, num_sms, grid, regs;
+    int warp_bytes, tile_bytes;
+};
+
 struct sx_config {
     DevConfig dev;
     sx_layout layout;
     int cells_per_lane;  // K
     int games_per_warp;  // G
+    // launch shapes already worked out, keyed by (device, ops, mode): the occupancy / attribute queries cost tens
+    // of microseconds, which matters for the one-game API
+    mutable std::mutex plan_mutex;
+    mutable std::map<uint64_t, LaunchPlan> plans;
 };
 
 static thread_local std::string g_error;
@@ -660,15 +671,35 @@ static int mode_for(const KernelArgs &a)
     return MODE_GENERIC;
 }
 
-struct LaunchPlan {
-    int warps_per_block, blocks_per_sm, smem_per_block, num_sms, grid, regs;
-    int warp_bytes, tile_bytes;
-};
 
 
 // Block shape: one block per SM with as many warps as the register file allows (SX_WARPS overrides; a
 // tuning aid); the block's shared memory is the background images plus one small slice per warp.
+static int plan_launch_uncached(const sx_config *cfg, uint32_t ops, int mode, long long num_envs, LaunchPlan *plan);
+
 static int plan_launch(const sx_config *cfg, uint32_t ops, int mode, long long num_envs, LaunchPlan *plan)
+{
+    int device = 0;
+    cudaError_t e = cudaGetDevice(&device);
+    if (e != cudaSuccess) return cuda_fail("cudaGetDevice", e);
+    const uint64_t key = (uint64_t(uint32_t(device)) << 40) | (uint64_t(ops) << 8) | uint64_t(mode);
+    {
+        std::lock_guard<std::mutex> lock(cfg->plan_mutex);
+        auto it = cfg->plans.find(key);
+        if (it == cfg->plans.end()) {
+            LaunchPlan full;
+            if (int rc = plan_launch_uncached(cfg, ops, mode, 1LL << 40, &full)) return rc;
+            it = cfg->plans.emplace(key, full).first;
+        }
+        *plan = it->second;
+    }
+    const long long per_block = (long long)plan->warps_per_block * cfg->games_per_warp;
+    const long long needed = (num_envs + per_block - 1) / per_block;
+    plan->grid = int(std::max(1LL, std::min((long long)plan->num_sms * plan->blocks_per_sm, needed)));
+    return 0;
+}
+
+static int plan_launch_uncached(const sx_config *cfg, uint32_t ops, int mode, long long num_envs, LaunchPlan *plan)
 {
     const int warp_bytes = carve_warp(cfg->dev, nullptr, nullptr);
     const int tile_bytes = carve_tile(cfg->dev, ops, nullptr, nullptr);
@@ -1044,6 +1075,14 @@ static int copy_outputs(const sx_host_env *h, const sx_outputs &host, int64_t lo
     return e == cudaSuccess ? 0 : cuda_fail("sx_host_env D2H", e);
 }
 
+extern "C" int sx_host_env_state(sx_host_env *env, sx_state *state_out, sx_outputs *device_outputs_out)
+{
+    if (!env || !state_out) return fail("sx_host_env_state: null argument");
+    *state_out = env->st;
+    if (device_outputs_out) *device_outputs_out = env->dev;
+    return 0;
+}
+
 extern "C" int sx_host_env_sync(sx_host_env *env)
 {
     if (!env) return fail("sx_host_env_sync: null env");
@@ -1077,8 +1116,9 @@ extern "C" int sx_host_env_reset(sx_host_env *h, sx_outputs host_out)
 }
 
 static int host_env_step_impl(sx_host_env *h, const int32_t *actions_host, const int32_t *actions_dev_src,
-                              const sx_outputs *host_out)
+                              const sx_outputs *host_out, int action_format = SX_ACTION_SPATIAL, int64_t flags = -1)
 {
+    const uint32_t step_flags = flags < 0 ? h->flags : uint32_t(flags);
     for (int c = 0; c < h->n_chunks; ++c) {
         const int64_t lo = h->num_envs * c / h->n_chunks, hi = h->num_envs * (c + 1) / h->n_chunks;
         cudaStream_t s = h->streams[c % h->streams.size()];
@@ -1088,7 +1128,7 @@ static int host_env_step_impl(sx_host_env *h, const int32_t *actions_host, const
                                             cudaMemcpyHostToDevice, s);
             if (e != cudaSuccess) return cuda_fail("sx_host_env H2D", e);
         }
-        if (int rc = sx_step_all(h->cfg, offset_state(h, lo), hi - lo, h->env_base + lo, acts, SX_ACTION_SPATIAL, h->flags,
+        if (int rc = sx_step_all(h->cfg, offset_state(h, lo), hi - lo, h->env_base + lo, acts, action_format, step_flags,
                                  h->setups_d, h->n_setups, h->seed, offset_outputs(h->cfg->dev, h->dev, lo), h->stats_d, s))
             return rc;
         if (host_out)
@@ -1101,6 +1141,15 @@ extern "C" int sx_host_env_step(sx_host_env *h, const int32_t *actions_host, sx_
 {
     if (!h || !actions_host) return fail("sx_host_env_step: null argument");
     if (int rc = host_env_step_impl(h, actions_host, nullptr, &host_out)) return rc;
+    return sx_host_env_sync(h);
+}
+
+extern "C" int sx_host_env_step_ex(sx_host_env *h, const int32_t *actions_host, int32_t action_format, uint32_t flags,
+                                   sx_outputs host_out)
+{
+    if (!h || !actions_host) return fail("sx_host_env_step_ex: null argument");
+    if (action_format != SX_ACTION_SPATIAL && action_format != SX_ACTION_1D) return fail("sx_host_env_step_ex: unknown action format");
+    if (int rc = host_env_step_impl(h, actions_host, nullptr, &host_out, action_format, int64_t(flags))) return rc;
     return sx_host_env_sync(h);
 }
 

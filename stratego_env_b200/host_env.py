@@ -75,6 +75,20 @@ class HostBufferEnv:
                        "sx_host_env_step")
         return self.host
 
+    def step_ex(self, one_d: bool = False, flags: int = 0) -> dict:
+        """one step of self.actions with an explicit action format / per-call flags (used by the one-game API)"""
+        with torch.cuda.device(self.engine.device):
+            _lib.check(self.engine.lib.sx_host_env_step_ex(
+                self._handle, self.actions.data_ptr(), _lib.SX_ACTION_1D if one_d else _lib.SX_ACTION_SPATIAL,
+                int(flags), self._out), "sx_host_env_step_ex")
+        return self.host
+
+    def device_state(self) -> "RawDeviceState":
+        """the object's device-resident state, usable with StrategoEngine.reset / import / export / observe"""
+        st = _lib.SxState()
+        _lib.check(self.engine.lib.sx_host_env_state(self._handle, C.byref(st), None), "sx_host_env_state")
+        return RawDeviceState(st, self.num_envs, self)
+
     def close(self):
         if self._handle:
             self.engine.lib.sx_host_env_destroy(self._handle)
@@ -85,3 +99,13 @@ class HostBufferEnv:
             self.close()
         except Exception:  # noqa: BLE001
             pass
+
+
+class RawDeviceState:
+    """state tensors owned by the library (sx_host_env), addressed by raw device pointers"""
+
+    def __init__(self, struct, num_envs, owner):
+        self._struct, self.num_envs, self._owner = struct, int(num_envs), owner  # owner keeps the buffers alive
+
+    def as_struct(self):
+        return self._struct

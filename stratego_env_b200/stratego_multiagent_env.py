@@ -19,7 +19,9 @@ import torch
 
 from . import setups as _setups
 from .config import HUMAN_INIT_TABLE, VERSION_CONFIGS, as_version
+from . import _lib
 from .engine import StrategoEngine, load_setup_table
+from .host_env import HostBufferEnv
 from .enums import GameVersions, ObservationComponents, ObservationModes
 from .spaces import Box, Dict, Discrete
 from .stratego_procedural_env import StrategoProceduralEnv
@@ -98,7 +100,13 @@ class StrategoMultiAgentEnv:
         self._dev = self._engine.device
         self._table = (self._engine.upload_setups(load_setup_table(HUMAN_INIT_TABLE[env_config['version']]))
                        if self._human_inits else None)
-        self._st = self._engine.alloc_state(1)
+        # one game held by the library's host-buffer object: a step is ONE C call (H2D action -> fused kernel -> D2H
+        # of the outputs into pinned memory -> sync), which keeps the per-step overhead below the reference's
+        self._henv = HostBufferEnv(self._engine, 1, setups=None, partial=self._want_po, full=self._want_fo, mask=True,
+                                   auto_reset=False, sample_actions=False, n_chunks=1)
+        self._st = self._henv.device_state()
+        self._host = {k: t.numpy() for k, t in self._henv.host.items()}   # zero-copy views of the pinned outputs
+        self._action_slot = self._henv.actions.numpy()
         self._out = self._engine.alloc_outputs(1, partial=self._want_po, full=self._want_fo, mask=True)
         self._fixed_setup = None
         if env_config['same_start_pos_everytime']:
@@ -162,11 +170,14 @@ class StrategoMultiAgentEnv:
 
     # ---- observations (maenv:447-497) -----------------------------------------------------------------
     def _obs_dict(self, out, player):
-        d = {ObservationComponents.VALID_ACTIONS_MASK.value: out["valid_mask"][0].cpu().numpy().astype(np.int64)}
+        """out: device tensors (engine.observe) or the numpy views of the pinned step outputs; returns fresh arrays"""
+        def host(x):
+            return x[0].copy() if isinstance(x, np.ndarray) else x[0].cpu().numpy()
+        d = {ObservationComponents.VALID_ACTIONS_MASK.value: host(out["valid_mask"]).astype(np.int64)}
         if self._want_po:
-            d[ObservationComponents.PARTIAL_OBSERVATION.value] = out["partial_obs"][0].cpu().numpy()
+            d[ObservationComponents.PARTIAL_OBSERVATION.value] = host(out["partial_obs"])
         if self._want_fo:
-            d[ObservationComponents.FULL_OBSERVATION.value] = out["full_obs"][0].cpu().numpy()
+            d[ObservationComponents.FULL_OBSERVATION.value] = host(out["full_obs"])
         if self.observation_includes_internal_state:
             viewer = torch.tensor([player], dtype=torch.int8)
             d[ObservationComponents.INTERNAL_STATE.value] = \
@@ -228,10 +239,11 @@ class StrategoMultiAgentEnv:
             action = int(self.base_env.get_action_1d_index_from_player_perspective(action_index=action,
                                                                                    player=self.player))
 
-        actions = torch.tensor([action], dtype=torch.int32, device=self._dev)
-        out = self._engine.step_all(self._st, actions, self._out, one_d=not is_spatial_index,
-                                    allow_piece_oscillation=allow_piece_oscillation)
-        illegal, done, winner, invalid = (int(out[k].item()) for k in ("illegal", "done", "winner", "ending_invalid"))
+        self._action_slot[0] = action
+        self._henv.step_ex(one_d=not is_spatial_index,
+                           flags=_lib.SX_ALLOW_OSCILLATION if allow_piece_oscillation else 0)
+        out = self._host
+        illegal, done, winner, invalid = (int(out[k][0]) for k in ("illegal", "done", "winner", "ending_invalid"))
         if illegal:
             raise ValueError("Couldn't get the next state because the move wasn't valid.")  # impl:902
         self._state_cache = None
