@@ -134,37 +134,48 @@ def physical_gpu_index(local_rank):
 # ---------------------------------------------------------------------------------------------------------
 # CPU legs (oracle/ = the checker; allowed here only as the reported CPU baseline / reference arm)
 # ---------------------------------------------------------------------------------------------------------
-def cpu_selfplay(workload, budget_s, threads=None):
-    """Random-valid self-play of the C restatement of the reference on `threads` host threads; one
-    independent env per work item, same loop as examples/basic_game_loop.py:34-63."""
-    from oracle import binding
-    from stratego_env_b200.config import VERSION_CONFIGS, as_version, obstacle_map
-    from stratego_env_b200.engine import load_setup_table
-    w = WORKLOADS[workload]
-    cfg = VERSION_CONFIGS[as_version(w["version"])]
-    table = load_setup_table(w["table"]) if w["table"] else None
-    threads = threads or os.cpu_count() or 1
-    obs_mode = 3 if w["full"] else 1
+class CpuSelfplay:
+    """Random-valid self-play of the C restatement of the reference on all host threads: independent envs, the
+    loop of examples/basic_game_loop.py:34-63 (oracle/stratego_oracle.c so_selfplay).  Calibrated once; every
+    run() is one bounded sample of the workload."""
 
-    def run(n_envs, steps_per_env):
+    def __init__(self, workload, threads=None):
+        from oracle import binding
+        from stratego_env_b200.config import VERSION_CONFIGS, as_version, obstacle_map
+        from stratego_env_b200.engine import load_setup_table
+        w = WORKLOADS[workload]
+        self.binding = binding
+        self.cfg = VERSION_CONFIGS[as_version(w["version"])]
+        self.obstacles = obstacle_map(self.cfg)
+        self.table = load_setup_table(w["table"]) if w["table"] else None
+        self.threads = threads or os.cpu_count() or 1
+        self.obs_mode = 3 if w["full"] else 1
+        self.per_env = 2000
+        steps, _, dt = self._run(self.threads * 2, 500)  # calibration (also warms caches)
+        self.rate = steps / dt
+
+    def _run(self, n_envs, steps_per_env):
+        cfg = self.cfg
         t0 = time.perf_counter()
-        steps, games, _ = binding.selfplay(cfg["rows"], cfg["columns"], cfg["max_turns"],
-                                           cfg["initial_state_usable_rows"], cfg["piece_amounts"], obstacle_map(cfg),
-                                           table, table is None, obs_mode, n_envs, steps_per_env, seed=1234,
-                                           n_threads=threads)
+        steps, games, _ = self.binding.selfplay(cfg["rows"], cfg["columns"], cfg["max_turns"],
+                                                cfg["initial_state_usable_rows"], cfg["piece_amounts"], self.obstacles,
+                                                self.table, self.table is None, self.obs_mode, n_envs, steps_per_env,
+                                                seed=1234, n_threads=self.threads)
         return steps, games, time.perf_counter() - t0
 
-    steps, _, dt = run(threads * 2, 500)  # calibration (also warms caches)
-    rate = steps / dt
-    per_env = 2000
-    n_envs = max(threads * 2, int(rate * budget_s / per_env))
-    n_envs = (n_envs + threads - 1) // threads * threads
-    steps, games, dt = run(n_envs, per_env)
-    return {"value": steps / dt, "unit": UNIT, "cores": threads, "kind": "port",
-            "sample": "%d independent envs x %d steps (%d games) of the same workload, %.1f s wall, oracle/ C "
-                      "restatement of the reference (the reference itself is Python+numba and cannot travel to "
-                      "the GPU box)" % (n_envs, per_env, games, dt),
-            "seconds": dt, "steps": steps}
+    def run(self, budget_s):
+        n_envs = max(self.threads * 2, int(self.rate * budget_s / self.per_env))
+        n_envs = (n_envs + self.threads - 1) // self.threads * self.threads
+        steps, games, dt = self._run(n_envs, self.per_env)
+        return {"value": steps / dt, "unit": UNIT, "cores": self.threads, "kind": "port",
+                "sample": "%d independent envs x %d steps (%d games) of the same workload, %.1f s wall, oracle/ C "
+                          "restatement of the reference (the reference itself is Python+numba and cannot travel to "
+                          "the GPU box)" % (n_envs, self.per_env, games, dt),
+                "seconds": dt, "steps": steps}
+
+
+def cpu_selfplay(workload, budget_s, threads=None):
+    return CpuSelfplay(workload, threads).run(budget_s)
 
 
 def run_reference_arm(args):
@@ -172,12 +183,14 @@ def run_reference_arm(args):
     if rank != 0:
         return 0
     w = WORKLOADS[args.workload]
-    per_step_budget = max(1.0, min(20.0, 120.0 / max(1, args.steps + args.warmup)))
+    # every "step" is one bounded sample; the whole run stays within a few minutes whatever --steps is
+    per_step_budget = max(0.5, min(20.0, 100.0 / max(1, args.steps + args.warmup)))
+    runner = CpuSelfplay(args.workload)
     for _ in range(args.warmup):
-        cpu_selfplay(args.workload, per_step_budget)
+        runner.run(per_step_budget)
     total_steps, total_s, last = 0, 0.0, None
     for _ in range(args.steps):
-        last = cpu_selfplay(args.workload, per_step_budget)
+        last = runner.run(per_step_budget)
         total_steps += last["steps"]
         total_s += last["seconds"]
     value = total_steps / total_s
@@ -186,7 +199,8 @@ def run_reference_arm(args):
         "warmup": args.warmup, "ms_per_step": 1e3 * total_s / max(1, args.steps), "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
         "config": {"workload": args.workload, "description": w["desc"]},
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": last["cores"], "kind": "port", "sample": last["sample"]},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": last["cores"], "kind": "port",
+                         "sample": "%d samples; each: %s" % (args.steps, last["sample"])},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
