@@ -32,6 +32,8 @@ extern "C" {
 
 #define SX_PO_CHANNELS 67 /* impl:1332 */
 #define SX_FO_CHANNELS 79 /* impl:1227 */
+#define SX_PO_CHANNELS_ORIGINAL 32 /* impl:1148, deprecated obs_channel_mode='original' */
+#define SX_FO_CHANNELS_ORIGINAL 33 /* impl:1070 */
 #define SX_NUM_STATE_LAYERS 34 /* impl:109 */
 #define SX_MAX_CAPTURE_COUNT 8
 
@@ -53,7 +55,16 @@ typedef struct {
                                      row-mirrored (human tables, util:241-275) */
     int32_t capture_capacity;     /* capture-list entries per game; 0 = 2 * pieces per side (enough for any game
                                      played from this variant's setups); the stateless facade passes rows*cols */
+    int32_t obs_channel_mode;     /* SX_CHANNELS_EXTENDED (67 / 79 one-hot channels, impl:1232-1397) or
+                                     SX_CHANNELS_ORIGINAL (deprecated 32 / 33 raw-value channels, impl:1048-1197;
+                                     env_config['obs_channel_mode'], maenv:370-375).  In the original mode unit_lut
+                                     holds the normalised 0 and 1 of the obstacle / still channels (hi 2, lo 0) and
+                                     captured_lut the hi-2 variant (maenv:87-199) */
+    const float *rank_lut;        /* [14] original mode: normalised true rank 0..12 (entry 13 unused) */
+    const float *po_rank_lut;     /* [14] original mode: normalised partially observable rank 0..13 */
 } sx_config_desc;
+
+enum { SX_CHANNELS_EXTENDED = 0, SX_CHANNELS_ORIGINAL = 1 };
 
 /* Byte/element strides of the device tensors for one variant. */
 typedef struct {
@@ -67,6 +78,7 @@ typedef struct {
     int32_t po_floats, fo_floats; /* float32 per env of each observation */
     int32_t setup_len;            /* usable_rows*cols bytes per setup-table row */
     int32_t pieces_per_side;
+    int32_t po_channels, fo_channels; /* 67 / 79, or 32 / 33 in the original channel mode */
 } sx_layout;
 
 /* Compact struct-of-arrays device state (DESIGN.md "State layout"). */
@@ -78,8 +90,8 @@ typedef struct {
 
 /* Per-step outputs; any pointer may be NULL to skip that output. */
 typedef struct {
-    float *partial_obs;      /* [num_envs][R][C][67] float32, maenv:461-475 (normalised) */
-    float *full_obs;         /* [num_envs][R][C][79] float32, maenv:480-492 (normalised) */
+    float *partial_obs;      /* [num_envs][R][C][67 | 32] float32, maenv:461-475 (normalised) */
+    float *full_obs;         /* [num_envs][R][C][79 | 33] float32, maenv:480-492 (normalised) */
     uint8_t *valid_mask;     /* [num_envs][R][C][A] uint8 0/1, maenv:454 / impl:400-517 */
     float *reward;           /* [num_envs] player +1's reward when the game ended this step, else 0
                                 (maenv:777-801: +-1, or 0 for an invalid ending) */
@@ -169,6 +181,13 @@ enum { SX_DTYPE_F32 = 0, SX_DTYPE_BF16 = 1, SX_DTYPE_F16 = 2 };
 int sx_sample_logits(const void *logits_d, int32_t logits_dtype, const uint8_t *mask_d, int64_t num_envs,
                      int32_t n_actions, int64_t env_base, uint64_t seed, uint32_t step, float temperature,
                      int32_t *actions_d, float *logprob_d, void *stream);
+
+/* impl:854-891 (_get_heuristic_rewards_from_move): rewards_d[b] = reward_matrix[rank of the mover's piece on the
+ * start square][rank of the opponent's piece on the end square, 0 = empty] for the action game b is about to play
+ * (call it BEFORE the step).  reward_matrix_d is float32 [13][13] on the device; a no-op scores 0.  Like the
+ * reference, the action is assumed to be valid. */
+int sx_heuristic_rewards(const sx_config *cfg, sx_state st, int64_t num_envs, const int32_t *actions_d,
+                         int32_t action_format, const float *reward_matrix_d, float *rewards_d, void *stream);
 
 /* Kernel/launch facts for the benchmark's roofline accounting. */
 typedef struct {

@@ -18,6 +18,8 @@ _PF32 = np.ctypeslib.ndpointer(dtype=np.float32, flags="C_CONTIGUOUS")
 NUM_STATE_LAYERS = 34
 PO_CHANNELS = 67
 FO_CHANNELS = 79
+PO_CHANNELS_ORIG = 32  # deprecated 'original' channel mode, impl:1148
+FO_CHANNELS_ORIG = 33  # impl:1070
 
 _lib = None
 
@@ -84,6 +86,17 @@ def lib():
     L.so_normalize.argtypes = [_I64, _I64, _PF32, _PF32, _PF32]
     L.so_env_current_obs.restype = None
     L.so_env_current_obs.argtypes = [_I64, _I64, _P64, _I64, _P64, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
+    for name in ("so_po_observation_orig", "so_fo_observation_orig"):
+        getattr(L, name).restype = None
+        getattr(L, name).argtypes = [_I64, _I64, _P64, _I64, _PF32]
+    for name in ("so_po_highs_lows_orig", "so_fo_highs_lows_orig"):
+        getattr(L, name).restype = None
+        getattr(L, name).argtypes = [_P64, _PF32, _PF32]
+    L.so_env_current_obs_ex.restype = None
+    L.so_env_current_obs_ex.argtypes = [_I64, _I64, _P64, _I64, _P64, C.c_int, C.c_int, C.c_void_p, C.c_void_p,
+                                        C.c_void_p]
+    L.so_heuristic_reward.restype = C.c_float
+    L.so_heuristic_reward.argtypes = [_I64, _I64, _P64, _I64, _I64, _PF32]
     L.so_env_apply_spatial_action.restype = C.c_int
     L.so_env_apply_spatial_action.argtypes = [_I64, _I64, _P64, _I64, _I64, _P64]
     L.so_selfplay.restype = _I64
@@ -225,6 +238,32 @@ class OracleProceduralEnv:
         return out
 
 
+    def get_heuristic_rewards_from_move(self, state, player, action_index, reward_matrix):  # impl:854-891
+        m = np.ascontiguousarray(reward_matrix, dtype=np.float32)
+        assert m.shape == (13, 13)
+        return np.float32(lib().so_heuristic_reward(self.rows, self.columns, _st(state), int(player), int(action_index), m))
+
+    def get_dict_of_valid_moves_by_position(self, state, player):  # penv:82 -> impl:1400-1429
+        mask = self.get_valid_moves_as_1d_mask(state, player)
+        moves = {}
+        for a in np.flatnonzero(mask):
+            # a no-op-only mask (stuck player / finished game) raises ValueError here, as in the reference (impl:355-367)
+            sr, sc, er, ec = self.get_action_positions_from_1d_index(int(a))
+            moves.setdefault("{},{}".format(sr, sc), []).append([er, ec])
+        return moves
+
+    # deprecated 'original' channel mode, penv:157-163
+    def get_fully_observable_observation(self, state, player):
+        out = np.empty((self.rows, self.columns, FO_CHANNELS_ORIG), dtype=np.float32)
+        lib().so_fo_observation_orig(self.rows, self.columns, _st(state), int(player), out)
+        return out
+
+    def get_partially_observable_observation(self, state, player):
+        out = np.empty((self.rows, self.columns, PO_CHANNELS_ORIG), dtype=np.float32)
+        lib().so_po_observation_orig(self.rows, self.columns, _st(state), int(player), out)
+        return out
+
+
 def piece_amounts_array(piece_amounts):
     """{piece_code(int 1..12): count} -> int64[13]"""
     arr = np.zeros(13, dtype=np.int64)
@@ -236,27 +275,35 @@ def piece_amounts_array(piece_amounts):
 class OracleEnvLogic:
     """maenv:447-497 (_get_current_obs) and maenv:684-692 (action conversion + next state)."""
 
-    def __init__(self, rows, columns, piece_amounts):
+    def __init__(self, rows, columns, piece_amounts, obs_channel_mode='extended'):
         self.rows, self.columns = int(rows), int(columns)
         self.base_env = OracleProceduralEnv(rows, columns)
         self.amounts = piece_amounts_array(piece_amounts)
+        assert obs_channel_mode in ('extended', 'original')
+        self.original = obs_channel_mode == 'original'  # maenv:370
+        self.po_channels = PO_CHANNELS_ORIG if self.original else PO_CHANNELS
+        self.fo_channels = FO_CHANNELS_ORIG if self.original else FO_CHANNELS
 
     def obs_highs_lows(self):
-        ph, pl = np.empty(PO_CHANNELS, np.float32), np.empty(PO_CHANNELS, np.float32)
-        fh, fl = np.empty(FO_CHANNELS, np.float32), np.empty(FO_CHANNELS, np.float32)
-        lib().so_po_highs_lows_ext(self.amounts, ph, pl)
-        lib().so_fo_highs_lows_ext(self.amounts, fh, fl)
+        ph, pl = np.empty(self.po_channels, np.float32), np.empty(self.po_channels, np.float32)
+        fh, fl = np.empty(self.fo_channels, np.float32), np.empty(self.fo_channels, np.float32)
+        if self.original:
+            lib().so_po_highs_lows_orig(self.amounts, ph, pl)
+            lib().so_fo_highs_lows_orig(self.amounts, fh, fl)
+        else:
+            lib().so_po_highs_lows_ext(self.amounts, ph, pl)
+            lib().so_fo_highs_lows_ext(self.amounts, fh, fl)
         return ph, pl, fh, fl
 
     def current_obs(self, state, player, obs_mode=3):
-        """returns (mask int64[R,C,A], po float32[R,C,67] | None, fo float32[R,C,79] | None)"""
+        """returns (mask int64[R,C,A], po float32[R,C,67 | 32] | None, fo float32[R,C,79 | 33] | None)"""
         R, Cc = self.rows, self.columns
         mask = np.empty(self.base_env.spatial_action_size, dtype=np.int64)
-        po = np.empty((R, Cc, PO_CHANNELS), np.float32) if obs_mode & 1 else None
-        fo = np.empty((R, Cc, FO_CHANNELS), np.float32) if obs_mode & 2 else None
-        lib().so_env_current_obs(R, Cc, _st(state), int(player), self.amounts, int(obs_mode),
-                                 mask.ctypes.data, po.ctypes.data if po is not None else None,
-                                 fo.ctypes.data if fo is not None else None)
+        po = np.empty((R, Cc, self.po_channels), np.float32) if obs_mode & 1 else None
+        fo = np.empty((R, Cc, self.fo_channels), np.float32) if obs_mode & 2 else None
+        lib().so_env_current_obs_ex(R, Cc, _st(state), int(player), self.amounts, int(obs_mode), int(self.original),
+                                    mask.ctypes.data, po.ctypes.data if po is not None else None,
+                                    fo.ctypes.data if fo is not None else None)
         return mask, po, fo
 
     def apply_spatial_action(self, state, player, flat_action):

@@ -13,6 +13,8 @@ Every array below is produced by reference code:
     (penv:38, penv:148) -- combat table, scout reveal, two-square rule, stuck opponent,
     max-turn tie, noop handling, illegal moves.
   * codecs: exhaustive tables of the index conversions (impl:264-396, 680-720).
+  * original channels: the deprecated 32/33-channel observations (obs_channel_mode='original',
+    maenv:370-375) of recorded states, from the env's own _get_current_obs.
   * setups: rows of the human-setup transform (util:241-275) and full initial states
     (util:278-298).
 """
@@ -384,9 +386,79 @@ def setup_vectors(se):
     return out
 
 
+def original_channel_vectors(se, only_missing=False):
+    """The deprecated obs_channel_mode='original' (maenv:370-375): the reference env's own _get_current_obs
+    (maenv:447-497) on states of the recorded trajectories -- every 3rd observation record for the player to
+    move, plus every terminal state for both players."""
+    from stratego_env.game.enums import GameVersions, ObservationModes, ObservationComponents as OC
+    out = {}
+    for version in TRAJECTORY_PLAN:
+        with np.load(os.path.join(OUT_DIR, "traj_%s.npz" % version)) as d:
+            states, players, obs_step = d["states"], d["players"], d["obs_step"]
+            term = d["term_step"] if "term_step" in d.files else np.zeros(0, np.int32)
+        env = se.StrategoMultiAgentEnv(env_config={
+            "version": GameVersions(version), "observation_mode": ObservationModes.BOTH_OBSERVATIONS,
+            "obs_channel_mode": "original"})
+        picks = [(int(k), int(players[k])) for k in obs_step[::3]]
+        picks += [(int(t) // 2, 1 if int(t) % 2 == 0 else -1) for t in term]
+        po, fo = [], []
+        for k, player in picks:
+            env.state = states[k].astype(np.int64)
+            env.player = player
+            o = env._get_current_obs(player)
+            po.append(o[OC.PARTIAL_OBSERVATION.value].astype(np.float32))
+            fo.append(o[OC.FULL_OBSERVATION.value].astype(np.float32))
+        out["orig_%s_state_index" % version] = np.asarray([k for k, _ in picks], np.int32)
+        out["orig_%s_player" % version] = np.asarray([p for _, p in picks], np.int8)
+        out["orig_%s_po" % version] = np.stack(po)
+        out["orig_%s_fo" % version] = np.stack(fo)
+        out["orig_%s_p_highs" % version], out["orig_%s_p_lows" % version] = env._p_obs_highs, env._p_obs_lows
+        out["orig_%s_f_highs" % version], out["orig_%s_f_lows" % version] = env._f_obs_highs, env._f_obs_lows
+    return out
+
+
+def side_channel_vectors(se):
+    """Side channels of SURVEY 8(f) rank 4, from the reference's own functions on recorded transitions:
+    _get_heuristic_rewards_from_move (impl:854-891) with a fixed pseudo-random 13x13 matrix, and
+    get_dict_of_valid_moves_by_position (penv:82, impl:1400-1429) serialised as JSON."""
+    import json
+    from stratego_env.game.stratego_procedural_env import StrategoProceduralEnv
+    from stratego_env.game.stratego_procedural_impl import _get_heuristic_rewards_from_move
+    matrix = np.random.default_rng(2026).normal(size=(13, 13)).astype(np.float32)
+    out = {"heuristic_matrix": matrix}
+    for version in ("barrage", "standard", "micro", "octa_barrage"):
+        with np.load(os.path.join(OUT_DIR, "traj_%s.npz" % version)) as d:
+            states, players, a1d = d["states"], d["players"], d["actions_1d"]
+            R, C = int(d["rows"]), int(d["columns"])
+        env = StrategoProceduralEnv(R, C)
+        idx = np.flatnonzero(a1d >= 0)[:400]
+        rewards = [_get_heuristic_rewards_from_move(states[i].astype(np.int64), np.int64(players[i]), np.int64(a1d[i]),
+                                                    env.action_size, env._mpapsp, False, matrix) for i in idx]
+        out["heuristic_%s_index" % version] = idx.astype(np.int32)
+        out["heuristic_%s_reward" % version] = np.asarray(rewards, np.float32)
+        picks = idx[::40]
+        dicts = [json.dumps(env.get_dict_of_valid_moves_by_position(states[i].astype(np.int64), int(players[i])),
+                            default=int) for i in picks]
+        out["moves_%s_index" % version] = picks.astype(np.int32)
+        out["moves_%s_json" % version] = np.asarray(dicts)
+    return out
+
+
 def main():
     se = import_reference()
     os.makedirs(OUT_DIR, exist_ok=True)
+    if "--side-channels-only" in sys.argv:
+        data = side_channel_vectors(se)
+        path = os.path.join(OUT_DIR, "side_channels.npz")
+        np.savez_compressed(path, **data)
+        print("side_channels.npz %7.1f KB (%d arrays)" % (os.path.getsize(path) / 1024, len(data)))
+        return
+    if "--original-only" in sys.argv:  # adds original_channels.npz from the committed trajectories
+        data = original_channel_vectors(se)
+        path = os.path.join(OUT_DIR, "original_channels.npz")
+        np.savez_compressed(path, **data)
+        print("original_channels.npz %7.1f KB (%d arrays)" % (os.path.getsize(path) / 1024, len(data)))
+        return
     for i, (version, (n_games, human, max_steps)) in enumerate(TRAJECTORY_PLAN.items()):
         data = record_trajectories(se, version, n_games, human, max_steps, seed=1000 + i)
         path = os.path.join(OUT_DIR, "traj_%s.npz" % version)
@@ -401,6 +473,14 @@ def main():
     path = os.path.join(OUT_DIR, "known_answers.npz")
     np.savez_compressed(path, **misc)
     print("known_answers.npz %7.1f KB (%d arrays)" % (os.path.getsize(path) / 1024, len(misc)))
+    data = original_channel_vectors(se)
+    path = os.path.join(OUT_DIR, "original_channels.npz")
+    np.savez_compressed(path, **data)
+    print("original_channels.npz %7.1f KB (%d arrays)" % (os.path.getsize(path) / 1024, len(data)))
+    data = side_channel_vectors(se)
+    path = os.path.join(OUT_DIR, "side_channels.npz")
+    np.savez_compressed(path, **data)
+    print("side_channels.npz %7.1f KB (%d arrays)" % (os.path.getsize(path) / 1024, len(data)))
 
 
 if __name__ == "__main__":

@@ -405,6 +405,18 @@ int so_get_next_state(int64_t R, int64_t C, const int64_t *st, int64_t player, i
     return 0;
 }
 
+/* impl:854-891: reward_matrix[13][13] indexed by the mover's rank at the start square and the opponent's rank at the
+ * end square; the no-op scores 0; the action is assumed valid */
+float so_heuristic_reward(int64_t R, int64_t C, const int64_t *state, int64_t player, int64_t action, const float *matrix)
+{
+    if (action == so_action_size(R, C) - 1) return 0.0f; /* impl:866-868 */
+    int64_t pos[4];
+    so_positions_from_1d(R, C, action, pos);             /* impl:872-874 */
+    const int64_t own = AT(LAYER(state, own_layer(player), R, C), pos[0], pos[1], C);
+    const int64_t enemy = AT(LAYER(state, own_layer(-player), R, C), pos[2], pos[3], C);
+    return matrix[own * 13 + enemy];                     /* impl:882 */
+}
+
 /* writes plane `ch` of an HWC float tensor from an int64 layer */
 static void put_plane(float *obs, int64_t n, int64_t channels, int64_t ch, const int64_t *layer)
 {
@@ -466,6 +478,78 @@ void so_fo_observation_ext(int64_t R, int64_t C, const int64_t *state, int64_t p
     free(buf);
 }
 
+/* Deprecated "original" channel mode (obs_channel_mode='original', maenv:370-375): raw layer values, one
+ * channel per state layer.  impl:1153-1197, channel map impl:1126-1148 */
+void so_po_observation_orig(int64_t R, int64_t C, const int64_t *state, int64_t player, float *obs)
+{
+    const int64_t n = CELLS(R, C), ch = SO_PO_CHANNELS_ORIG;
+    int64_t *buf = NULL;
+    const int64_t *st = state;
+    if (player != 1) {
+        buf = (int64_t *)malloc(sizeof(int64_t) * SO_NUM_STATE_LAYERS * n);
+        so_state_from_player_perspective(R, C, state, player, buf); /* impl:1156 */
+        st = buf;
+    }
+    put_plane(obs, n, ch, 0, LAYER(st, L_P1, R, C));
+    put_plane(obs, n, ch, 1, LAYER(st, L_P1_PO, R, C));
+    put_plane(obs, n, ch, 2, LAYER(st, L_P2_PO, R, C));
+    put_plane(obs, n, ch, 3, LAYER(st, L_OBST, R, C));
+    put_plane(obs, n, ch, 4, LAYER(st, L_P1_RECENT, R, C));
+    put_plane(obs, n, ch, 5, LAYER(st, L_P2_RECENT, R, C));
+    for (int t = 0; t < 12; ++t) put_plane(obs, n, ch, 6 + t, LAYER(st, L_P1_CAP0 + t, R, C));
+    for (int t = 0; t < 12; ++t) put_plane(obs, n, ch, 18 + t, LAYER(st, L_P2_CAP0 + t, R, C));
+    put_plane(obs, n, ch, 30, LAYER(st, L_P1_STILL, R, C));
+    put_plane(obs, n, ch, 31, LAYER(st, L_P2_STILL, R, C));
+    free(buf);
+}
+
+/* impl:1075-1123, channel map impl:1048-1070 */
+void so_fo_observation_orig(int64_t R, int64_t C, const int64_t *state, int64_t player, float *obs)
+{
+    const int64_t n = CELLS(R, C), ch = SO_FO_CHANNELS_ORIG;
+    int64_t *buf = NULL;
+    const int64_t *st = state;
+    if (player != 1) {
+        buf = (int64_t *)malloc(sizeof(int64_t) * SO_NUM_STATE_LAYERS * n);
+        so_state_from_player_perspective(R, C, state, player, buf); /* impl:1078 */
+        st = buf;
+    }
+    put_plane(obs, n, ch, 0, LAYER(st, L_P1, R, C));
+    put_plane(obs, n, ch, 1, LAYER(st, L_P2, R, C));
+    put_plane(obs, n, ch, 2, LAYER(st, L_OBST, R, C));
+    put_plane(obs, n, ch, 3, LAYER(st, L_P1_RECENT, R, C));
+    put_plane(obs, n, ch, 4, LAYER(st, L_P2_RECENT, R, C));
+    put_plane(obs, n, ch, 5, LAYER(st, L_P1_PO, R, C));
+    put_plane(obs, n, ch, 6, LAYER(st, L_P2_PO, R, C));
+    for (int t = 0; t < 12; ++t) put_plane(obs, n, ch, 7 + t, LAYER(st, L_P1_CAP0 + t, R, C));
+    for (int t = 0; t < 12; ++t) put_plane(obs, n, ch, 19 + t, LAYER(st, L_P2_CAP0 + t, R, C));
+    put_plane(obs, n, ch, 31, LAYER(st, L_P1_STILL, R, C));
+    put_plane(obs, n, ch, 32, LAYER(st, L_P2_STILL, R, C));
+    free(buf);
+}
+
+/* maenv:146-199 */
+void so_po_highs_lows_orig(const int64_t amounts[13], float hi[SO_PO_CHANNELS_ORIG], float lo[SO_PO_CHANNELS_ORIG])
+{
+    for (int c = 0; c < SO_PO_CHANNELS_ORIG; ++c) { hi[c] = 2.0f; lo[c] = 0.0f; } /* obstacles, captured, still */
+    hi[0] = (float)SP_BOMB;                                                       /* own true ranks */
+    hi[1] = hi[2] = (float)SP_UNKNOWN;                                            /* PO ranks */
+    hi[4] = hi[5] = (float)RM_CAME_FROM; lo[4] = lo[5] = (float)RM_ARRIVED_CANT;
+    for (int t = 1; t <= 12; ++t)
+        if (amounts[t] > 1) { hi[6 + t - 1] = (float)amounts[t]; hi[18 + t - 1] = (float)amounts[t]; } /* maenv:176-180 */
+}
+
+/* maenv:87-143 */
+void so_fo_highs_lows_orig(const int64_t amounts[13], float hi[SO_FO_CHANNELS_ORIG], float lo[SO_FO_CHANNELS_ORIG])
+{
+    for (int c = 0; c < SO_FO_CHANNELS_ORIG; ++c) { hi[c] = 2.0f; lo[c] = 0.0f; }
+    hi[0] = hi[1] = (float)SP_BOMB;
+    hi[3] = hi[4] = (float)RM_CAME_FROM; lo[3] = lo[4] = (float)RM_ARRIVED_CANT;
+    hi[5] = hi[6] = (float)SP_UNKNOWN;
+    for (int t = 1; t <= 12; ++t)
+        if (amounts[t] > 1) { hi[7 + t - 1] = (float)amounts[t]; hi[19 + t - 1] = (float)amounts[t]; } /* maenv:120-124 */
+}
+
 /* maenv:261-313 */
 void so_po_highs_lows_ext(const int64_t amounts[13], float hi[SO_PO_CHANNELS], float lo[SO_PO_CHANNELS])
 {
@@ -502,9 +586,9 @@ void so_normalize(int64_t n_cells, int64_t channels, const float *hi, const floa
     }
 }
 
-/* maenv:447-497 */
-void so_env_current_obs(int64_t R, int64_t C, const int64_t *state, int64_t player, const int64_t amounts[13],
-                        int obs_mode, int64_t *mask_out, float *po_out, float *fo_out)
+/* maenv:447-497; original_channels selects obs_channel_mode='original' (maenv:370-375, 460-468, 479-487) */
+void so_env_current_obs_ex(int64_t R, int64_t C, const int64_t *state, int64_t player, const int64_t amounts[13],
+                           int obs_mode, int original_channels, int64_t *mask_out, float *po_out, float *fo_out)
 {
     const int64_t n = CELLS(R, C);
     int64_t *persp = (int64_t *)malloc(sizeof(int64_t) * SO_NUM_STATE_LAYERS * n);
@@ -512,17 +596,35 @@ void so_env_current_obs(int64_t R, int64_t C, const int64_t *state, int64_t play
     if (mask_out) so_valid_moves_spatial_mask(R, C, persp, 1, mask_out); /* maenv:454 */
     if ((obs_mode & 1) && po_out) {                                     /* maenv:458-475 */
         float hi[SO_PO_CHANNELS], lo[SO_PO_CHANNELS];
-        so_po_observation_ext(R, C, persp, 1, po_out);
-        so_po_highs_lows_ext(amounts, hi, lo);
-        so_normalize(n, SO_PO_CHANNELS, hi, lo, po_out);
+        if (original_channels) {
+            so_po_observation_orig(R, C, persp, 1, po_out);
+            so_po_highs_lows_orig(amounts, hi, lo);
+            so_normalize(n, SO_PO_CHANNELS_ORIG, hi, lo, po_out);
+        } else {
+            so_po_observation_ext(R, C, persp, 1, po_out);
+            so_po_highs_lows_ext(amounts, hi, lo);
+            so_normalize(n, SO_PO_CHANNELS, hi, lo, po_out);
+        }
     }
     if ((obs_mode & 2) && fo_out) {                                     /* maenv:477-492 */
         float hi[SO_FO_CHANNELS], lo[SO_FO_CHANNELS];
-        so_fo_observation_ext(R, C, persp, 1, fo_out);
-        so_fo_highs_lows_ext(amounts, hi, lo);
-        so_normalize(n, SO_FO_CHANNELS, hi, lo, fo_out);
+        if (original_channels) {
+            so_fo_observation_orig(R, C, persp, 1, fo_out);
+            so_fo_highs_lows_orig(amounts, hi, lo);
+            so_normalize(n, SO_FO_CHANNELS_ORIG, hi, lo, fo_out);
+        } else {
+            so_fo_observation_ext(R, C, persp, 1, fo_out);
+            so_fo_highs_lows_ext(amounts, hi, lo);
+            so_normalize(n, SO_FO_CHANNELS, hi, lo, fo_out);
+        }
     }
     free(persp);
+}
+
+void so_env_current_obs(int64_t R, int64_t C, const int64_t *state, int64_t player, const int64_t amounts[13],
+                        int obs_mode, int64_t *mask_out, float *po_out, float *fo_out)
+{
+    so_env_current_obs_ex(R, C, state, player, amounts, obs_mode, 0, mask_out, po_out, fo_out);
 }
 
 /* maenv:684-692 */

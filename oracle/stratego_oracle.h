@@ -24,7 +24,8 @@
 extern "C" {
 #endif
 
-enum { SO_NUM_STATE_LAYERS = 34, SO_PO_CHANNELS = 67, SO_FO_CHANNELS = 79 };
+enum { SO_NUM_STATE_LAYERS = 34, SO_PO_CHANNELS = 67, SO_FO_CHANNELS = 79,
+       SO_PO_CHANNELS_ORIG = 32 /* impl:1148 */, SO_FO_CHANNELS_ORIG = 33 /* impl:1070 */ };
 
 /* impl:253-259 */
 int64_t so_action_size(int64_t R, int64_t C);
@@ -69,9 +70,20 @@ int so_get_game_result_is_invalid(int64_t R, int64_t C, const int64_t *state);
 int so_get_next_state(int64_t R, int64_t C, const int64_t *state, int64_t player, int64_t action,
                       int allow_piece_oscillation, int64_t *state_out);
 
+/* impl:854-891 : reward_matrix is float32 [13][13] */
+float so_heuristic_reward(int64_t R, int64_t C, const int64_t *state, int64_t player, int64_t action,
+                          const float *reward_matrix);
+
 /* impl:1337-1397 / impl:1232-1303 : raw (un-normalised) float32 HWC observations */
 void so_po_observation_ext(int64_t R, int64_t C, const int64_t *state, int64_t player, float *out);
 void so_fo_observation_ext(int64_t R, int64_t C, const int64_t *state, int64_t player, float *out);
+
+/* the deprecated "original" channel mode (obs_channel_mode='original'): impl:1153-1197 / impl:1075-1123, one
+ * channel per state layer with raw values; highs and lows maenv:146-199 / maenv:87-143 */
+void so_po_observation_orig(int64_t R, int64_t C, const int64_t *state, int64_t player, float *out);
+void so_fo_observation_orig(int64_t R, int64_t C, const int64_t *state, int64_t player, float *out);
+void so_po_highs_lows_orig(const int64_t piece_amounts[13], float highs[SO_PO_CHANNELS_ORIG], float lows[SO_PO_CHANNELS_ORIG]);
+void so_fo_highs_lows_orig(const int64_t piece_amounts[13], float highs[SO_FO_CHANNELS_ORIG], float lows[SO_FO_CHANNELS_ORIG]);
 
 /* maenv:261-313 / maenv:202-258 : per-channel highs and lows.  piece_amounts[t] for t = 1..12
  * (index 0 unused) */
@@ -85,6 +97,11 @@ void so_normalize(int64_t n_cells, int64_t channels, const float *highs, const f
 void so_env_current_obs(int64_t R, int64_t C, const int64_t *state, int64_t player,
                         const int64_t piece_amounts[13], int obs_mode, int64_t *mask_out, float *po_out,
                         float *fo_out);
+
+/* same with obs_channel_mode: original_channels != 0 renders the 32 / 33-channel observations */
+void so_env_current_obs_ex(int64_t R, int64_t C, const int64_t *state, int64_t player,
+                           const int64_t piece_amounts[13], int obs_mode, int original_channels, int64_t *mask_out,
+                           float *po_out, float *fo_out);
 
 /* maenv:659-699 : flat spatial action in the mover's frame -> next state; returns 0 / -1 (ValueError) */
 int so_env_apply_spatial_action(int64_t R, int64_t C, const int64_t *state, int64_t player, int64_t flat_action,

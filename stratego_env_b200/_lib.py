@@ -13,18 +13,20 @@ _i32, _i64, _u32, _u64, _vp = C.c_int32, C.c_int64, C.c_uint32, C.c_uint64, C.c_
 SX_ACTION_SPATIAL, SX_ACTION_1D = 0, 1
 SX_AUTO_RESET, SX_SAMPLE_NEXT, SX_ALLOW_OSCILLATION, SX_RESET_RANDOM_SHUFFLE = 1, 2, 4, 8
 OBS_PO, OBS_FO, OBS_MASK = 1, 2, 4
+SX_CHANNELS_EXTENDED, SX_CHANNELS_ORIGINAL = 0, 1
 
 
 class SxConfigDesc(C.Structure):
     _fields_ = [("rows", _i32), ("cols", _i32), ("max_turns", _i32), ("usable_rows", _i32),
                 ("piece_amounts", _i32 * 13), ("obstacles", _vp), ("captured_lut", _vp), ("recent_lut", _vp),
-                ("unit_lut", _vp), ("p2_rot180", _i32), ("capture_capacity", _i32)]
+                ("unit_lut", _vp), ("p2_rot180", _i32), ("capture_capacity", _i32), ("obs_channel_mode", _i32),
+                ("rank_lut", _vp), ("po_rank_lut", _vp)]
 
 
 class SxLayout(C.Structure):
     _fields_ = [(n, _i32) for n in ("rows", "cols", "cells", "spatial_channels", "spatial_actions", "action_size",
                                     "board_stride", "aux_stride", "captured_stride", "po_floats", "fo_floats",
-                                    "setup_len", "pieces_per_side")]
+                                    "setup_len", "pieces_per_side", "po_channels", "fo_channels")]
 
 
 class SxState(C.Structure):
@@ -58,6 +60,7 @@ SYMBOLS = {
     "sx_step_all": (C.c_int, [_vp, SxState, _i64, _i64, _vp, _i32, _u32, _vp, _i32, _u64, SxOutputs, _vp, _vp]),
     "sx_sample_valid": (C.c_int, [_vp, _i64, _i32, _i64, _u64, _u32, _vp, _vp]),
     "sx_sample_logits": (C.c_int, [_vp, _i32, _vp, _i64, _i32, _i64, _u64, _u32, C.c_float, _vp, _vp, _vp]),
+    "sx_heuristic_rewards": (C.c_int, [_vp, SxState, _i64, _vp, _i32, _vp, _vp, _vp]),
     "sx_step_all_launch_info": (C.c_int, [_vp, _u32, C.POINTER(SxLaunchInfo)]),
     "sx_host_env_create": (C.c_int, [_vp, _i64, _i64, _u32, _u32, _vp, _i32, _u64, _i32, C.POINTER(_vp)]),
     "sx_host_env_destroy": (None, [_vp]),

@@ -140,5 +140,38 @@ def unit_channel_lut() -> np.ndarray:
     return ((np.asarray([0.0, 1.0], dtype=np.float32) - mid) / rng).astype(np.float32)
 
 
+# ---- deprecated obs_channel_mode='original' (maenv:370-375): one channel per state layer, raw values ------------
+def _norm(values, hi, lo):
+    hi, lo = np.float32(hi), np.float32(lo)
+    rng, mid = (hi - lo) / np.float32(2.0), (hi + lo) / np.float32(2.0)  # maenv:388-396
+    return ((np.asarray(values, dtype=np.float32) - mid) / rng).astype(np.float32)  # maenv:499-508
+
+
+def original_rank_lut() -> np.ndarray:
+    """float32[14]: normalised true-rank value 0..12 (hi = SP.BOMB 12, lo 0; maenv:88-89, 147-148)."""
+    return _norm(np.arange(14), SP.BOMB.value, SP.NOPIECE.value)
+
+
+def original_po_rank_lut() -> np.ndarray:
+    """float32[14]: normalised partially observable rank 0..13 (hi = SP.UNKNOWN 13; maenv:91-92, 150-151)."""
+    return _norm(np.arange(14), SP.UNKNOWN.value, SP.NOPIECE.value)
+
+
+def original_unit_lut() -> np.ndarray:
+    """float32[2]: normalised 0 and 1 of the obstacle / still channels, hi 2 / lo 0 (maenv:111, 117-118)."""
+    return _norm([0.0, 1.0], 2.0, 0.0)
+
+
+def original_captured_lut(piece_amounts: Dict) -> np.ndarray:
+    """float32[12][9]: captured-count channels with hi 2, or the piece count when > 1 (maenv:115-124, 171-180)."""
+    highs = np.full(12, 2.0, dtype=np.float32)
+    amounts = piece_amounts_array(piece_amounts)
+    for code in range(1, 13):
+        if amounts[code] > 1:
+            highs[code - 1] = np.float32(amounts[code])
+    n = np.arange(MAX_CAPTURE_COUNT + 1, dtype=np.float32)
+    return np.stack([_norm(n, h, 0.0) for h in highs]).astype(np.float32)
+
+
 def enumerate_versions() -> List[GameVersions]:
     return list(VERSION_CONFIGS.keys())

@@ -59,6 +59,10 @@ struct DevConfig {
     float cap_lut[12 * 9];
     float recent_lut[5];
     float unit_lut[2];
+    // deprecated 'original' channel mode (maenv:370-375): one channel per state layer carrying the normalised raw value
+    int original_channels, po_ch, fo_ch;  // po_ch / fo_ch: channels of the two observations (67 / 79 or 32 / 33)
+    float rank_lut[14];     // normalised true-rank value 0..12 (maenv:88-89)
+    float po_rank_lut[14];  // normalised partially observable rank 0..13 (maenv:91-92)
     uint8_t obstacles[256];
     uint8_t piece_seq[128];  // pieces in placement order (piece code ascending, util:24-28)
 };
@@ -730,6 +734,18 @@ struct ObsMap {
 };
 __device__ __forceinline__ ObsMap po_map() { return ObsMap{67, 0, -1, 12, 25, 38, 39, 40, 41, 53, 65, 66}; }
 __device__ __forceinline__ ObsMap fo_map() { return ObsMap{79, 0, 12, 24, 37, 50, 51, 52, 53, 65, 77, 78}; }
+// the deprecated 'original' channel mode: one channel per state layer (impl:1126-1148 partial, impl:1048-1070 full)
+__device__ __forceinline__ ObsMap po_map_original() { return ObsMap{32, 0, -1, 1, 2, 3, 4, 5, 6, 18, 30, 31}; }
+__device__ __forceinline__ ObsMap fo_map_original() { return ObsMap{33, 0, 1, 5, 6, 2, 3, 4, 7, 19, 31, 32}; }
+
+// Rows (cells) to skip at the start of a background image so that the copy's source is congruent mod 16 to a
+// destination that is `a` words past a 16-byte boundary: the image is periodic in the cell, and a cell is
+// `channels` words, so k cells shift the phase by k * channels words (67, 79 = 3 mod 4; 33 = 1 mod 4; 32 = 0).
+__device__ __forceinline__ int align_rows(int channels, int a)
+{
+    const int c = channels & 3;
+    return c == 3 ? ((4 - a) & 3) : c == 1 ? a : 0;
+}
 
 // fills a tile with what an empty board looks like after normalisation
 static __device__ __noinline__ void fill_background(const DevConfig &cfg, float *tile, const ObsMap om, int first, int stride)
@@ -742,13 +758,18 @@ static __device__ __noinline__ void fill_background(const DevConfig &cfg, float 
         if (ch == om.own_recent || ch == om.enemy_recent) v = cfg.recent_lut[3];
         else if (ch >= om.own_cap && ch < om.own_cap + 12) v = cfg.cap_lut[(ch - om.own_cap) * 9];
         else if (ch >= om.enemy_cap && ch < om.enemy_cap + 12) v = cfg.cap_lut[(ch - om.enemy_cap) * 9];
+        else if (cfg.original_channels) {  // rank planes hold "no piece" instead of a one-hot zero
+            if (ch == om.own_true || ch == om.enemy_true) v = cfg.rank_lut[0];
+            else if (ch == om.own_po || ch == om.enemy_po) v = cfg.po_rank_lut[0];
+        }
         tile[i] = v;
     }
 }
 
 // Writes the sparse, state-dependent entries of observer `me`'s observation on top of the background
 // image at `tile` (global memory).
-template <int K, class GT>
+// ORIG = the deprecated 'original' channel mode: rank planes carry the normalised rank instead of one-hot groups.
+template <int K, class GT, bool ORIG = false>
 __device__ __forceinline__ void patch_obs(const DevConfig &cfg, const WarpMem &m, const Aux &a, float *tile,
                                           const ObsMap om, int me, uint64_t pol)
 {
@@ -764,7 +785,12 @@ __device__ __forceinline__ void patch_obs(const DevConfig &cfg, const WarpMem &m
             const int rank = b & CELL_RANK;
             if (rank) {
                 const int po = (b & CELL_REVEALED) ? rank : SP_UNKNOWN;
-                if (int((b >> 4) & 1) == me) {
+                const bool own = int((b >> 4) & 1) == me;
+                if (ORIG) {  // impl:1178-1195 / impl:1102-1121 + maenv:499-508
+                    if (own || om.enemy_true >= 0) st_hint(cell + (own ? om.own_true : om.enemy_true), cfg.rank_lut[rank], pol);
+                    st_hint(cell + (own ? om.own_po : om.enemy_po), cfg.po_rank_lut[po], pol);
+                    if (b & CELL_STILL) st_hint(cell + (own ? om.own_still : om.enemy_still), one, pol);
+                } else if (own) {
                     st_hint(cell + om.own_true + rank - 1, one, pol);
                     st_hint(cell + om.own_po + po - 1, one, pol);
                     if (b & CELL_STILL) st_hint(cell + om.own_still, one, pol);

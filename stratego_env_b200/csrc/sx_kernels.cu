@@ -64,9 +64,9 @@ __host__ __device__ inline int carve_tile(const DevConfig &cfg, uint32_t ops, ui
     // three extra cell rows: the image is periodic in the cell (67 or 79 floats = 12 mod 16 bytes), so starting the
     // copy k rows in gives a source congruent mod 16 to ANY 4-byte aligned destination (5x5 and 15x15 observations
     // are not multiples of 16 bytes, so their rows in the output tensor are 4-, 8- or 12-byte misaligned)
-    off += (ops & OP_PO) ? round16((cfg.N + 3) * SX_PO_CHANNELS * 4) : 0;
+    off += (ops & OP_PO) ? round16((cfg.N + 3) * cfg.po_ch * 4) : 0;
     if (t) t->fo = reinterpret_cast<float *>(base + off);
-    off += (ops & OP_FO) ? round16((cfg.N + 3) * SX_FO_CHANNELS * 4) : 0;
+    off += (ops & OP_FO) ? round16((cfg.N + 3) * cfg.fo_ch * 4) : 0;
     if (t) t->mask = base + off;
     off += (ops & OP_MASK) ? round16(cfg.mask_bytes + 16) : 0;
     return off;
@@ -131,7 +131,10 @@ __global__ void __launch_bounds__(K <= 2 ? 1024 : SX_MAX_THREADS, 1) sx_fused_ke
     const bool allow_osc = flags & SX_ALLOW_OSCILLATION;
     const bool need_moves = do_mask || do_sample || (ops & (OP_MASK_1D | OP_NEED_MOVES));
     const int mask_tile_bytes = round16(cfg.mask_bytes + 16);
-    const ObsMap pom = po_map(), fom = fo_map();
+    // the 32 / 33-channel 'original' observations run through the generic kernel only; the specialised hot modes keep
+    // compile-time channel maps
+    const bool original = MODE == MODE_GENERIC && cfg.original_channels != 0;
+    const ObsMap pom = original ? po_map_original() : po_map(), fom = original ? fo_map_original() : fo_map();
 
     // the block's read-only background images
     Tile bg;
@@ -173,14 +176,14 @@ __global__ void __launch_bounds__(K <= 2 ? 1024 : SX_MAX_THREADS, 1) sx_fused_ke
         if (flags & 0x10000u) return;  // experiment switch
         if (do_po) {
             float *g = args.out.partial_obs + e * cfg.po_floats;
-            const int k = (4 - int((reinterpret_cast<uintptr_t>(g) >> 2) & 3)) & 3;  // k * 12 == misalignment (mod 16)
-            emit_tile<GT>(reinterpret_cast<uint8_t *>(g), reinterpret_cast<const uint8_t *>(bg.po + k * SX_PO_CHANNELS),
+            const int k = align_rows(pom.channels, int((reinterpret_cast<uintptr_t>(g) >> 2) & 3));
+            emit_tile<GT>(reinterpret_cast<uint8_t *>(g), reinterpret_cast<const uint8_t *>(bg.po + k * pom.channels),
                           cfg.po_floats * 4, pol_stream);
         }
         if (do_fo) {
             float *g = args.out.full_obs + e * cfg.fo_floats;
-            const int k = (4 - int((reinterpret_cast<uintptr_t>(g) >> 2) & 3)) & 3;
-            emit_tile<GT>(reinterpret_cast<uint8_t *>(g), reinterpret_cast<const uint8_t *>(bg.fo + k * SX_FO_CHANNELS),
+            const int k = align_rows(fom.channels, int((reinterpret_cast<uintptr_t>(g) >> 2) & 3));
+            emit_tile<GT>(reinterpret_cast<uint8_t *>(g), reinterpret_cast<const uint8_t *>(bg.fo + k * fom.channels),
                           cfg.fo_floats * 4, pol_stream);
         }
         if (do_mask) {
@@ -336,8 +339,13 @@ __global__ void __launch_bounds__(K <= 2 ? 1024 : SX_MAX_THREADS, 1) sx_fused_ke
             if (lane == 0) bulk_wait_all();  // this game's background is in global memory
             GT::sync();
             if (flags & 0x80000u) continue;  // experiment: wait but skip the sparse stores
-            if (do_po) patch_obs<K, GT>(cfg, m, a, args.out.partial_obs + env * cfg.po_floats, pom, viewer, pol_stream);
-            if (do_fo) patch_obs<K, GT>(cfg, m, a, args.out.full_obs + env * cfg.fo_floats, fom, viewer, pol_stream);
+            if (original) {
+                if (do_po) patch_obs<K, GT, true>(cfg, m, a, args.out.partial_obs + env * cfg.po_floats, pom, viewer, pol_stream);
+                if (do_fo) patch_obs<K, GT, true>(cfg, m, a, args.out.full_obs + env * cfg.fo_floats, fom, viewer, pol_stream);
+            } else {
+                if (do_po) patch_obs<K, GT>(cfg, m, a, args.out.partial_obs + env * cfg.po_floats, pom, viewer, pol_stream);
+                if (do_fo) patch_obs<K, GT>(cfg, m, a, args.out.full_obs + env * cfg.fo_floats, fom, viewer, pol_stream);
+            }
             if (do_mask) {
                 uint8_t *gmask = args.out.valid_mask + env * cfg.mask_bytes;
                 mark_spatial<K, GT>(cfg, m, gmask, pol_stream);
@@ -525,6 +533,30 @@ __global__ void sx_sample_kernel(const uint8_t *mask, long long num_envs, int ma
     if (lane == 0) actions[env] = action;
 }
 
+// impl:854-891: reward_matrix[rank the mover has on the start square][rank the opponent has on the end square] of the
+// action each game is about to play; a no-op (and anything outside the action space) scores 0.  One thread per game.
+__global__ void sx_heuristic_kernel(DevConfig cfg, const uint8_t *board, const int16_t *aux, long long num_envs,
+                                    const int32_t *actions, int action_format, const float *matrix, float *rewards)
+{
+    const long long env = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (env >= num_envs) return;
+    const uint4 aw = *reinterpret_cast<const uint4 *>(aux + env * 8);
+    const uint32_t w[4] = {aw.x, aw.y, aw.z, aw.w};
+    Aux a;
+    aux_unpack(w, a);
+    const int me = a.to_move;
+    const Move mv = action_format == SX_ACTION_SPATIAL ? decode_spatial(cfg, actions[env], me) : decode_1d(cfg, actions[env]);
+    float r = 0.0f;
+    if (!mv.bad && !mv.noop) {
+        const uint8_t *b = board + env * cfg.board_stride;
+        const uint32_t sb = b[mv.start], eb = b[mv.end];
+        const int own = int((sb >> 4) & 1) == me ? int(sb & CELL_RANK) : 0;      // owned_pieces[start], impl:879
+        const int enemy = int((eb >> 4) & 1) != me ? int(eb & CELL_RANK) : 0;    // enemy_pieces[end], impl:880
+        r = matrix[own * 13 + enemy];                                            // impl:882
+    }
+    rewards[env] = r;
+}
+
 }  // namespace sx
 
 // =====================================================================================================
@@ -601,8 +633,17 @@ extern "C" int sx_config_create(const sx_config_desc *desc, sx_config **out)
     if (d.usable_rows < 1 || 2 * d.usable_rows > d.R || d.setup_len > 120 || pieces > d.setup_len) { delete c; return fail("pieces do not fit in the usable rows"); }
     if (desc->capture_capacity < 0 || desc->capture_capacity > 248) { delete c; return fail("capture_capacity out of range 0..248"); }
     d.cap_stride = std::max(8, ((desc->capture_capacity > 0 ? desc->capture_capacity : 2 * pieces) + 7) & ~7);
-    d.po_floats = d.N * SX_PO_CHANNELS;
-    d.fo_floats = d.N * SX_FO_CHANNELS;
+    d.original_channels = desc->obs_channel_mode == SX_CHANNELS_ORIGINAL ? 1 : 0;
+    if (desc->obs_channel_mode != SX_CHANNELS_EXTENDED && desc->obs_channel_mode != SX_CHANNELS_ORIGINAL) { delete c; return fail("unknown obs_channel_mode"); }
+    if (d.original_channels && (!desc->rank_lut || !desc->po_rank_lut)) { delete c; return fail("sx_config_create: the original channel mode needs rank_lut and po_rank_lut"); }
+    d.po_ch = d.original_channels ? SX_PO_CHANNELS_ORIGINAL : SX_PO_CHANNELS;
+    d.fo_ch = d.original_channels ? SX_FO_CHANNELS_ORIGINAL : SX_FO_CHANNELS;
+    d.po_floats = d.N * d.po_ch;
+    d.fo_floats = d.N * d.fo_ch;
+    if (d.original_channels) {
+        std::memcpy(d.rank_lut, desc->rank_lut, sizeof(d.rank_lut));
+        std::memcpy(d.po_rank_lut, desc->po_rank_lut, sizeof(d.po_rank_lut));
+    }
     d.mask_bytes = d.N * d.A;
     std::memcpy(d.cap_lut, desc->captured_lut, sizeof(d.cap_lut));
     std::memcpy(d.recent_lut, desc->recent_lut, sizeof(d.recent_lut));
@@ -619,6 +660,7 @@ extern "C" int sx_config_create(const sx_config_desc *desc, sx_config **out)
     l.rows = d.R; l.cols = d.C; l.cells = d.N; l.spatial_channels = d.A; l.spatial_actions = d.mask_bytes;
     l.action_size = d.action_size; l.board_stride = d.board_stride; l.aux_stride = 8; l.captured_stride = d.cap_stride;
     l.po_floats = d.po_floats; l.fo_floats = d.fo_floats; l.setup_len = d.setup_len; l.pieces_per_side = pieces;
+    l.po_channels = d.po_ch; l.fo_channels = d.fo_ch;
     *out = c;
     return 0;
 }
@@ -660,9 +702,10 @@ static fused_fn fused_for(const sx_config *cfg, int mode)
 }
 
 // the specialised kernel for this launch, if one matches exactly
-static int mode_for(const KernelArgs &a)
+static int mode_for(const sx_config *cfg, const KernelArgs &a)
 {
     if (a.reset_mask || a.setup_idx || a.mask1d) return MODE_GENERIC;
+    if (cfg->dev.original_channels && (a.ops & (OP_PO | OP_FO))) return MODE_GENERIC;
     for (int mode : {MODE_MASK, MODE_OBSERVE_PO_MASK})
         if (a.ops == mode_ops(mode) && !(a.flags & SX_SAMPLE_NEXT)) return mode;
     if (a.player_override) return MODE_GENERIC;
@@ -747,7 +790,7 @@ static int launch_fused(const sx_config *cfg, KernelArgs &args, cudaStream_t str
 {
     if (args.num_envs <= 0) return 0;
     LaunchPlan plan;
-    const int mode = mode_for(args);
+    const int mode = mode_for(cfg, args);
     if (int rc = plan_launch(cfg, args.ops, mode, args.num_envs, &plan)) return rc;
     args.cfg = cfg->dev;
     args.warp_bytes = plan.warp_bytes;
@@ -930,6 +973,20 @@ extern "C" int sx_sample_valid(const uint8_t *mask_d, int64_t num_envs, int32_t 
     return e == cudaSuccess ? 0 : cuda_fail("sx_sample_kernel", e);
 }
 
+extern "C" int sx_heuristic_rewards(const sx_config *cfg, sx_state st, int64_t num_envs, const int32_t *actions_d,
+                                    int32_t action_format, const float *reward_matrix_d, float *rewards_d, void *stream)
+{
+    if (int rc = check_state(cfg, st, "sx_heuristic_rewards")) return rc;
+    if (!actions_d || !reward_matrix_d || !rewards_d) return fail("sx_heuristic_rewards: null argument");
+    if (action_format != SX_ACTION_SPATIAL && action_format != SX_ACTION_1D) return fail("sx_heuristic_rewards: unknown action format");
+    if (num_envs <= 0) return 0;
+    const int threads = 256;
+    sx_heuristic_kernel<<<unsigned((num_envs + threads - 1) / threads), threads, 0, static_cast<cudaStream_t>(stream)>>>(
+        cfg->dev, st.board, st.aux, num_envs, actions_d, action_format, reward_matrix_d, rewards_d);
+    cudaError_t e = cudaGetLastError();
+    return e == cudaSuccess ? 0 : cuda_fail("sx_heuristic_kernel", e);
+}
+
 extern "C" int sx_step_all_launch_info(const sx_config *cfg, uint32_t obs_mask, sx_launch_info *out)
 {
     if (!cfg || !out) return fail("sx_step_all_launch_info: null argument");
@@ -941,7 +998,7 @@ extern "C" int sx_step_all_launch_info(const sx_config *cfg, uint32_t obs_mask, 
     KernelArgs probe;
     std::memset(&probe, 0, sizeof(probe));
     probe.ops = ops;
-    if (int rc = plan_launch(cfg, ops, mode_for(probe), 1LL << 40, &plan)) return rc;
+    if (int rc = plan_launch(cfg, ops, mode_for(cfg, probe), 1LL << 40, &plan)) return rc;
     out->warps_per_block = plan.warps_per_block; out->blocks_per_sm = plan.blocks_per_sm;
     out->smem_bytes_per_block = plan.smem_per_block; out->num_sms = plan.num_sms; out->grid_blocks = plan.grid;
     out->regs_per_thread = plan.regs;

@@ -13,7 +13,8 @@ import numpy as np
 import torch
 
 from . import _lib
-from .config import (captured_lut, obstacle_map, piece_amounts_array, recent_moves_lut, unit_channel_lut)
+from .config import (captured_lut, obstacle_map, original_captured_lut, original_po_rank_lut, original_rank_lut,
+                     original_unit_lut, piece_amounts_array, recent_moves_lut, unit_channel_lut)
 from .enums import NUM_STATE_LAYERS
 
 DATA_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "data")
@@ -57,9 +58,14 @@ def _stream():
 
 class StrategoEngine:
     def __init__(self, game_version_config: dict, device=None, p2_rot180: bool = True, normalize: bool = True,
-                 capture_capacity: int = 0):
+                 capture_capacity: int = 0, obs_channel_mode: str = 'extended'):
         """normalize=False: observations carry the raw channel values of the procedural layer (penv:157-173)
-        instead of the env-level [-1, 1] normalisation (maenv:499-508)."""
+        instead of the env-level [-1, 1] normalisation (maenv:499-508).  obs_channel_mode='original' selects the
+        deprecated 32 / 33-channel observations (maenv:370-375, impl:1048-1197)."""
+        if obs_channel_mode not in ('extended', 'original'):
+            raise ValueError("obs_channel_mode must be 'extended' or 'original'")
+        self.obs_channel_mode = obs_channel_mode
+        original = obs_channel_mode == 'original'
         if not torch.cuda.is_available():
             raise _lib.StrategoB200Error("StrategoEngine needs a CUDA device; there is no CPU fallback")
         self.lib = _lib.load()
@@ -77,13 +83,21 @@ class StrategoEngine:
             desc.piece_amounts[i] = int(amounts[i])
         self._obst = np.ascontiguousarray(obstacle_map(cfg).reshape(-1), dtype=np.uint8)
         if normalize:
-            self._cap_lut = np.ascontiguousarray(captured_lut(cfg['piece_amounts']), dtype=np.float32)
+            self._cap_lut = np.ascontiguousarray((original_captured_lut if original else captured_lut)(cfg['piece_amounts']),
+                                                 dtype=np.float32)
             self._recent_lut = np.ascontiguousarray(recent_moves_lut(), dtype=np.float32)
-            self._unit_lut = np.ascontiguousarray(unit_channel_lut(), dtype=np.float32)
+            self._unit_lut = np.ascontiguousarray(original_unit_lut() if original else unit_channel_lut(), dtype=np.float32)
+            self._rank_lut = np.ascontiguousarray(original_rank_lut(), dtype=np.float32)
+            self._po_rank_lut = np.ascontiguousarray(original_po_rank_lut(), dtype=np.float32)
         else:
             self._cap_lut = np.ascontiguousarray(np.tile(np.arange(9, dtype=np.float32), (12, 1)))
             self._recent_lut = np.arange(-3, 2, dtype=np.float32)
             self._unit_lut = np.asarray([0.0, 1.0], dtype=np.float32)
+            self._rank_lut = np.arange(14, dtype=np.float32)
+            self._po_rank_lut = np.arange(14, dtype=np.float32)
+        desc.obs_channel_mode = _lib.SX_CHANNELS_ORIGINAL if original else _lib.SX_CHANNELS_EXTENDED
+        desc.rank_lut = self._rank_lut.ctypes.data
+        desc.po_rank_lut = self._po_rank_lut.ctypes.data
         desc.obstacles = self._obst.ctypes.data
         desc.captured_lut = self._cap_lut.ctypes.data
         desc.recent_lut = self._recent_lut.ctypes.data
@@ -98,6 +112,7 @@ class StrategoEngine:
         self.layout = lay
         self.cells = lay.cells
         self.spatial_channels = lay.spatial_channels
+        self.po_channels, self.fo_channels = lay.po_channels, lay.fo_channels
         self.spatial_action_size = (self.rows, self.columns, lay.spatial_channels)
         self.action_size = lay.action_size
 
@@ -132,9 +147,9 @@ class StrategoEngine:
             "player": torch.zeros(num_envs, dtype=torch.int8, device=d),
         }
         if partial:
-            out["partial_obs"] = torch.empty((num_envs, R, Cc, 67), dtype=torch.float32, device=d)
+            out["partial_obs"] = torch.empty((num_envs, R, Cc, self.po_channels), dtype=torch.float32, device=d)
         if full:
-            out["full_obs"] = torch.empty((num_envs, R, Cc, 79), dtype=torch.float32, device=d)
+            out["full_obs"] = torch.empty((num_envs, R, Cc, self.fo_channels), dtype=torch.float32, device=d)
         if mask:
             out["valid_mask"] = torch.empty((num_envs, R, Cc, self.spatial_channels), dtype=torch.uint8, device=d)
         if sample:
@@ -293,6 +308,21 @@ class StrategoEngine:
                                                  float(temperature), actions.data_ptr(), _ptr(logprob), _stream()),
                        "sx_sample_logits")
         return (actions, logprob) if return_logprob else actions
+
+    def heuristic_rewards(self, state: DeviceState, actions: torch.Tensor, reward_matrix: torch.Tensor,
+                          one_d: bool = False) -> torch.Tensor:
+        """impl:854-891 batched: reward_matrix[mover's rank at start, opponent's rank at end] of the action each game
+        is about to play (call before the step).  reward_matrix: float32 [13, 13]."""
+        assert actions.dtype == torch.int32 and actions.is_contiguous() and actions.shape == (state.num_envs,)
+        matrix = reward_matrix.to(self.device, dtype=torch.float32).contiguous()
+        assert matrix.shape == (13, 13), matrix.shape
+        rewards = torch.empty(state.num_envs, dtype=torch.float32, device=self.device)
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.sx_heuristic_rewards(self._cfg, state.as_struct(), state.num_envs, actions.data_ptr(),
+                                                     _lib.SX_ACTION_1D if one_d else _lib.SX_ACTION_SPATIAL,
+                                                     matrix.data_ptr(), rewards.data_ptr(), _stream()),
+                       "sx_heuristic_rewards")
+        return rewards
 
     def launch_info(self, partial=True, full=False, mask=True) -> dict:
         info = _lib.SxLaunchInfo()

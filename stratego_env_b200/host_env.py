@@ -43,9 +43,9 @@ class HostBufferEnv:
                      "next_action": pinned((B,), torch.int32)}
         if copy_obs:  # copy_obs=False: observations and mask stay on the device (scalars only cross PCIe)
             if partial:
-                self.host["partial_obs"] = pinned((B, R, Cc, 67), torch.float32)
+                self.host["partial_obs"] = pinned((B, R, Cc, engine.po_channels), torch.float32)
             if full:
-                self.host["full_obs"] = pinned((B, R, Cc, 79), torch.float32)
+                self.host["full_obs"] = pinned((B, R, Cc, engine.fo_channels), torch.float32)
             if mask:
                 self.host["valid_mask"] = pinned((B, R, Cc, A), torch.uint8)
         self._out = _lib.SxOutputs()

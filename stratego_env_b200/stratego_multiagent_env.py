@@ -8,9 +8,10 @@ numpy arrays with the reference's keys, shapes and dtypes (mask ``int64[R, C, A]
 behaviour (``ValueError`` on an illegal move, ``AssertionError`` when the wrong player acts).  It is
 meant for porting and parity checking -- throughput comes from ``batched_env.BatchedStrategoEnv``.
 
-Not carried over (outside the accelerated path): ``vs_human`` / ``vs_bot`` transports,
-curriculum ``.h5`` start states and the deprecated ``obs_channel_mode='original'``; asking for them
-raises ``NotImplementedError`` instead of silently doing something else.
+``obs_channel_mode='original'`` (the deprecated 32 / 33-channel observations, maenv:370-375) is rendered by the
+same kernel with the original channel map.  Not carried over (outside the accelerated path):
+``vs_human`` / ``vs_bot`` transports; asking for them raises ``NotImplementedError`` instead of silently doing
+something else.
 """
 import copy
 
@@ -66,20 +67,23 @@ class StrategoMultiAgentEnv:
         version_config = VERSION_CONFIGS[env_config['version']]
         env_config = with_base_config(base_config=version_config, extra_config=env_config)
 
-        for key, why in (('vs_human', "the web GUI transport"), ('vs_bot', "the external bot transport"),
-                         ('curriculum_start_states_path', "curriculum .h5 start states")):
+        for key, why in (('vs_human', "the web GUI transport"), ('vs_bot', "the external bot transport")):
             if env_config[key]:
                 raise NotImplementedError("%s (%s) is outside the accelerated path of this package" % (key, why))
-        if env_config['obs_channel_mode'] != 'extended':
-            raise NotImplementedError("obs_channel_mode='original' is deprecated upstream (impl:1049) and is not part "
-                                      "of the accelerated path")
+        if env_config['obs_channel_mode'] not in ('extended', 'original'):
+            raise ValueError("obs_channel_mode must be 'extended' or 'original'")
+        self._extended_channels = env_config['obs_channel_mode'] == 'extended'  # maenv:370
 
         rows, columns = env_config['rows'], env_config['columns']
         self.penalize_ties = env_config['penalize_ties']
         self.random_player_assignment = env_config['random_player_assignment']
         self.repeat_games_from_other_side = env_config['repeat_games_from_other_side']
+        assert not (env_config['human_inits'] and env_config['curriculum_start_states_path'])  # maenv:332
+        self.use_curriculum_inits = bool(env_config['curriculum_start_states_path'])
+        if self.use_curriculum_inits:  # maenv:346-351
+            self.random_player_assignment = True
+            self._curriculum = _setups.load_curriculum_table(env_config['curriculum_start_states_path'])
         assert not (self.random_player_assignment and self.repeat_games_from_other_side)
-        self.use_curriculum_inits = False
         self.vs_human = self.vs_bot = False
         self.observation_mode = env_config['observation_mode']
         if not isinstance(self.observation_mode, ObservationModes):
@@ -95,7 +99,8 @@ class StrategoMultiAgentEnv:
 
         # the engine: human tables are stored row-mirrored for player -1 (util:241-275), toy setups rotated (impl:221)
         self._engine = StrategoEngine({k: env_config[k] for k in version_config}, device=device,
-                                      p2_rot180=not self._human_inits)
+                                      p2_rot180=not self._human_inits, obs_channel_mode=env_config['obs_channel_mode'])
+        self._p_obs_num_layers, self._f_obs_num_layers = self._engine.po_channels, self._engine.fo_channels
         self.base_env = StrategoProceduralEnv(rows=rows, columns=columns, device=self._engine.device)
         self._dev = self._engine.device
         self._table = (self._engine.upload_setups(load_setup_table(HUMAN_INIT_TABLE[env_config['version']]))
@@ -124,10 +129,10 @@ class StrategoMultiAgentEnv:
                                                                      shape=self.base_env.spatial_action_size)}
         if self._want_po:
             space[ObservationComponents.PARTIAL_OBSERVATION.value] = Box(low=np.float32(-1.0), high=np.float32(1.0),
-                                                                         shape=(rows, columns, PO_CHANNELS))
+                                                                         shape=(rows, columns, self._p_obs_num_layers))
         if self._want_fo:
             space[ObservationComponents.FULL_OBSERVATION.value] = Box(low=np.float32(-1.0), high=np.float32(1.0),
-                                                                      shape=(rows, columns, FO_CHANNELS))
+                                                                      shape=(rows, columns, self._f_obs_num_layers))
         if self.observation_includes_internal_state:
             space[ObservationComponents.INTERNAL_STATE.value] = Box(low=np.float32(-np.inf), high=np.float32(np.inf),
                                                                     shape=(34, rows, columns))
@@ -192,7 +197,15 @@ class StrategoMultiAgentEnv:
 
     # ---- reset (maenv:513-657) --------------------------------------------------------------------------
     def reset(self, first_player_override=None, initial_state_override=None):
-        if self.repeat_games_from_other_side and self.episodes_completed % 2 == 1:
+        if self.use_curriculum_inits:  # maenv:519-527
+            initial_state, likely_winner = _setups.draw_curriculum_state(*self._curriculum,
+                                                                         self._game_version_config['max_turns'])
+            self.player = int(np.random.choice([-1, 1]))
+            self._load_state(initial_state, self.player)
+            # player 1 gets the advantage of the curriculum start
+            self.player_map = lambda p: likely_winner if p == 1 else (-likely_winner if p == -1 else p)
+            self.reverse_player_map = lambda p: 1 if p == likely_winner else (-1 if p == -likely_winner else p)
+        elif self.repeat_games_from_other_side and self.episodes_completed % 2 == 1:
             assert not self.random_player_assignment
             initial_state = self.base_env.get_state_from_player_perspective(state=self.last_initial_state, player=-1)
             self.player = -1
@@ -207,7 +220,7 @@ class StrategoMultiAgentEnv:
                     self.reverse_player_map = lambda p: -p if p != "__all__" else p
             self._apply_setup(self._fixed_setup if self._fixed_setup is not None else self._draw_setup())
             self.player = 1
-        if self.repeat_games_from_other_side:
+        if self.repeat_games_from_other_side and not self.use_curriculum_inits:
             self.last_initial_state = self.state.copy()
 
         if initial_state_override is not None:

@@ -12,6 +12,7 @@ done on the host are scalar index arithmetic (the action codecs, impl:253-396 / 
 assembly of an initial state from caller-provided piece maps (impl:213-249), neither of which is a
 kernel in the reference's hot loop (the batched reset kernel covers sampled setups).
 """
+from pickle import dumps
 from typing import Tuple
 
 import numpy as np
@@ -39,6 +40,7 @@ class StrategoProceduralEnv(object):
         cfg = {'rows': R, 'columns': C, 'max_turns': 1, 'obstacle_locations': [], 'piece_amounts': {},
                'initial_state_usable_rows': 1}
         self._engine = StrategoEngine(cfg, device=device, normalize=False, capture_capacity=R * C)
+        self._engine_original = None
         A = int(self.spatial_action_size[2])
         # channel of the same move after a 180-degree rotation: +row <-> -row, +col <-> -col, noop stays
         perm = np.arange(A)
@@ -155,6 +157,25 @@ class StrategoProceduralEnv(object):
         st = self._import(state, player)
         return self._engine.valid_mask(st, one_d=True).cpu().numpy()[0].astype(INT_DTYPE_NP)
 
+    def get_dict_of_valid_moves_by_position(self, state: np.ndarray, player):
+        """penv:82 -> impl:1400-1429: {"start_r,start_c": [[end_r, end_c], ...]} in ascending 1D-index order, the
+        structure the reference's web GUI / bot side channels consume (stratego_human_server.py:153-179).  The mask
+        comes from the device; only the index decode (impl:352-383) runs here.  A no-op-only mask (stuck player,
+        finished game) raises ValueError like the reference's decoder does (impl:355-367)."""
+        mask = self.get_valid_moves_as_1d_mask(state, player)
+        moves = {}
+        for action in np.flatnonzero(mask):
+            start_r, start_c, end_r, end_c = self.get_action_positions_from_1d_index(int(action))
+            moves.setdefault("{},{}".format(start_r, start_c), []).append([end_r, end_c])
+        return moves
+
+    def get_heuristic_rewards_from_move(self, state: np.ndarray, player, action_index, reward_matrix):
+        """impl:854-891 (not exposed by penv upstream): reward_matrix[mover's rank, captured rank] of a valid move"""
+        st = self._import(state, player)
+        action = torch.tensor([int(action_index)], dtype=torch.int32, device=self._engine.device)
+        matrix = torch.as_tensor(np.asarray(reward_matrix, dtype=np.float32))
+        return np.float32(self._engine.heuristic_rewards(st, action, matrix, one_d=True).item())
+
     def is_move_valid_by_1d_index(self, state: np.ndarray, player, action_index, allow_piece_oscillation=False):
         st = self._import(state, player)
         out = self._engine.step(st, torch.tensor([int(action_index)], dtype=torch.int32, device=self._engine.device),
@@ -207,8 +228,32 @@ class StrategoProceduralEnv(object):
         out = self._engine.observe(st, partial=True, full=False, mask=False)
         return out["partial_obs"].cpu().numpy()[0]   # in `player`'s frame, like impl:1338
 
-    def get_fully_observable_observation(self, state, player):
-        raise NotImplementedError("the deprecated 'original' observation channels (impl:1048-1197) are not part of "
-                                  "the accelerated path; use the *_extended_channels getters")
+    # the deprecated 'original' channels (penv:157-163 -> impl:1075-1123 / impl:1153-1197): one raw-valued channel per
+    # state layer; rendered by the same kernel with the original channel map (a second engine object, made on first use)
+    def _original_engine(self):
+        if self._engine_original is None:
+            self._engine_original = StrategoEngine(self._engine.game_version_config, device=self._engine.device,
+                                                   normalize=False, capture_capacity=int(self.rows) * int(self.columns),
+                                                   obs_channel_mode='original')
+        return self._engine_original
 
-    get_partially_observable_observation = get_fully_observable_observation
+    def _observe_original(self, state, player, full):
+        eng = self._original_engine()
+        st = self._import(state, player)   # the compact state layout does not depend on the channel mode
+        out = eng.observe(st, partial=not full, full=full, mask=False)
+        return out["full_obs" if full else "partial_obs"].cpu().numpy()[0]
+
+    def get_fully_observable_observation(self, state, player):
+        return self._observe_original(state, player, full=True)
+
+    def get_partially_observable_observation(self, state, player):
+        return self._observe_original(state, player, full=False)
+
+    def get_serializable_string_for_fully_observable_state(self, state: np.ndarray):
+        return dumps(self.get_fully_observable_observation(state, 1))        # penv:175-177
+
+    def get_serializable_string_for_partially_observable_state(self, state: np.ndarray):
+        return dumps(self.get_partially_observable_observation(state, 1))    # penv:179-181
+
+    def print_board_to_console(self, state, partially_observable=False, hide_still_piece_markers=True):
+        raise NotImplementedError("the console printer (penv:183-232) is a debugging aid outside the accelerated path")

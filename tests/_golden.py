@@ -26,6 +26,14 @@ def known():
     return load("known_answers")
 
 
+def original_channels():
+    return load("original_channels")
+
+
+def side_channels():
+    return load("side_channels")
+
+
 def unpack_mask(bits, n):
     return np.unpackbits(bits, axis=-1)[..., :n]
 

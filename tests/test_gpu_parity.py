@@ -168,3 +168,88 @@ def test_reset_from_setup_table_matches_reference(tag):
     dense, player = eng.export_ref_state(st)
     assert np.array_equal(dense.cpu().numpy(), k["setup_%s_states" % tag].astype(np.int64))
     assert (player == 1).all().item()
+
+
+# ---- deprecated obs_channel_mode='original' (maenv:370-375): 32 / 33 raw-value channels ------------------------
+def _engine_original(version, normalize=True):
+    from stratego_env_b200.config import VERSION_CONFIGS, as_version
+    from stratego_env_b200.engine import StrategoEngine
+    return StrategoEngine(VERSION_CONFIGS[as_version(version)], device="cuda:0", obs_channel_mode="original",
+                          normalize=normalize)
+
+
+@pytest.mark.parametrize("version", VERSIONS)
+def test_original_channels_observe_vs_golden_and_oracle(version):
+    """sx_observe in the original channel mode against the reference's own 32 / 33-channel observations"""
+    from oracle.binding import OracleEnvLogic
+    from stratego_env_b200.config import VERSION_CONFIGS, as_version
+    from _golden import original_channels
+    t, g = traj(version), original_channels()
+    cfg = VERSION_CONFIGS[as_version(version)]
+    eng = _engine_original(version)
+    orc = OracleEnvLogic(cfg["rows"], cfg["columns"], cfg["piece_amounts"], obs_channel_mode="original")
+    assert (eng.po_channels, eng.fo_channels) == (32, 33)
+    states = t["states"].astype(np.int64)
+    pick, who = g["orig_%s_state_index" % version], g["orig_%s_player" % version]
+    st = eng.import_ref_state(_t(states[pick], torch.int64), _t(who, torch.int8))
+    out = eng.observe(st, _t(who, torch.int8))
+    torch.cuda.synchronize()
+    po, fo = out["partial_obs"].cpu().numpy(), out["full_obs"].cpu().numpy()
+    assert po.shape[1:] == (cfg["rows"], cfg["columns"], 32) and fo.shape[1:] == (cfg["rows"], cfg["columns"], 33)
+    assert np.array_equal(_bits(po), _bits(g["orig_%s_po" % version])), version
+    assert np.array_equal(_bits(fo), _bits(g["orig_%s_fo" % version])), version
+    # every recorded state, both players, against the oracle
+    st = eng.import_ref_state(_t(states, torch.int64), _t(t["players"], torch.int8))
+    for sign in (1, -1):
+        viewer = (t["players"].astype(np.int64) * sign).astype(np.int8)
+        out = eng.observe(st, _t(viewer, torch.int8))
+        torch.cuda.synchronize()
+        mask, po, fo = (out[k].cpu().numpy() for k in ("valid_mask", "partial_obs", "full_obs"))
+        for i in range(0, len(states), 5):
+            m_o, po_o, fo_o = orc.current_obs(states[i], int(viewer[i]), 3)
+            assert np.array_equal(mask[i], m_o), (version, i, sign)
+            assert np.array_equal(_bits(po[i]), _bits(po_o)), (version, i, sign)
+            assert np.array_equal(_bits(fo[i]), _bits(fo_o)), (version, i, sign)
+
+
+@pytest.mark.parametrize("version", ["barrage", "standard", "micro", "fives", "standard2"])
+def test_original_channels_fused_step(version):
+    """the fused step (sx_step_all) renders the original channels of the NEXT state; odd offsets included (a game's
+    33-channel observation is not a multiple of 16 bytes)"""
+    from oracle.binding import OracleEnvLogic
+    from stratego_env_b200.config import VERSION_CONFIGS, as_version
+    t = traj(version)
+    cfg = VERSION_CONFIGS[as_version(version)]
+    eng = _engine_original(version)
+    orc = OracleEnvLogic(cfg["rows"], cfg["columns"], cfg["piece_amounts"], obs_channel_mode="original")
+    idx = transitions(t)[:257]
+    states = t["states"].astype(np.int64)
+    st = eng.import_ref_state(_t(states[idx], torch.int64), _t(t["players"][idx], torch.int8))
+    out = eng.alloc_outputs(len(idx), partial=True, full=True, mask=True)
+    eng.step_all(st, _t(t["actions_spatial"][idx], torch.int32), out)
+    dense, _ = eng.export_ref_state(st)
+    torch.cuda.synchronize()
+    assert np.array_equal(dense.cpu().numpy(), states[idx + 1])
+    po, fo, mask = (out[k].cpu().numpy() for k in ("partial_obs", "full_obs", "valid_mask"))
+    for row, i in enumerate(idx):
+        m_o, po_o, fo_o = orc.current_obs(states[i + 1], int(t["players"][i + 1]), 3)
+        assert np.array_equal(mask[row], m_o)
+        assert np.array_equal(_bits(po[row]), _bits(po_o)), (version, i)
+        assert np.array_equal(_bits(fo[row]), _bits(fo_o)), (version, i)
+
+
+def test_original_channels_raw_facade_getters():
+    """penv.get_partially_observable_observation / get_fully_observable_observation (penv:157-163), un-normalised"""
+    from oracle.binding import OracleProceduralEnv
+    from stratego_env_b200 import StrategoProceduralEnv
+    for version in ("barrage", "micro"):
+        t = traj(version)
+        R, C = int(t["rows"]), int(t["columns"])
+        env, orc = StrategoProceduralEnv(R, C, device="cuda:0"), OracleProceduralEnv(R, C)
+        states = t["states"].astype(np.int64)
+        for i in range(0, len(states), 97):
+            for p in (1, -1):
+                assert np.array_equal(_bits(env.get_partially_observable_observation(states[i], p)),
+                                      _bits(orc.get_partially_observable_observation(states[i], p)))
+                assert np.array_equal(_bits(env.get_fully_observable_observation(states[i], p)),
+                                      _bits(orc.get_fully_observable_observation(states[i], p)))

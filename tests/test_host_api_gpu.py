@@ -84,6 +84,125 @@ def test_multiagent_env_replays_reference_run(version):
     assert games >= 1
 
 
+@pytest.mark.parametrize("version", ["barrage", "micro", "fives"])
+def test_multiagent_env_original_channel_mode(version):
+    """obs_channel_mode='original' (maenv:370-375) through the drop-in env: replay the recorded games and compare the
+    32 / 33-channel observation dicts with the reference's (tests/golden/original_channels.npz)"""
+    from stratego_env_b200 import GameVersions, ObservationComponents as OC, ObservationModes, StrategoMultiAgentEnv
+    from _golden import original_channels
+    human, seed = RECORDED[version]
+    t, g = traj(version), original_channels()
+    np.random.seed(seed)
+    random.seed(seed)
+    env = StrategoMultiAgentEnv({"version": GameVersions(version), "human_inits": human, "obs_channel_mode": "original",
+                                 "observation_mode": ObservationModes.BOTH_OBSERVATIONS})
+    R, C = int(t["rows"]), int(t["columns"])
+    assert env.observation_space.spaces[OC.PARTIAL_OBSERVATION.value].shape == (R, C, 32)
+    assert env.observation_space.spaces[OC.FULL_OBSERVATION.value].shape == (R, C, 33)
+    golden = {(int(k), int(p)): j for j, (k, p) in enumerate(zip(g["orig_%s_state_index" % version],
+                                                                  g["orig_%s_player" % version]))}
+    states = t["states"].astype(np.int64)
+    i, checked, obs = 0, 0, None
+    while i < min(len(states) - 1, 400):
+        if t["game_start"][i]:
+            obs = env.reset()
+        player = int(t["players"][i])
+        assert np.array_equal(env.state, states[i]), (version, i)
+        for p, o in obs.items():
+            j = golden.get((i, int(p)))
+            if j is not None:
+                assert np.array_equal(_bits(o[OC.PARTIAL_OBSERVATION.value]), _bits(g["orig_%s_po" % version][j]))
+                assert np.array_equal(_bits(o[OC.FULL_OBSERVATION.value]), _bits(g["orig_%s_fo" % version][j]))
+                checked += 1
+        if t["actions_spatial"][i] < 0:
+            i += 1  # terminal record: the next row starts a new game
+            continue
+        obs, _, dones, _ = env.step({player: int(t["actions_spatial"][i])})
+        i += 1
+    assert checked >= 3
+
+
+@pytest.mark.parametrize("version", ["barrage", "micro", "octa_barrage"])
+def test_side_channels(version):
+    """batched heuristic-reward kernel (impl:854-891), the facade's valid-move dict (impl:1400-1429)
+    and the pickled original-channel state strings (penv:175-181), against reference-generated vectors"""
+    import json
+    import pickle
+    from _golden import side_channels
+    from oracle.binding import OracleProceduralEnv
+    from stratego_env_b200 import StrategoProceduralEnv
+    from stratego_env_b200.config import VERSION_CONFIGS, as_version
+    from stratego_env_b200.engine import StrategoEngine
+    t, g = traj(version), side_channels()
+    R, C = int(t["rows"]), int(t["columns"])
+    states = t["states"].astype(np.int64)
+    idx, matrix = g["heuristic_%s_index" % version], g["heuristic_matrix"]
+    eng = StrategoEngine(VERSION_CONFIGS[as_version(version)], device="cuda:0")
+    st = eng.import_ref_state(torch.as_tensor(states[idx]), torch.as_tensor(t["players"][idx]))
+    for one_d, key in ((True, "actions_1d"), (False, "actions_spatial")):
+        acts = torch.as_tensor(t[key][idx].astype(np.int32), device="cuda:0")
+        got = eng.heuristic_rewards(st, acts, torch.as_tensor(matrix), one_d=one_d).cpu().numpy()
+        assert np.array_equal(_bits(got), _bits(g["heuristic_%s_reward" % version])), (version, one_d)
+    noop = torch.full((len(idx),), eng.action_size - 1, dtype=torch.int32, device="cuda:0")
+    assert not eng.heuristic_rewards(st, noop, torch.as_tensor(matrix), one_d=True).any().item()
+    env, orc = StrategoProceduralEnv(R, C, device="cuda:0"), OracleProceduralEnv(R, C)
+    for i, text in zip(g["moves_%s_index" % version], g["moves_%s_json" % version]):
+        assert env.get_dict_of_valid_moves_by_position(states[i], int(t["players"][i])) == json.loads(str(text))
+    k = int(idx[3])
+    assert np.float32(env.get_heuristic_rewards_from_move(states[k], int(t["players"][k]), int(t["actions_1d"][k]),
+                                                          matrix)) == g["heuristic_%s_reward" % version][3]
+    blob = pickle.loads(env.get_serializable_string_for_partially_observable_state(states[k]))
+    assert np.array_equal(_bits(blob), _bits(orc.get_partially_observable_observation(states[k], 1)))
+    blob = pickle.loads(env.get_serializable_string_for_fully_observable_state(states[k]))
+    assert np.array_equal(_bits(blob), _bits(orc.get_fully_observable_observation(states[k], 1)))
+    # a finished game has a no-op-only mask: the reference's decoder raises (impl:355-367)
+    last = np.flatnonzero(t["dones"])
+    if len(last):
+        with pytest.raises(ValueError):
+            env.get_dict_of_valid_moves_by_position(states[int(last[0]) + 1], 1)
+
+
+def test_multiagent_env_curriculum_start_states(tmp_path):
+    """curriculum_start_states_path (maenv:346-351, 519-527): start from a stored mid-game state, random first player,
+    player ids remapped so that player 1 is the side expected to win"""
+    from stratego_env_b200 import GameVersions, ObservationComponents as OC, ObservationModes, StrategoMultiAgentEnv
+    from oracle.binding import OracleEnvLogic
+    from stratego_env_b200.config import BARRAGE_STRATEGO_CONFIG as CFG
+    t = traj("barrage")
+    pick = np.flatnonzero(~t["dones"] & (t["actions_spatial"] >= 0))[40:72]
+    states = t["states"][pick].astype(np.int64)
+    winners = np.where(np.arange(len(pick)) % 2 == 0, 1, -1)
+    path = str(tmp_path / "curriculum.npz")
+    np.savez(path, state=states, winner=winners)
+    env = StrategoMultiAgentEnv({"version": GameVersions.BARRAGE, "curriculum_start_states_path": path,
+                                 "observation_mode": ObservationModes.PARTIALLY_OBSERVABLE})
+    assert env.use_curriculum_inits and env.random_player_assignment
+    orc = OracleEnvLogic(10, 10, CFG["piece_amounts"])
+    for seed in range(6):
+        np.random.seed(seed)
+        offset = np.random.randint(low=0, high=len(states))
+        first = int(np.random.choice([-1, 1]))
+        np.random.seed(seed)
+        obs = env.reset()
+        expect = states[offset].copy()
+        expect[5, 0, 0], expect[5, 1, 0] = 0, CFG["max_turns"]
+        assert np.array_equal(env.state, expect) and env.player == first
+        likely = int(winners[offset])
+        agent = likely if first == 1 else -likely   # maenv:526
+        assert list(obs.keys()) == [agent]
+        mask, po, _ = orc.current_obs(expect, first, 1)
+        assert np.array_equal(obs[agent][OC.VALID_ACTIONS_MASK.value], mask)
+        assert np.array_equal(_bits(obs[agent][OC.PARTIAL_OBSERVATION.value]), _bits(po))
+        action = int(np.flatnonzero(mask.reshape(-1))[0])
+        with pytest.raises(AssertionError):
+            env.step({-agent: action})
+        obs, rewards, dones, _ = env.step({agent: action})
+        if not dones["__all__"]:
+            assert list(obs.keys()) == [-agent]
+        ns, _ = orc.apply_spatial_action(expect, first, action)
+        assert np.array_equal(env.state, ns)
+
+
 def test_multiagent_env_errors_and_options():
     from stratego_env_b200 import GameVersions, ObservationComponents as OC, ObservationModes, StrategoMultiAgentEnv
     t = traj("barrage")
@@ -108,9 +227,11 @@ def test_multiagent_env_errors_and_options():
     obs, _, _, _ = env.step({env.player: int(t["actions_spatial"][0])})
     flipped = OracleProceduralEnv(10, 10).get_state_from_player_perspective(t["states"][1].astype(np.int64), -1)
     assert np.array_equal(obs[-1][OC.INTERNAL_STATE.value], flipped)
-    for bad in ({"vs_human": True}, {"vs_bot": True}, {"obs_channel_mode": "original"}):
+    for bad in ({"vs_human": True}, {"vs_bot": True}):
         with pytest.raises(NotImplementedError):
             StrategoMultiAgentEnv(dict(version=GameVersions.TINY, **bad))
+    with pytest.raises(ValueError):
+        StrategoMultiAgentEnv({"version": GameVersions.TINY, "obs_channel_mode": "compact"})
     with pytest.raises(ValueError):
         StrategoMultiAgentEnv({"version": GameVersions.TINY, "human_inits": True})
 

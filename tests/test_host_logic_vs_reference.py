@@ -88,3 +88,65 @@ def test_human_setup_sampler_and_table_equal_reference(version):
         # own-frame maps: player 1 as is; the table stores player 2's map in its own frame too (row-mirrored on
         # the board by the reset kernel, p2_rot180 = False), i.e. the same transform as player 1's
         assert np.array_equal(table[int(rows[0])].reshape(4, 10), pos[0][:4])
+
+
+def test_curriculum_start_states_consume_rng_like_reference(tmp_path, monkeypatch):
+    """util:322-387: the reference reads one row of an HDF5 file per reset (h5py is absent from this image, so its
+    File object is stood in for by a dict of numpy arrays); same offset draw, same state edits, same likely winner.
+    The reference's wrapper get_random_curriculum_init_fn itself cannot run under numpy >= 1.24 (util:377 squeezes a
+    ragged (array, int) tuple), so its reader load_h5 (util:322-369) is driven directly, in the wrapper's order."""
+    import sys
+    import_reference()
+    from stratego_env.game import util as ref_util
+    from _golden import traj
+    t = traj("barrage")
+    states = t["states"][:64].astype(np.int64)
+    winners = np.where(np.arange(64) % 3 == 0, -1, 1).astype(np.int64)
+
+    class FakeGroup:  # nothing in the fake file is a group
+        pass
+
+    class FakeFile(dict):
+        def __init__(self, fname, mode):
+            super().__init__(state=states.astype(np.float64), winner=winners.astype(np.float64))
+
+        def close(self):
+            pass
+
+    monkeypatch.setattr(sys.modules["h5py"], "File", FakeFile, raising=False)
+    monkeypatch.setattr(sys.modules["h5py"], "Group", FakeGroup, raising=False)
+    path = str(tmp_path / "curriculum.npz")
+    np.savez(path, state=states, winner=winners)
+    table = my_setups.load_curriculum_table(path)
+    def ref_fn():  # util:373-385
+        state, offset = ref_util.load_h5(fname="unused.h5", key='state', num_samples_to_load=1, read_offset=-1)
+        winner, w_offset = ref_util.load_h5(fname="unused.h5", key='winner', num_samples_to_load=1, read_offset=offset)
+        assert offset == w_offset
+        state = np.squeeze(state)
+        state[5, 0, 0] = 0.0
+        state[5, 1, 0] = 1000
+        return state, int(np.squeeze(winner))
+
+    for seed in (0, 5, 77):
+        np.random.seed(seed)
+        ref_state, ref_winner = ref_fn()
+        ref_next = np.random.random()
+        np.random.seed(seed)
+        state, winner = my_setups.draw_curriculum_state(*table, 1000)
+        assert np.random.random() == ref_next  # same number of draws
+        assert winner == ref_winner and np.array_equal(state, ref_state.astype(np.int64))
+        assert state[5, 0, 0] == 0 and state[5, 1, 0] == 1000
+
+
+def test_valid_move_dict_raises_on_noop_only_mask_like_reference():
+    """impl:1400-1429 decodes every set index, so a finished game's no-op-only mask raises (impl:355-367)"""
+    import_reference()
+    from stratego_env.game.stratego_procedural_env import StrategoProceduralEnv
+    from oracle.binding import OracleProceduralEnv
+    from _golden import traj
+    t = traj("micro")
+    k = int(np.flatnonzero(t["dones"])[0]) + 1
+    state = t["states"][k].astype(np.int64)
+    for env in (StrategoProceduralEnv(3, 4), OracleProceduralEnv(3, 4)):
+        with pytest.raises(ValueError):
+            env.get_dict_of_valid_moves_by_position(state, 1)

@@ -5,7 +5,7 @@ import pytest
 from oracle.binding import OracleEnvLogic, OracleProceduralEnv
 from stratego_env_b200.config import VERSION_CONFIGS, as_version
 
-from _golden import VERSIONS, known, traj, transitions, unpack_mask
+from _golden import VERSIONS, known, original_channels, side_channels, traj, transitions, unpack_mask
 
 
 def bits_equal(a, b):
@@ -57,6 +57,44 @@ def test_trajectory_observations_bitwise(version):
             assert bits_equal(po, t["term_po"][j]) and bits_equal(fo, t["term_fo"][j])
             # terminal masks are noop-only (impl:414, 514-515)
             assert mask.sum() == 1 and mask[0, 0, A - 1] == 1
+
+
+@pytest.mark.parametrize("version", VERSIONS)
+def test_original_channel_observations_bitwise(version):
+    """obs_channel_mode='original' (maenv:370-375): 32 / 33 raw-value channels + their normaliser (maenv:87-199)"""
+    t, g = traj(version), original_channels()
+    R, C = int(t["rows"]), int(t["columns"])
+    cfg = VERSION_CONFIGS[as_version(version)]
+    logic = OracleEnvLogic(R, C, cfg["piece_amounts"], obs_channel_mode="original")
+    ph, pl, fh, fl = logic.obs_highs_lows()
+    assert bits_equal(ph, g["orig_%s_p_highs" % version]) and bits_equal(pl, g["orig_%s_p_lows" % version])
+    assert bits_equal(fh, g["orig_%s_f_highs" % version]) and bits_equal(fl, g["orig_%s_f_lows" % version])
+    states = t["states"].astype(np.int64)
+    for j, (k, p) in enumerate(zip(g["orig_%s_state_index" % version], g["orig_%s_player" % version])):
+        _, po, fo = logic.current_obs(states[k], int(p), obs_mode=3)
+        assert po.shape == (R, C, 32) and fo.shape == (R, C, 33)
+        assert bits_equal(po, g["orig_%s_po" % version][j]), (version, k)
+        assert bits_equal(fo, g["orig_%s_fo" % version][j]), (version, k)
+        # the raw facade getters (penv:157-163) de-normalise to the same planes
+        raw = logic.base_env.get_partially_observable_observation(states[k], int(p))
+        mid, rng = (ph + pl) / np.float32(2), (ph - pl) / np.float32(2)
+        assert bits_equal((raw - mid) / rng, po)
+
+
+@pytest.mark.parametrize("version", ["barrage", "standard", "micro", "octa_barrage"])
+def test_side_channels(version):
+    """heuristic reward lookup (impl:854-891) and the valid-move dict of the GUI / bot side channel (impl:1400-1429)"""
+    import json
+    t, g = traj(version), side_channels()
+    env = OracleProceduralEnv(int(t["rows"]), int(t["columns"]))
+    states = t["states"].astype(np.int64)
+    matrix = g["heuristic_matrix"]
+    for i, r in zip(g["heuristic_%s_index" % version], g["heuristic_%s_reward" % version]):
+        got = env.get_heuristic_rewards_from_move(states[i], int(t["players"][i]), int(t["actions_1d"][i]), matrix)
+        assert np.float32(got).view(np.uint32) == np.float32(r).view(np.uint32), (version, i)
+    assert env.get_heuristic_rewards_from_move(states[0], 1, env.action_size - 1, matrix) == 0  # impl:866-868
+    for i, text in zip(g["moves_%s_index" % version], g["moves_%s_json" % version]):
+        assert env.get_dict_of_valid_moves_by_position(states[i], int(t["players"][i])) == json.loads(str(text))
 
 
 @pytest.mark.parametrize("tag", ["10x10", "3x4", "4x4"])
