@@ -174,6 +174,11 @@ __global__ void __launch_bounds__(K <= 2 ? 1024 : SX_MAX_THREADS, 1) sx_fused_ke
     };
     auto issue_background = [&](long long e) {
         if (flags & 0x10000u) return;  // experiment switch
+        // the small mask copy goes first (measured: +3 % over observation-first at 10 warps per SM)
+        if (do_mask) {
+            uint8_t *gmask = args.out.valid_mask + e * cfg.mask_bytes;
+            emit_tile<GT>(gmask, bg.mask + (reinterpret_cast<uintptr_t>(gmask) & 15), cfg.mask_bytes, pol_stream);
+        }
         if (do_po) {
             float *g = args.out.partial_obs + e * cfg.po_floats;
             const int k = align_rows(pom.channels, int((reinterpret_cast<uintptr_t>(g) >> 2) & 3));
@@ -186,10 +191,6 @@ __global__ void __launch_bounds__(K <= 2 ? 1024 : SX_MAX_THREADS, 1) sx_fused_ke
             emit_tile<GT>(reinterpret_cast<uint8_t *>(g), reinterpret_cast<const uint8_t *>(bg.fo + k * fom.channels),
                           cfg.fo_floats * 4, pol_stream);
         }
-        if (do_mask) {
-            uint8_t *gmask = args.out.valid_mask + e * cfg.mask_bytes;
-            emit_tile<GT>(gmask, bg.mask + (reinterpret_cast<uintptr_t>(gmask) & 15), cfg.mask_bytes, pol_stream);
-        }
         if (lane == 0) bulk_commit();
     };
 
@@ -197,10 +198,12 @@ __global__ void __launch_bounds__(K <= 2 ? 1024 : SX_MAX_THREADS, 1) sx_fused_ke
     const long long total_warps = (long long)gridDim.x * warps_per_block;
     long long env = (long long)blockIdx.x * warps_per_block + warp;
     Prefetched pf;
-    // Where a game's background copy is issued.  The sparse entries must reach L2 while the background lines
-    // are still resident there (otherwise every 4-byte store becomes a DRAM read-modify-write), so the copy is
-    // issued late: after the rules, right before the (short) wait.  SX_DEBUG bits 4-5 select the point for
-    // experiments: 0 = late (default), 1 = after the outcome / before write-back and sampling, 2 = top of the game.
+    // Where a game's background copy is issued.  The sparse entries must reach L2 while the background lines are
+    // still resident there (otherwise every 4-byte store becomes a DRAM read-modify-write; measured: storing them one
+    // whole game later costs 10-25 %), and the warp should have work to do while its copy drains.  0 = late, right
+    // before the wait; 1 = after the outcome, before state write-back and sampling (best for a 10x10 board with one
+    // observation: ~400 instructions overlap the drain); 2 = top of the game.  sx_step_all picks per variant
+    // (SX_DEBUG bits 4-5 override).
     const int issue_at = (flags >> 20) & 3;
     if (env < args.num_envs) load_state(env, pf);
     for (; env < args.num_envs; env += total_warps) {
@@ -761,7 +764,8 @@ static int plan_launch_uncached(const sx_config *cfg, uint32_t ops, int mode, lo
     const int max_warps = std::max(1, std::min(attr.maxThreadsPerBlock / 32, 32));
     // Measured on B200: throughput peaks when ~0.4 MB of output per SM is in flight and falls beyond it (more
     // resident warps only lengthen the TMA completion queue), so fewer warps for bigger per-game outputs.
-    const int preferred = tile_bytes <= 8 * 1024 ? 32 : tile_bytes <= 32 * 1024 ? (2 * cfg->dev.n_pieces <= 24 ? 10 : 12)
+    // 8 warps is a sharp optimum for one 10x10 observation + mask (7: -11 %, 9 and more: -3 to -12 %, not monotonic).
+    const int preferred = tile_bytes <= 8 * 1024 ? 32 : tile_bytes <= 32 * 1024 ? (cfg->dev.N >= 100 ? 8 : 10)
                           : tile_bytes <= 64 * 1024 ? 6 : 4;
     int warps = std::min(max_warps, std::max(1, env_int("SX_WARPS", std::min(max_warps, preferred))));
     const int games = cfg->games_per_warp;  // each game of a warp has its own slice
@@ -951,7 +955,11 @@ extern "C" int sx_step_all(const sx_config *cfg, sx_state st, int64_t num_envs, 
     // bits 16+: tuning / experiment switches (SX_DEBUG overrides): 1 skip TMA, 2 skip wait + sparse stores, 4 plain L2
     // policy, 8 skip sparse stores, 16/32 background issue point.  Sparse boards (Barrage-like) gain from issuing the
     // background at the top of the game; dense boards need it late so the sparse stores still hit L2 (see kernel).
-    const int tune = env_int("SX_DEBUG", (cfg->dev.N >= 64 && 2 * cfg->dev.n_pieces <= 24) ? 32 : 0);
+    // B200 sweeps (tools/sweep_fused.py, profiles/r1k_sweep*.txt): a 10x10 board with ONE observation is fastest with the
+    // copy issued after the outcome (16) at 8 warps per SM; both observations and the toy boards issue late (0).
+    const bool one_obs = (out.partial_obs != nullptr) != (out.full_obs != nullptr);
+    const int n = cfg->dev.N;
+    const int tune = env_int("SX_DEBUG", (n >= 100 && n <= 128 && one_obs) ? 16 : (n >= 64 && 2 * cfg->dev.n_pieces <= 24) ? 32 : 0);
     a.flags = (flags & 0xffffu) | (uint32_t(tune) << 16);
     a.out = out;
     a.ops = step_all_ops(out, flags);

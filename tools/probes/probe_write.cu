@@ -51,7 +51,10 @@ __global__ void k_tma(uint8_t *p, size_t n_tiles, int tile) {
 }
 // the engine's output layout: per game a 26 800 B observation (16 B aligned) and a 3 700 B mask row (4 B aligned),
 // written with the same TMA bulk + head/tail word stores, nothing else (no logic, no sparse entries)
-__global__ void k_layout(uint8_t *obs, uint8_t *mask, size_t n_envs, int obs_bytes, int mask_bytes, int wait_read, const uint32_t *state = nullptr, uint32_t *sink = nullptr) {
+// state_mode: 0 none; 1 per-game ~176 B state reads (scattered among the output stream); 2 per-game reads + write-back;
+// 3 reads from a small L2-resident buffer (what a resident state would cost); 4 contiguous 32-game chunks per warp:
+// one coalesced 5.6 KB state read per chunk; 5 = 4 + coalesced write-back per chunk; 6 contiguous chunks, no state
+__global__ void k_layout(uint8_t *obs, uint8_t *mask, size_t n_envs, int obs_bytes, int mask_bytes, int wait_read, uint32_t *state = nullptr, uint32_t *sink = nullptr, int state_mode = 1) {
     extern __shared__ __align__(128) uint8_t smem[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, wpb = blockDim.x >> 5;
     for (int i = threadIdx.x * 16; i < obs_bytes + mask_bytes + 32; i += blockDim.x * 16) *reinterpret_cast<uint4 *>(smem + i) = make_uint4(0, 0, 0, 0);
@@ -59,8 +62,7 @@ __global__ void k_layout(uint8_t *obs, uint8_t *mask, size_t n_envs, int obs_byt
     __syncthreads();
     const uint32_t s_obs = (uint32_t)__cvta_generic_to_shared(smem), s_mask = s_obs + ((obs_bytes + 15) & ~15);
     uint32_t acc = 0;
-    for (size_t e = blockIdx.x * (size_t)wpb + warp; e < n_envs; e += (size_t)gridDim.x * wpb) {
-        if (state) acc += state[e * 40 + lane] + state[n_envs * 40 + e * 4 + (lane & 3)];  // ~176 B of per-game state reads
+    auto emit = [&](size_t e) {
         uint8_t *go = obs + e * obs_bytes, *gm = mask + e * mask_bytes;
         const int head = int((16 - (reinterpret_cast<uintptr_t>(gm) & 15)) & 15), body = (mask_bytes - head) & ~15, tail = mask_bytes - head - body;
         if (lane < (head >> 2)) reinterpret_cast<uint32_t *>(gm)[lane] = 0;
@@ -73,6 +75,37 @@ __global__ void k_layout(uint8_t *obs, uint8_t *mask, size_t n_envs, int obs_byt
             else asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
         }
         __syncwarp();
+    };
+    if (state && state_mode >= 4) {
+        const size_t n_chunks = n_envs / 32;
+        for (size_t c = blockIdx.x * (size_t)wpb + warp; c < n_chunks; c += (size_t)gridDim.x * wpb) {
+            uint32_t v[40];
+            if (state_mode != 6) {
+#pragma unroll
+                for (int j = 0; j < 40; ++j) v[j] = state[c * 1280 + j * 32 + lane];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) acc += state[n_envs * 40 + c * 128 + j * 32 + lane];
+#pragma unroll
+                for (int j = 0; j < 40; ++j) acc += v[j];
+            }
+            for (int i = 0; i < 32; ++i) emit(c * 32 + i);
+            if (state_mode == 5) {
+#pragma unroll
+                for (int j = 0; j < 40; ++j) state[c * 1280 + j * 32 + lane] = v[j] + 1;
+#pragma unroll
+                for (int j = 0; j < 4; ++j) state[n_envs * 40 + c * 128 + j * 32 + lane] = acc;
+            }
+        }
+    } else {
+        for (size_t e = blockIdx.x * (size_t)wpb + warp; e < n_envs; e += (size_t)gridDim.x * wpb) {
+            if (state) {
+                const size_t se = state_mode == 3 ? (e & 4095) : e;
+                const uint32_t a = state[se * 40 + lane], b = state[n_envs * 40 + se * 4 + (lane & 3)];  // ~176 B of per-game state reads
+                acc += a + b;
+                if (state_mode == 2) { state[se * 40 + lane] = a + 1; if (lane < 4) state[n_envs * 40 + se * 4 + lane] = b + 1; }
+            }
+            emit(e);
+        }
     }
     if (sink && acc == 0x12345678u) sink[0] = acc;
 }
@@ -117,12 +150,16 @@ int main() {
         const size_t n_envs = 262144;
         uint8_t *mask = b;
         cudaFuncSetAttribute(k_layout, cudaFuncAttributeMaxDynamicSharedMemorySize, 40000);
-        for (int wpb : {4, 8, 12, 16}) for (int wr : {1, 0}) {
+        for (int wpb : {8, 10, 12, 16}) for (int wr : {1, 0}) {
             char nm[96]; snprintf(nm, 96, "engine layout obs26800+mask3700 W=%d wait=%s", wpb, wr ? "read" : "full");
             RUN(nm, (double)n_envs * (ob + mb), (k_layout<<<148, wpb * 32, 32768>>>(a, mask, n_envs, ob, mb, wr)));
             if (!wr) {
-                snprintf(nm, 96, "  + 176 B/game state reads        W=%d", wpb);
-                RUN(nm, (double)n_envs * (ob + mb), (k_layout<<<148, wpb * 32, 32768>>>(a, mask, n_envs, ob, mb, wr, (const uint32_t *)(b + (4ull << 30)), (uint32_t *)(b + (6ull << 30)))));
+                const char *names[7] = {"", "+ per-game state reads", "+ per-game state reads + write-back", "+ state reads from an L2-resident buffer",
+                                        "contiguous 32-game chunks, coalesced state read", "contiguous chunks, coalesced read + write-back", "contiguous chunks, no state"};
+                for (int sm : {1, 2, 3, 4, 5, 6}) {
+                    snprintf(nm, 96, "  %-52s W=%d", names[sm], wpb);
+                    RUN(nm, (double)n_envs * (ob + mb), (k_layout<<<148, wpb * 32, 32768>>>(a, mask, n_envs, ob, mb, wr, (uint32_t *)(b + (4ull << 30)), (uint32_t *)(b + (6ull << 30)), sm)));
+                }
             }
         }
     }
