@@ -351,7 +351,8 @@ def run_gpu_arm(args):
                        "dephase_steps": args.dephase if args.dephase is not None else w["dephase"]},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": recorded_traffic(args.workload, B), "peak_source": peak_src,
-                         "kernel": "sx_fused_kernel", "algorithmic_bytes_per_env_step": bytes_step,
+                         "kernel": "sx_toy_kernel" if info.get("thread_per_game") else "sx_fused_kernel",
+                         "algorithmic_bytes_per_env_step": bytes_step,
                          "kernel_ms": kernel_ms, "launch": info},
             "e2e": e2e,
             "e2e_device_obs": e2e_device_obs,

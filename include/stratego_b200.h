@@ -193,6 +193,7 @@ int sx_heuristic_rewards(const sx_config *cfg, sx_state st, int64_t num_envs, co
 typedef struct {
     int32_t warps_per_block, blocks_per_sm, smem_bytes_per_block, num_sms, grid_blocks, regs_per_thread;
     int32_t background_bytes; /* shared-memory background images of a block (DESIGN.md "Rendering") */
+    int32_t thread_per_game;  /* 1: the variant steps through sx_toy_kernel (one thread per game, boards of <= 16 cells) */
 } sx_launch_info;
 int sx_step_all_launch_info(const sx_config *cfg, uint32_t obs_mask /*1 po, 2 fo, 4 mask*/, sx_launch_info *out);
 

@@ -20,6 +20,7 @@
 
 #include "../../include/stratego_b200.h"
 #include "sx_device.cuh"
+#include "sx_toy.cuh"
 
 namespace sx {
 
@@ -360,6 +361,224 @@ __global__ void __launch_bounds__(K <= 2 ? 1024 : SX_MAX_THREADS, 1) sx_fused_ke
 
     if (args.stats) {
         if (lane == 0) {  // all lanes carry identical counters; lane 0 publishes
+            if (n_games) atomicAdd(reinterpret_cast<unsigned long long *>(args.stats + 0), (unsigned long long)n_games);
+            if (n_p1) atomicAdd(reinterpret_cast<unsigned long long *>(args.stats + 1), (unsigned long long)n_p1);
+            if (n_p2) atomicAdd(reinterpret_cast<unsigned long long *>(args.stats + 2), (unsigned long long)n_p2);
+            if (n_invalid) atomicAdd(reinterpret_cast<unsigned long long *>(args.stats + 3), (unsigned long long)n_invalid);
+            if (n_illegal) atomicAdd(reinterpret_cast<unsigned long long *>(args.stats + 4), (unsigned long long)n_illegal);
+        }
+    }
+}
+
+
+// ---- toy boards: one thread per game (sx_toy.cuh has the design) ------------------------------------------------------
+// shared memory: [block background images][per warp: stage 32 x 48 B | mask image of 32 rows | two observation tiles]
+// Measured (profiles/r1l_*): throughput follows the number of resident warps (8: 0.87 G, 12: 1.23 G, 16: 1.43 G
+// env-steps/s on Micro), not the number of tiles per warp (2, 4, 8, 16 tiles: same), so the launch keeps two tiles and
+// as many warps as shared memory holds.
+template <int MODE>
+__global__ void __launch_bounds__(512, 1) sx_toy_kernel(const __grid_constant__ KernelArgs args)
+{
+    using GT = Grp<1>;
+    extern __shared__ __align__(16) uint8_t smem[];
+    const DevConfig &cfg = args.cfg;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, wpb = blockDim.x >> 5;
+    constexpr uint32_t ops = mode_ops(MODE);
+    constexpr bool do_mask = (ops & OP_MASK) != 0, do_po = (ops & OP_PO) != 0, do_fo = (ops & OP_FO) != 0;
+    constexpr bool do_tile = do_mask || do_po || do_fo;
+    const uint32_t flags = args.flags;
+    const bool do_sample = (flags & SX_SAMPLE_NEXT) && args.out.next_action != nullptr;
+    const bool allow_osc = flags & SX_ALLOW_OSCILLATION;
+    const ObsMap pom = po_map(), fom = fo_map();
+    const uint64_t pol = l2_policy(0);
+
+    Tile bg;
+    carve_tile(cfg, ops, smem, &bg);
+    if (do_tile) {
+        if (do_po) fill_background(cfg, bg.po, pom, threadIdx.x, blockDim.x);
+        if (do_fo) fill_background(cfg, bg.fo, fom, threadIdx.x, blockDim.x);
+    }
+    __syncthreads();
+
+    uint8_t *const stage = smem + args.tile_bytes + size_t(warp) * args.warp_bytes;
+    uint8_t *const mask_img = stage + toy::GAMES * toy::STAGE_BYTES;
+    const int mask_total = toy::GAMES * cfg.mask_bytes;
+    const int mask_img_bytes = do_mask ? round16(mask_total + 16) : 0;
+    uint8_t *const tiles = mask_img + mask_img_bytes;
+    const int po_bytes = do_po ? cfg.po_floats * 4 : 0, fo_bytes = do_fo ? cfg.fo_floats * 4 : 0;
+    const int tile_stride = po_bytes + fo_bytes;
+    // the warp's two observation tiles hold the background image for the whole launch
+    constexpr int T = 2;  // tiles per warp (4 or 8 tiles with fewer warps were slower, profiles/r1l_toy_sweeps.txt)
+    uint32_t undo_po[T], undo_fo[T];
+#pragma unroll
+    for (int h = 0; h < T; ++h) undo_po[h] = undo_fo[h] = toy::UNDO_NONE;
+    for (int h = 0; h < T; ++h) {
+        if (do_po)
+            for (int i = lane; i < (po_bytes >> 4); i += 32)
+                reinterpret_cast<uint4 *>(tiles + h * tile_stride)[i] = reinterpret_cast<const uint4 *>(bg.po)[i];
+        if (do_fo)
+            for (int i = lane; i < (fo_bytes >> 4); i += 32)
+                reinterpret_cast<uint4 *>(tiles + h * tile_stride + po_bytes)[i] = reinterpret_cast<const uint4 *>(bg.fo)[i];
+    }
+    __syncwarp();
+
+    const toy::Geometry geo = toy::make_geometry(cfg);
+    long long n_games = 0, n_p1 = 0, n_p2 = 0, n_invalid = 0, n_illegal = 0;
+    const long long n_groups = args.num_envs / toy::GAMES;
+    for (long long group = (long long)blockIdx.x * wpb + warp; group < n_groups; group += (long long)gridDim.x * wpb) {
+        const long long env0 = group * toy::GAMES, env = env0 + lane;
+        const uint64_t gid = uint64_t(args.env_base + env);
+        if (do_tile) {
+            if (lane == 0) bulk_wait_read();  // the previous group's copies have left shared memory
+            __syncwarp();
+            if (do_mask)
+                for (int i = lane; i < (mask_img_bytes >> 4); i += 32) reinterpret_cast<uint4 *>(mask_img)[i] = make_uint4(0, 0, 0, 0);
+        }
+        // ---- this thread's game: 48 bytes of state in registers ------------------------------------------------
+        toy::State s;
+        {
+            const uint4 bw = *reinterpret_cast<const uint4 *>(args.board + env * 16);
+            const uint4 cw = *reinterpret_cast<const uint4 *>(args.cap + env * 8);
+            s.b[0] = bw.x; s.b[1] = bw.y; s.b[2] = bw.z; s.b[3] = bw.w;
+            s.c[0] = cw.x; s.c[1] = cw.y; s.c[2] = cw.z; s.c[3] = cw.w;
+        }
+        Aux a;
+        {
+            const uint4 aw = *reinterpret_cast<const uint4 *>(args.aux + env * 8);
+            const uint32_t w[4] = {aw.x, aw.y, aw.z, aw.w};
+            aux_unpack(w, a);
+        }
+        const int action = args.actions[env];
+        uint32_t mv[16];
+
+        // ---- step: decode, validate, apply (impl:897-1028) ----------------------------------------------------
+        const int mover = a.to_move;
+        Move move = args.action_format == SX_ACTION_SPATIAL ? decode_spatial(cfg, action, mover) : decode_1d(cfg, action);
+        StepStatus status = STEP_ILLEGAL;
+        bool done = false;
+        int viewer = 0, total = 0;
+        // Move generation is ONE inlined copy run up to three times: pass 0 only for a noop action (legal only when
+        // nothing else is, impl:809-814), pass 1 for the next player (stuck check, impl:1031-1036), pass 2 for the fresh
+        // game of an auto-reset.
+#pragma unroll 1
+        for (int pass = (move.noop && !move.bad && !a.over) ? 0 : 1; pass < 3; ++pass) {
+            if (pass == 1) {
+                status = toy::apply_move(cfg, s, a, move, allow_osc);
+                viewer = a.to_move;
+            }
+            const int who = pass == 0 ? mover : viewer;
+            total = toy::gen_moves(cfg, geo, s, a, who, false, mv);
+            if (pass == 0) {
+                if (total > 0) move.bad = true;
+                continue;
+            }
+            if (pass == 2) break;
+            if (status == STEP_MOVED) {
+                if (total == 0 && !a.over) { a.over = 1; a.winner = mover == 0 ? 1 : -1; }
+                if (a.turn >= a.max_turns && !a.over) {  // impl:1040-1043; terminal masks are noop-only
+                    a.over = 1;
+                    a.invalid = 1;
+                    total = 0;
+#pragma unroll
+                    for (int p = 0; p < 16; ++p) mv[p] = 0;
+                }
+            }
+            done = status != STEP_ILLEGAL && a.over;
+            const int w = a.winner;
+            if (args.out.done) args.out.done[env] = done ? 1 : 0;
+            if (args.out.winner) args.out.winner[env] = int8_t(done ? w : 0);
+            if (args.out.ending_invalid) args.out.ending_invalid[env] = (done && a.invalid) ? 1 : 0;
+            if (args.out.illegal) args.out.illegal[env] = status == STEP_ILLEGAL ? 1 : 0;
+            if (args.out.reward) args.out.reward[env] = (done && !a.invalid) ? float(w) : 0.0f;  // maenv:777-801
+            if (status == STEP_ILLEGAL) n_illegal += 1;
+            if (done && status != STEP_UNCHANGED) {
+                n_games += 1;
+                n_p1 += w == 1;
+                n_p2 += w == -1;
+                n_invalid += a.invalid;
+            }
+            if (!(done && (flags & SX_AUTO_RESET))) break;
+            toy::reset_game(cfg, s, a, args.setups, args.n_setups, (flags & SX_RESET_RANDOM_SHUFFLE) != 0, args.key, gid);
+            viewer = a.to_move;
+        }
+        if (args.out.player) args.out.player[env] = viewer == 0 ? 1 : -1;
+
+        // ---- state write-back, uniform valid-action sample -----------------------------------------------------
+        *reinterpret_cast<uint4 *>(args.board + env * 16) = make_uint4(s.b[0], s.b[1], s.b[2], s.b[3]);
+        *reinterpret_cast<uint4 *>(args.cap + env * 8) = make_uint4(s.c[0], s.c[1], s.c[2], s.c[3]);
+        {
+            uint32_t w[4];
+            aux_pack(a, w);
+            *reinterpret_cast<uint4 *>(args.aux + env * 8) = make_uint4(w[0], w[1], w[2], w[3]);
+        }
+        if (do_sample) {
+            const uint4 rnd = philox4x32_10(make_uint4(uint32_t(gid), uint32_t(gid >> 32), RNG_SAMPLE ^ uint32_t(a.turn), a.episode), args.key);
+            args.out.next_action[env] = toy::pick_move(cfg, mv, total, rnd.x);
+        }
+        if (!do_tile) continue;
+
+        // ---- render the warp's 32 games ------------------------------------------------------------------------
+        uint8_t *gmask = do_mask ? args.out.valid_mask + env0 * cfg.mask_bytes : nullptr;
+        uint8_t *mask_rows = mask_img + (reinterpret_cast<uintptr_t>(gmask) & 15);  // source congruent to the destination mod 16
+        __syncwarp();  // the mask image is zero
+        if (do_mask) {
+            uint8_t *row = mask_rows + lane * cfg.mask_bytes;
+#pragma unroll
+            for (int p = 0; p < 16; ++p)
+                for (uint32_t w = mv[p]; w != 0; w &= w - 1) row[p * cfg.A + __ffs(w) - 1] = 1;
+            if (total == 0) row[cfg.A - 1] = 1;  // [0,0,A-1], impl:514-515
+        }
+        {
+            uint8_t *st = stage + lane * toy::STAGE_BYTES;
+            *reinterpret_cast<uint4 *>(st) = make_uint4(s.b[0], s.b[1], s.b[2], s.b[3]);
+            *reinterpret_cast<uint4 *>(st + 16) = make_uint4(s.c[0], s.c[1], s.c[2], s.c[3]);
+            *reinterpret_cast<uint32_t *>(st + 32) = uint32_t(a.rfrom[0]) | (uint32_t(a.rto[0]) << 8) | (uint32_t(a.rfrom[1]) << 16) |
+                                                      (uint32_t(a.rto[1]) << 24);
+            *reinterpret_cast<uint32_t *>(st + 36) = uint32_t(a.rcode[0]) | (uint32_t(a.rcode[1]) << 4) | (uint32_t(a.ncap) << 8) |
+                                                      (uint32_t(viewer) << 16);
+        }
+        fence_async_smem();
+        __syncwarp();
+        if (do_mask) {  // the 32 mask rows are contiguous in the output tensor: one bulk copy (+ unaligned head / tail words)
+            emit_tile<GT>(gmask, mask_rows, mask_total, pol);
+            if (lane == 0) bulk_commit();
+        }
+        if (do_po || do_fo) {
+#pragma unroll 1
+            for (int g = 0; g < toy::GAMES; g += T) {
+#pragma unroll
+                for (int h = 0; h < T; ++h) {  // T tiles: one is patched while the others' copies are read
+                    uint8_t *tile = tiles + h * tile_stride;
+                    if (lane == 0) asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(T - 1) : "memory");  // the copy T games ago left this tile
+                    __syncwarp();
+                    if (do_po) toy::restore_tile(cfg, reinterpret_cast<float *>(tile), pom, lane, undo_po[h]);
+                    if (do_fo) toy::restore_tile(cfg, reinterpret_cast<float *>(tile + po_bytes), fom, lane, undo_fo[h]);
+                    __syncwarp();  // an entry being undone and a new entry of another lane may share an address
+                    const uint8_t *st = stage + (g + h) * toy::STAGE_BYTES;
+                    if (do_po) undo_po[h] = toy::patch_tile(cfg, st, reinterpret_cast<float *>(tile), pom, lane);
+                    if (do_fo) undo_fo[h] = toy::patch_tile(cfg, st, reinterpret_cast<float *>(tile + po_bytes), fom, lane);
+                    fence_async_smem();
+                    __syncwarp();
+                    if (lane == 0) {
+                        if (do_po) bulk_store(args.out.partial_obs + (env0 + g + h) * cfg.po_floats, tile, uint32_t(po_bytes), pol);
+                        if (do_fo) bulk_store(args.out.full_obs + (env0 + g + h) * cfg.fo_floats, tile + po_bytes, uint32_t(fo_bytes), pol);
+                        bulk_commit();
+                    }
+                }
+            }
+        }
+    }
+    if (do_tile && lane == 0) bulk_wait_read();  // shared memory must outlive the copies
+
+    if (args.stats) {
+        for (int off = 16; off > 0; off >>= 1) {
+            n_games += __shfl_xor_sync(FULL, n_games, off);
+            n_p1 += __shfl_xor_sync(FULL, n_p1, off);
+            n_p2 += __shfl_xor_sync(FULL, n_p2, off);
+            n_invalid += __shfl_xor_sync(FULL, n_invalid, off);
+            n_illegal += __shfl_xor_sync(FULL, n_illegal, off);
+        }
+        if (lane == 0) {
             if (n_games) atomicAdd(reinterpret_cast<unsigned long long *>(args.stats + 0), (unsigned long long)n_games);
             if (n_p1) atomicAdd(reinterpret_cast<unsigned long long *>(args.stats + 1), (unsigned long long)n_p1);
             if (n_p2) atomicAdd(reinterpret_cast<unsigned long long *>(args.stats + 2), (unsigned long long)n_p2);
@@ -790,11 +1009,109 @@ static int plan_launch_uncached(const sx_config *cfg, uint32_t ops, int mode, lo
     return 0;
 }
 
+
+// ---- toy-board launch (sx_toy_kernel) ------------------------------------------------------------------------------------
+// Eligible: at most 16 cells with 16-byte aligned observation rows, a board / capture list of 16 bytes each, at most 8
+// setup cells and pieces, extended channels, and one of the three step modes without per-launch overrides.
+static bool toy_eligible(const sx_config *cfg, const KernelArgs &a, int mode)
+{
+    const DevConfig &d = cfg->dev;
+    if (env_int("SX_TOY", 1) == 0) return false;
+    if (mode != MODE_STEP_PO_MASK && mode != MODE_STEP_PO_FO_MASK && mode != MODE_STEP_LEAN) return false;
+    if (d.N > 16 || (d.N & 3) != 0 || d.A > 16 || d.board_stride != 16 || d.cap_stride != 8) return false;
+    if (d.setup_len > 8 || d.n_pieces > 8 || d.original_channels) return false;
+    if (a.player_override || a.reset_mask || a.setup_idx || a.mask1d) return false;
+    return a.num_envs >= toy::GAMES;
+}
+
+typedef void (*toy_fn)(const KernelArgs);
+static toy_fn toy_for_mode(int mode)
+{
+    return mode == MODE_STEP_PO_MASK ? sx_toy_kernel<MODE_STEP_PO_MASK>
+         : mode == MODE_STEP_PO_FO_MASK ? sx_toy_kernel<MODE_STEP_PO_FO_MASK> : sx_toy_kernel<MODE_STEP_LEAN>;
+}
+
+static int toy_warp_bytes(const DevConfig &d, uint32_t ops)
+{
+    const int mask_img = (ops & OP_MASK) ? round16(toy::GAMES * d.mask_bytes + 16) : 0;
+    const int tile = ((ops & OP_PO) ? d.po_floats * 4 : 0) + ((ops & OP_FO) ? d.fo_floats * 4 : 0);
+    return toy::GAMES * toy::STAGE_BYTES + mask_img + 2 * tile;
+}
+
+struct ToyPlan {
+    int warps, smem, grid_max, tile_bytes, warp_bytes, num_sms;
+};
+static int plan_toy(const sx_config *cfg, uint32_t ops, ToyPlan *plan)
+{
+    int device = 0, max_smem = 0;
+    cudaError_t e = cudaGetDevice(&device);
+    if (e != cudaSuccess) return cuda_fail("cudaGetDevice", e);
+    cudaDeviceGetAttribute(&plan->num_sms, cudaDevAttrMultiProcessorCount, device);
+    cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, device);
+    plan->tile_bytes = carve_tile(cfg->dev, ops, nullptr, nullptr);
+    plan->warp_bytes = toy_warp_bytes(cfg->dev, ops);
+    // as many warps as shared memory holds, up to 16: Micro 8 warps 1.10 G, 12 warps 1.42 G, 16 warps 1.41 G env-steps/s
+    plan->warps = std::max(1, std::min(16, env_int("SX_TOY_WARPS", 16)));
+    while (plan->warps > 1 && plan->tile_bytes + plan->warps * plan->warp_bytes > max_smem) --plan->warps;
+    plan->smem = plan->tile_bytes + plan->warps * plan->warp_bytes;
+    if (plan->smem > max_smem) return fail("toy kernel does not fit in shared memory");
+    plan->grid_max = plan->num_sms;
+    return 0;
+}
+
+static int launch_toy(const sx_config *cfg, KernelArgs &args, int mode, cudaStream_t stream)
+{
+    const uint32_t ops = mode_ops(mode);
+    ToyPlan plan;
+    if (int rc = plan_toy(cfg, ops, &plan)) return rc;
+    toy_fn fn = toy_for_mode(mode);
+    static std::mutex attr_mutex;
+    {
+        std::lock_guard<std::mutex> lock(attr_mutex);
+        cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, plan.smem);
+        if (e != cudaSuccess) return cuda_fail("cudaFuncSetAttribute", e);
+    }
+    args.cfg = cfg->dev;
+    args.ops = ops;
+    args.warp_bytes = plan.warp_bytes;
+    args.tile_bytes = plan.tile_bytes;
+    const long long groups = args.num_envs / toy::GAMES;
+    const int grid = int(std::max(1LL, std::min((long long)plan.grid_max, (groups + plan.warps - 1) / plan.warps)));
+    fn<<<grid, plan.warps * 32, plan.smem, stream>>>(args);
+    cudaError_t e = cudaGetLastError();
+    return e == cudaSuccess ? 0 : cuda_fail("sx toy kernel launch", e);
+}
+
 static int launch_fused(const sx_config *cfg, KernelArgs &args, cudaStream_t stream)
 {
     if (args.num_envs <= 0) return 0;
     LaunchPlan plan;
     const int mode = mode_for(cfg, args);
+    if (toy_eligible(cfg, args, mode)) {
+        // whole groups of 32 games go to the thread-per-game kernel, the last num_envs % 32 games to the warp-level one
+        const long long whole = args.num_envs / toy::GAMES * toy::GAMES, rest = args.num_envs - whole;
+        KernelArgs head = args;
+        head.num_envs = whole;
+        if (int rc = launch_toy(cfg, head, mode, stream)) return rc;
+        if (rest == 0) return 0;
+        args.board += whole * cfg->dev.board_stride;
+        args.aux += whole * 8;
+        args.cap += whole * cfg->dev.cap_stride;
+        args.actions += whole;
+        args.env_base += whole;
+        args.num_envs = rest;
+        sx_outputs &o = args.out;
+        if (o.partial_obs) o.partial_obs += whole * cfg->dev.po_floats;
+        if (o.full_obs) o.full_obs += whole * cfg->dev.fo_floats;
+        if (o.valid_mask) o.valid_mask += whole * cfg->dev.mask_bytes;
+        if (o.reward) o.reward += whole;
+        if (o.done) o.done += whole;
+        if (o.winner) o.winner += whole;
+        if (o.ending_invalid) o.ending_invalid += whole;
+        if (o.illegal) o.illegal += whole;
+        if (o.player) o.player += whole;
+        if (o.next_action) o.next_action += whole;
+    }
     if (int rc = plan_launch(cfg, args.ops, mode, args.num_envs, &plan)) return rc;
     args.cfg = cfg->dev;
     args.warp_bytes = plan.warp_bytes;
@@ -1006,6 +1323,20 @@ extern "C" int sx_step_all_launch_info(const sx_config *cfg, uint32_t obs_mask, 
     KernelArgs probe;
     std::memset(&probe, 0, sizeof(probe));
     probe.ops = ops;
+    probe.num_envs = 1LL << 40;
+    out->thread_per_game = 0;
+    if (toy_eligible(cfg, probe, mode_for(cfg, probe))) {  // the toy boards step through sx_toy_kernel
+        ToyPlan tp;
+        if (int rc = plan_toy(cfg, ops, &tp)) return rc;
+        cudaFuncAttributes attr;
+        cudaError_t e = cudaFuncGetAttributes(&attr, toy_for_mode(mode_for(cfg, probe)));
+        if (e != cudaSuccess) return cuda_fail("cudaFuncGetAttributes", e);
+        out->warps_per_block = tp.warps; out->blocks_per_sm = 1; out->smem_bytes_per_block = tp.smem;
+        out->num_sms = tp.num_sms; out->grid_blocks = tp.grid_max; out->regs_per_thread = attr.numRegs;
+        out->background_bytes = tp.tile_bytes;
+        out->thread_per_game = 1;
+        return 0;
+    }
     if (int rc = plan_launch(cfg, ops, mode_for(cfg, probe), 1LL << 40, &plan)) return rc;
     out->warps_per_block = plan.warps_per_block; out->blocks_per_sm = plan.blocks_per_sm;
     out->smem_bytes_per_block = plan.smem_per_block; out->num_sms = plan.num_sms; out->grid_blocks = plan.grid;

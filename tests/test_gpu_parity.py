@@ -253,3 +253,65 @@ def test_original_channels_raw_facade_getters():
                                       _bits(orc.get_partially_observable_observation(states[i], p)))
                 assert np.array_equal(_bits(env.get_fully_observable_observation(states[i], p)),
                                       _bits(orc.get_fully_observable_observation(states[i], p)))
+
+
+# ---- toy boards: the thread-per-game kernel (sx_toy_kernel) against the warp-level kernel -------------------------
+@pytest.mark.parametrize("version,full", [("micro", False), ("micro", True), ("tiny", False), ("tiny", True)])
+def test_toy_kernel_equals_warp_level_kernel(version, full, monkeypatch):
+    """Same seeds, same actions: the two implementations of the fused step must agree on every output and on the
+    state after every step -- rules, auto-reset (same Philox streams), sampling order, rendering.  167 games = five
+    whole groups of 32 for the toy kernel + 7 games that always take the warp-level kernel."""
+    from stratego_env_b200.config import VERSION_CONFIGS, as_version
+    from stratego_env_b200.engine import StrategoEngine
+    cfg = VERSION_CONFIGS[as_version(version)]
+    B, steps = 167, 70
+    runs = {}
+    for toy_on in ("1", "0"):
+        monkeypatch.setenv("SX_TOY", toy_on)
+        eng = StrategoEngine(cfg, device="cuda:0")
+        st = eng.alloc_state(B)
+        eng.reset(st, seed=5, env_base=1000, shuffle=True)
+        out = eng.alloc_outputs(B, partial=True, full=full, mask=True, sample=True)
+        eng.observe(st, out=out, partial=True, full=full, mask=True)
+        actions = eng.sample_valid(out["valid_mask"], seed=5, step=0, env_base=1000)
+        stats = torch.zeros(8, dtype=torch.int64, device="cuda:0")
+        trace = []
+        for s in range(steps):
+            eng.step_all(st, actions, out, env_base=1000, auto_reset=True, sample_next=True, shuffle=True, seed=5, stats=stats)
+            dense, player = eng.export_ref_state(st)
+            torch.cuda.synchronize()
+            trace.append({k: v.cpu().numpy().copy() for k, v in out.items()} | {"dense": dense.cpu().numpy(),
+                                                                               "to_move": player.cpu().numpy()})
+            actions = out["next_action"].clone()
+        runs[toy_on] = (trace, stats.cpu().numpy())
+    (toy, toy_stats), (ref, ref_stats) = runs["1"], runs["0"]
+    assert toy_stats[0] > B  # many games ended and were re-set on the device
+    assert np.array_equal(toy_stats, ref_stats)
+    for s in range(steps):
+        for key in ref[s]:
+            a, b = toy[s][key], ref[s][key]
+            if a.dtype == np.float32:
+                a, b = a.view(np.uint32), b.view(np.uint32)
+            assert np.array_equal(a, b), (version, full, s, key)
+
+
+@pytest.mark.parametrize("version", ["micro", "tiny"])
+def test_toy_kernel_recorded_transitions_1d_actions(version):
+    """the toy kernel on the reference's recorded transitions, absolute 1D actions, padded to whole groups of 32"""
+    t = traj(version)
+    eng, orc = _engine(version), _oracle(version)
+    idx = transitions(t)
+    idx = idx[:len(idx) // 32 * 32]
+    states = t["states"].astype(np.int64)
+    st = eng.import_ref_state(_t(states[idx], torch.int64), _t(t["players"][idx], torch.int8))
+    out = eng.alloc_outputs(len(idx), partial=True, full=True, mask=True)
+    eng.step_all(st, _t(t["actions_1d"][idx], torch.int32), out, one_d=True)
+    dense, player = eng.export_ref_state(st)
+    torch.cuda.synchronize()
+    assert np.array_equal(dense.cpu().numpy(), states[idx + 1])
+    assert np.array_equal(player.cpu().numpy(), t["players"][idx + 1])
+    mask, po, fo = (out[k].cpu().numpy() for k in ("valid_mask", "partial_obs", "full_obs"))
+    for row, i in enumerate(idx):
+        m_o, po_o, fo_o = orc.current_obs(states[i + 1], int(t["players"][i + 1]), 3)
+        assert np.array_equal(mask[row], m_o), (version, i)
+        assert np.array_equal(_bits(po[row]), _bits(po_o)) and np.array_equal(_bits(fo[row]), _bits(fo_o)), (version, i)
