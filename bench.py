@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """Benchmark of the hot path: env-steps/s of the fused step (mask + step + obs + auto-reset).
 
-    python bench.py --gpus N --steps K --warmup W [--workload barrage|micro|standard|standard_both]
+    python bench.py --gpus N --steps K --warmup W [--workload barrage|micro|tiny|standard|standard_both]
     python bench.py --impl reference ...      # the CPU restatement of the reference on the host cores
 
 One "step" = one pass of the fused kernel over every game of the batch: each game applies one
@@ -37,6 +37,8 @@ WORKLOADS = {
                          "setup table, PO obs f32[B,10,10,67] + spatial mask u8[B,10,10,37] every step"),
     "micro": dict(version="micro", table=None, envs=1048576, full=False, dephase=100,
                   desc="Micro 3x4, 1M envs/GPU, random-valid self-play, auto-reset with shuffled setups, PO obs + mask"),
+    "tiny": dict(version="tiny", table=None, envs=1048576, full=False, dephase=200,
+                 desc="Tiny 4x4, 1M envs/GPU, random-valid self-play, auto-reset with shuffled setups, PO obs + mask"),
     "standard": dict(version="standard", table="standard", envs=524288, full=False, dephase=3000,
                      desc="Standard 10x10 (40 pieces/side), 512k envs/GPU, human setup table, PO obs + mask"),
     "standard_both": dict(version="standard", table="standard", envs=262144, full=True, dephase=3000,

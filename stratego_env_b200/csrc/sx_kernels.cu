@@ -425,7 +425,18 @@ __global__ void __launch_bounds__(512, 1) sx_toy_kernel(const __grid_constant__ 
     const toy::Geometry geo = toy::make_geometry(cfg);
     long long n_games = 0, n_p1 = 0, n_p2 = 0, n_invalid = 0, n_illegal = 0;
     const long long n_groups = args.num_envs / toy::GAMES;
-    for (long long group = (long long)blockIdx.x * wpb + warp; group < n_groups; group += (long long)gridDim.x * wpb) {
+    // the next group's state loads are issued before this group is rendered, so they never stall the rules
+    uint4 pf_b = make_uint4(0, 0, 0, 0), pf_c = pf_b, pf_a = pf_b;
+    int pf_action = 0;
+    auto load_state = [&](long long e) {
+        pf_b = *reinterpret_cast<const uint4 *>(args.board + e * 16);
+        pf_c = *reinterpret_cast<const uint4 *>(args.cap + e * 8);
+        pf_a = *reinterpret_cast<const uint4 *>(args.aux + e * 8);
+        pf_action = args.actions[e];
+    };
+    const long long group_stride = (long long)gridDim.x * wpb;
+    if ((long long)blockIdx.x * wpb + warp < n_groups) load_state(((long long)blockIdx.x * wpb + warp) * toy::GAMES + lane);
+    for (long long group = (long long)blockIdx.x * wpb + warp; group < n_groups; group += group_stride) {
         const long long env0 = group * toy::GAMES, env = env0 + lane;
         const uint64_t gid = uint64_t(args.env_base + env);
         if (do_tile) {
@@ -434,21 +445,16 @@ __global__ void __launch_bounds__(512, 1) sx_toy_kernel(const __grid_constant__ 
             if (do_mask)
                 for (int i = lane; i < (mask_img_bytes >> 4); i += 32) reinterpret_cast<uint4 *>(mask_img)[i] = make_uint4(0, 0, 0, 0);
         }
-        // ---- this thread's game: 48 bytes of state in registers ------------------------------------------------
+        // ---- this thread's game: 48 bytes of state in registers (requested one group ahead) --------------------------
         toy::State s;
-        {
-            const uint4 bw = *reinterpret_cast<const uint4 *>(args.board + env * 16);
-            const uint4 cw = *reinterpret_cast<const uint4 *>(args.cap + env * 8);
-            s.b[0] = bw.x; s.b[1] = bw.y; s.b[2] = bw.z; s.b[3] = bw.w;
-            s.c[0] = cw.x; s.c[1] = cw.y; s.c[2] = cw.z; s.c[3] = cw.w;
-        }
+        s.b[0] = pf_b.x; s.b[1] = pf_b.y; s.b[2] = pf_b.z; s.b[3] = pf_b.w;
+        s.c[0] = pf_c.x; s.c[1] = pf_c.y; s.c[2] = pf_c.z; s.c[3] = pf_c.w;
         Aux a;
         {
-            const uint4 aw = *reinterpret_cast<const uint4 *>(args.aux + env * 8);
-            const uint32_t w[4] = {aw.x, aw.y, aw.z, aw.w};
+            const uint32_t w[4] = {pf_a.x, pf_a.y, pf_a.z, pf_a.w};
             aux_unpack(w, a);
         }
-        const int action = args.actions[env];
+        const int action = pf_action;
         uint32_t mv[16];
 
         // ---- step: decode, validate, apply (impl:897-1028) ----------------------------------------------------
@@ -515,6 +521,7 @@ __global__ void __launch_bounds__(512, 1) sx_toy_kernel(const __grid_constant__ 
             const uint4 rnd = philox4x32_10(make_uint4(uint32_t(gid), uint32_t(gid >> 32), RNG_SAMPLE ^ uint32_t(a.turn), a.episode), args.key);
             args.out.next_action[env] = toy::pick_move(cfg, mv, total, rnd.x);
         }
+        if (group + group_stride < n_groups) load_state((group + group_stride) * toy::GAMES + lane);
         if (!do_tile) continue;
 
         // ---- render the warp's 32 games ------------------------------------------------------------------------
@@ -1050,8 +1057,9 @@ static int plan_toy(const sx_config *cfg, uint32_t ops, ToyPlan *plan)
     cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, device);
     plan->tile_bytes = carve_tile(cfg->dev, ops, nullptr, nullptr);
     plan->warp_bytes = toy_warp_bytes(cfg->dev, ops);
-    // as many warps as shared memory holds, up to 16: Micro 8 warps 1.10 G, 12 warps 1.42 G, 16 warps 1.41 G env-steps/s
-    plan->warps = std::max(1, std::min(16, env_int("SX_TOY_WARPS", 16)));
+    // 12 warps per SM (or as many as shared memory holds): Micro 8 warps 1.10 G, 10: 1.35 G, 11: 1.42 G, 12: 1.49 G,
+    // 13-16: 1.40-1.43 G env-steps/s; Tiny 8: 1.02 G, 10-13: 1.08 G
+    plan->warps = std::max(1, std::min(16, env_int("SX_TOY_WARPS", 12)));
     while (plan->warps > 1 && plan->tile_bytes + plan->warps * plan->warp_bytes > max_smem) --plan->warps;
     plan->smem = plan->tile_bytes + plan->warps * plan->warp_bytes;
     if (plan->smem > max_smem) return fail("toy kernel does not fit in shared memory");
