@@ -54,7 +54,7 @@ class BatchedStrategoEnv:
         self.num_envs, self.seed, self.env_base = int(num_envs), int(seed), int(env_base)
         self.auto_reset, self.sample_actions, self.raise_on_illegal = auto_reset, sample_actions, raise_on_illegal
         self.engine = StrategoEngine({k: cfg[k] for k in version_config}, device=device,
-                                     p2_rot180=not self.human_inits)
+                                     p2_rot180=not self.human_inits, obs_channel_mode=cfg['obs_channel_mode'])
         self.device = self.engine.device
         self.rows, self.columns = self.engine.rows, self.engine.columns
         self.spatial_action_size = self.engine.spatial_action_size
@@ -134,6 +134,13 @@ class BatchedStrategoEnv:
         return self.engine.sample_logits(logits, self.out["valid_mask"], seed=self.seed, step=self._policy_step,
                                          env_base=self.env_base, temperature=temperature,
                                          return_logprob=return_logprob)
+
+    def heuristic_rewards(self, actions: torch.Tensor, reward_matrix: torch.Tensor) -> torch.Tensor:
+        """impl:854-891 for the whole batch: reward_matrix[mover's rank, captured rank] (float32 [13, 13]) of the action
+        each game is about to play -- call it before ``step(actions)``"""
+        if actions.dtype != torch.int32:
+            actions = actions.to(torch.int32)
+        return self.engine.heuristic_rewards(self.state, actions.contiguous(), reward_matrix)
 
     def observe(self, player: Optional[torch.Tensor] = None, partial=True, full=True, mask=True) -> dict:
         """mask + observations for an arbitrary viewer per game (+1 / -1; default: the player to move)"""

@@ -347,6 +347,38 @@ def test_batched_env_selfplay_vs_oracle(version, human):
     assert stats["illegal_actions"] == 0 and stats["games_finished"] >= finished
 
 
+def test_batched_env_original_channels_and_heuristic_rewards():
+    """obs_channel_mode='original' and the heuristic-reward kernel through BatchedStrategoEnv, vs the oracle"""
+    from oracle.binding import OracleEnvLogic
+    from stratego_env_b200 import BatchedStrategoEnv, GameVersions, ObservationComponents as OC, ObservationModes
+    from stratego_env_b200.config import VERSION_CONFIGS, as_version
+    cfg = VERSION_CONFIGS[as_version("barrage")]
+    B = 96
+    env = BatchedStrategoEnv({"version": GameVersions.BARRAGE, "human_inits": True, "obs_channel_mode": "original",
+                              "observation_mode": ObservationModes.BOTH_OBSERVATIONS}, num_envs=B, seed=3,
+                             sample_actions=True)
+    orc = OracleEnvLogic(cfg["rows"], cfg["columns"], cfg["piece_amounts"], obs_channel_mode="original")
+    matrix = torch.arange(169, dtype=torch.float32).reshape(13, 13)
+    obs = env.reset()
+    for s in range(25):
+        dense0, player0 = (x.cpu().numpy() for x in env.export_states())
+        actions = obs["sampled_action"].clone()
+        heur = env.heuristic_rewards(actions, matrix).cpu().numpy()
+        obs, _, dones, _ = env.step(actions)
+        dense1, player1 = (x.cpu().numpy() for x in env.export_states())
+        po, fo = obs[OC.PARTIAL_OBSERVATION.value].cpu().numpy(), obs[OC.FULL_OBSERVATION.value].cpu().numpy()
+        assert po.shape == (B, 10, 10, 32) and fo.shape == (B, 10, 10, 33)
+        acts = actions.cpu().numpy()
+        for b in range(0, B, 5):
+            _, po_o, fo_o = orc.current_obs(dense1[b], int(player1[b]), 3)
+            assert np.array_equal(_bits(po[b]), _bits(po_o)) and np.array_equal(_bits(fo[b]), _bits(fo_o)), (s, b)
+            sp = np.unravel_index(int(acts[b]), env.spatial_action_size)
+            a1d = orc.base_env.get_action_1d_index_from_spatial_index(sp)
+            a1d = orc.base_env.get_action_1d_index_from_player_perspective(a1d, int(player0[b]))
+            expect = orc.base_env.get_heuristic_rewards_from_move(dense0[b], int(player0[b]), a1d, matrix.numpy())
+            assert heur[b] == expect, (s, b)
+
+
 def test_batched_env_is_placement_independent():
     """a game's trajectory depends on (seed, global env id) only: one batch of 96 == shards of 32 + 64"""
     from stratego_env_b200 import BatchedStrategoEnv, GameVersions, ObservationModes
