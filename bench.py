@@ -252,7 +252,20 @@ def run_gpu_arm(args):
     device = torch.device("cuda", local_rank)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        dist.init_process_group("nccl", device_id=device)
+        # NCCL prints its version banner on stdout when the first communicator is created: keep stdout for the ONE
+        # JSON line by pointing fd 1 at stderr while the process group comes up
+        sys.stdout.flush()
+        saved_stdout = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            dist.init_process_group("nccl", device_id=device)
+            warm = torch.zeros(1, device=device)
+            dist.all_reduce(warm)
+            torch.cuda.synchronize()
+        finally:
+            sys.stdout.flush()
+            os.dup2(saved_stdout, 1)
+            os.close(saved_stdout)
 
     w = WORKLOADS[args.workload]
     B = args.envs or w["envs"]
