@@ -186,7 +186,7 @@ def run_reference_arm(args):
         return 0
     w = WORKLOADS[args.workload]
     # every "step" is one bounded sample; the whole run stays within a few minutes whatever --steps is
-    per_step_budget = max(0.5, min(20.0, 100.0 / max(1, args.steps + args.warmup)))
+    per_step_budget = max(0.2, min(args.ref_seconds, 100.0 / max(1, args.steps + args.warmup)))
     runner = CpuSelfplay(args.workload)
     for _ in range(args.warmup):
         runner.run(per_step_budget)
@@ -417,6 +417,7 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=8)
     ap.add_argument("--e2e-envs", type=int, default=None)
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
+    ap.add_argument("--ref-seconds", type=float, default=20.0, help="--impl reference: upper bound of one step's sample")
     ap.add_argument("--also", default="micro,standard",
                     help="other workloads summarised in the same line at N=1 (comma list, '' = none)")
     ap.add_argument("--no-e2e", action="store_true")
