@@ -315,3 +315,66 @@ def test_toy_kernel_recorded_transitions_1d_actions(version):
         m_o, po_o, fo_o = orc.current_obs(states[i + 1], int(t["players"][i + 1]), 3)
         assert np.array_equal(mask[row], m_o), (version, i)
         assert np.array_equal(_bits(po[row]), _bits(po_o)) and np.array_equal(_bits(fo[row]), _bits(fo_o)), (version, i)
+
+
+CUSTOM_TOYS = {
+    # stock toy variants have neither scouts nor lakes: these exercise the toy kernel's ray loop, lake handling,
+    # bombs / miners / spies and the 8-cell setup shuffle
+    "scouts_lakes_4x4": dict(rows=4, columns=4, max_turns=40, obstacle_locations=[(1, 1), (2, 2)],
+                             piece_amounts={2: 2, 3: 1, 11: 1}, initial_state_usable_rows=1),
+    "spy_scout_3x4": dict(rows=3, columns=4, max_turns=30, obstacle_locations=[],
+                          piece_amounts={1: 1, 2: 1, 10: 1, 11: 1}, initial_state_usable_rows=1),
+    "eight_pieces_4x4": dict(rows=4, columns=4, max_turns=60, obstacle_locations=[],
+                             piece_amounts={2: 3, 3: 1, 9: 1, 11: 1, 12: 2}, initial_state_usable_rows=2),
+}
+
+
+@pytest.mark.parametrize("name", sorted(CUSTOM_TOYS))
+def test_toy_kernel_custom_variants_vs_warp_level_kernel_and_oracle(name, monkeypatch):
+    from oracle.binding import OracleEnvLogic
+    from stratego_env_b200.engine import StrategoEngine
+    cfg = CUSTOM_TOYS[name]
+    orc = OracleEnvLogic(cfg["rows"], cfg["columns"], cfg["piece_amounts"])
+    B, steps = 96, 60
+    runs = {}
+    for toy_on in ("1", "0"):
+        monkeypatch.setenv("SX_TOY", toy_on)
+        eng = StrategoEngine(cfg, device="cuda:0")
+        st = eng.alloc_state(B)
+        eng.reset(st, seed=9, shuffle=True)
+        out = eng.alloc_outputs(B, partial=True, full=True, mask=True, sample=True)
+        eng.observe(st, out=out)
+        actions = eng.sample_valid(out["valid_mask"], seed=9, step=0)
+        stats = torch.zeros(8, dtype=torch.int64, device="cuda:0")
+        trace = []
+        for s in range(steps):
+            dense0, player0 = (x.cpu().numpy() for x in eng.export_ref_state(st))
+            eng.step_all(st, actions, out, auto_reset=True, sample_next=True, shuffle=True, seed=9, stats=stats)
+            dense1, player1 = (x.cpu().numpy() for x in eng.export_ref_state(st))
+            rec = {k: v.cpu().numpy().copy() for k, v in out.items()}
+            rec.update(dense=dense1, to_move=player1)
+            trace.append(rec)
+            if toy_on == "1":  # the toy kernel against the oracle, every 5th game
+                acts = actions.cpu().numpy()
+                for b in range(0, B, 5):
+                    ns, npl = orc.apply_spatial_action(dense0[b], int(player0[b]), int(acts[b]))
+                    over = orc.base_env.get_game_ended(ns, npl) != 0
+                    assert bool(rec["done"][b]) == bool(over), (name, s, b)
+                    if over:
+                        ns, npl = dense1[b], 1  # re-set on the device
+                    else:
+                        assert np.array_equal(ns, dense1[b]) and npl == player1[b], (name, s, b)
+                    m_o, po_o, fo_o = orc.current_obs(ns, npl, 3)
+                    assert np.array_equal(rec["valid_mask"][b], m_o), (name, s, b)
+                    assert np.array_equal(_bits(rec["partial_obs"][b]), _bits(po_o)), (name, s, b)
+                    assert np.array_equal(_bits(rec["full_obs"][b]), _bits(fo_o)), (name, s, b)
+            actions = out["next_action"].clone()
+        runs[toy_on] = (trace, stats.cpu().numpy())
+    (toy, toy_stats), (ref, ref_stats) = runs["1"], runs["0"]
+    assert toy_stats[0] > 0 and np.array_equal(toy_stats, ref_stats)
+    for s in range(steps):
+        for key in ref[s]:
+            a, b = toy[s][key], ref[s][key]
+            if a.dtype == np.float32:
+                a, b = a.view(np.uint32), b.view(np.uint32)
+            assert np.array_equal(a, b), (name, s, key)
