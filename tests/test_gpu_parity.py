@@ -378,3 +378,63 @@ def test_toy_kernel_custom_variants_vs_warp_level_kernel_and_oracle(name, monkey
             if a.dtype == np.float32:
                 a, b = a.view(np.uint32), b.view(np.uint32)
             assert np.array_equal(a, b), (name, s, key)
+
+
+@pytest.mark.parametrize("version", ["micro", "tiny", "barrage"])
+def test_double_back_moves_with_and_without_oscillation(version):
+    """The two-square rule (impl:771-777) under both settings of allow_piece_oscillation: during self-play every game
+    tries to move its last-moved piece straight back; legality and the resulting state must match the oracle.
+    Micro / Tiny go through the thread-per-game kernel, Barrage through the warp-level one."""
+    from oracle.binding import OracleProceduralEnv
+    from stratego_env_b200.config import VERSION_CONFIGS, as_version
+    from stratego_env_b200.engine import StrategoEngine, load_setup_table
+    cfg = VERSION_CONFIGS[as_version(version)]
+    R, C = cfg["rows"], cfg["columns"]
+    human = version == "barrage"
+    eng = StrategoEngine(cfg, device="cuda:0", p2_rot180=not human)
+    setups = eng.upload_setups(load_setup_table("barrage")) if human else None
+    orc = OracleProceduralEnv(R, C)
+    B = 128
+    st = eng.alloc_state(B)
+    eng.reset(st, seed=21, setups=setups, shuffle=not human)
+    out = eng.alloc_outputs(B, partial=False, full=False, mask=True, sample=True)
+    eng.observe(st, out=out, partial=False, full=False, mask=True)
+    actions = eng.sample_valid(out["valid_mask"], seed=21, step=0)
+    blocked_seen = legal_seen = 0
+    for s in range(40 if not human else 60):
+        eng.step_all(st, actions, out, auto_reset=True, sample_next=True, setups=setups, shuffle=not human, seed=21)
+        dense, player = (x.cpu().numpy() for x in eng.export_ref_state(st))
+        back = np.full(B, orc.action_size - 1, dtype=np.int32)  # games without a recorded move try the noop
+        for b in range(B):
+            recent = dense[b][6 if player[b] == 1 else 7]
+            came, arrived = np.argwhere(recent == 1), np.argwhere(recent < 0)
+            if len(came) == 1 and len(arrived) == 1:
+                (er, ec), (sr, sc) = came[0], arrived[0]
+                back[b] = orc.get_action_1d_index_from_positions(int(sr), int(sc), int(er), int(ec))
+        for allow in (False, True):
+            trial = st.clone()
+            res = eng.step(trial, torch.as_tensor(back, device="cuda:0"), one_d=True, allow_piece_oscillation=allow)
+            after, _ = eng.export_ref_state(trial)
+            illegal, after = res["illegal"].cpu().numpy().astype(bool), after.cpu().numpy()
+            for b in range(0, B, 3):
+                ok = orc.is_move_valid_by_1d_index(dense[b], int(player[b]), int(back[b]), allow)
+                assert illegal[b] == (not ok), (version, s, b, allow)
+                if ok:
+                    ns, _ = orc.get_next_state(dense[b], int(player[b]), int(back[b]), allow_piece_oscillation=allow)
+                    assert np.array_equal(ns, after[b]), (version, s, b, allow)
+                    legal_seen += 1
+                else:
+                    assert np.array_equal(after[b], dense[b])  # untouched, impl:899-902
+                    blocked_seen += 1
+        # keep oscillating where possible so that the rule actually triggers: play the double-back when it is legal
+        legal_back = ~eng.step(st.clone(), torch.as_tensor(back, device="cuda:0"), one_d=True)["illegal"].cpu().numpy().astype(bool)
+        nxt = out["next_action"].cpu().numpy().copy()
+        for b in range(B):
+            if legal_back[b] and back[b] != orc.action_size - 1 and (s + b) % 2 == 0:
+                a = int(back[b])
+                if player[b] == -1:
+                    a = orc.get_action_1d_index_from_player_perspective(a, -1)
+                r, c, ch = orc.get_action_spatial_index_from_1d_index(a)
+                nxt[b] = (r * C + c) * eng.spatial_channels + ch
+        actions = torch.as_tensor(nxt, dtype=torch.int32, device="cuda:0")
+    assert legal_seen > 50 and blocked_seen > 20
