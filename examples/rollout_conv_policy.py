@@ -57,9 +57,27 @@ def main():
     torch.cuda.synchronize()
     dt = time.perf_counter() - t0
     stats = env.reduce_stats()
+    # where the time goes (CUDA events, a few more steps): conv policy (cuDNN) / masked-logit sampler / fused env step
+    parts = {"policy": 0.0, "sampler": 0.0, "env": 0.0}
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
+    with torch.no_grad():
+        for _ in range(10):
+            ev[0].record()
+            x = obs["partial_observation"].permute(0, 3, 1, 2).to(dtype)
+            logits = policy(x).permute(0, 2, 3, 1).contiguous()
+            ev[1].record()
+            actions = env.sample_actions_from_logits(logits)
+            ev[2].record()
+            obs, rewards, dones, infos = env.step(actions)
+            ev[3].record()
+            torch.cuda.synchronize()
+            for k, (a, b) in zip(parts, ((0, 1), (1, 2), (2, 3))):
+                parts[k] += ev[a].elapsed_time(ev[b]) / 10
     if env.shard.rank == 0:
         print("%d GPU(s) x %d games, %d steps: %.2f M env-steps/s incl. policy; %s" % (
             world, args.envs, args.steps, world * args.envs * args.steps / dt / 1e6, stats))
+        print("per step on rank 0: policy %.3f ms, masked-logit sampler %.3f ms, fused env step %.3f ms (%s policy)" % (
+            parts["policy"], parts["sampler"], parts["env"], "bf16" if args.bf16 else "fp32"))
     if world > 1:
         dist.destroy_process_group()
 

@@ -61,13 +61,24 @@ __global__ void __launch_bounds__(256) sx_sample_logits_kernel(const T *logits, 
         if (mrow[i]) visit(i);
     const int words = (n_actions - min(head, n_actions)) >> 2;
     const uint32_t *mw = reinterpret_cast<const uint32_t *>(mrow + head);
-    for (int w = lane; w < words; w += 32) {
-        uint32_t m = mw[w];
-        if (m == 0) continue;
-        const int base = head + (w << 2);
+    // the mask words are fetched in batches of 8 independent loads per lane (8 x 32 words = 1 KB per batch) so that
+    // the memory latency is paid once per batch instead of once per word; only valid entries cost a logit fetch
+    constexpr int BATCH = 8;
+    for (int w0 = 0; w0 < words; w0 += 32 * BATCH) {
+        uint32_t m[BATCH];
 #pragma unroll
-        for (int b = 0; b < 4; ++b)
-            if ((m >> (8 * b)) & 0xff) visit(base + b);
+        for (int j = 0; j < BATCH; ++j) {
+            const int w = w0 + 32 * j + lane;
+            m[j] = w < words ? __ldg(mw + w) : 0u;
+        }
+#pragma unroll
+        for (int j = 0; j < BATCH; ++j) {
+            if (m[j] == 0) continue;
+            const int base = head + ((w0 + 32 * j + lane) << 2);
+#pragma unroll 1
+            for (int b = 0; b < 4; ++b)
+                if ((m[j] >> (8 * b)) & 0xff) visit(base + b);
+        }
     }
     for (int i = head + (words << 2) + lane; i < n_actions; i += 32)
         if (mrow[i]) visit(i);

@@ -465,15 +465,16 @@ def test_odd_batch_sizes(num_envs):
         assert np.array_equal(_bits(po[b]), _bits(po_o)) and np.array_equal(_bits(fo[b]), _bits(fo_o))
 
 
-@pytest.mark.parametrize("version,B", [("barrage", 262144), ("standard", 131072)])
+@pytest.mark.parametrize("version,B", [("barrage", 262144), ("standard", 131072), ("micro", 262144)])
 def test_full_size_step_every_game_vs_oracle(version, B):
     """BASELINE config 3 size (262 144 Barrage games): after de-phasing, one fused step under full load is
     re-derived game by game by the oracle -- every mask byte and every observation float.  This is the test
-    that would catch an ordering problem between the TMA background copies and the sparse stores."""
+    that would catch an ordering problem between the TMA background copies and the sparse stores (10x10 boards)
+    or between the tile undo / patch / copy phases of the thread-per-game kernel (Micro)."""
     from oracle.binding import OracleEnvLogic
     from stratego_env_b200 import BatchedStrategoEnv, GameVersions, ObservationModes
     from stratego_env_b200.config import VERSION_CONFIGS
-    env = BatchedStrategoEnv({"version": GameVersions(version), "human_inits": True,
+    env = BatchedStrategoEnv({"version": GameVersions(version), "human_inits": version != "micro",
                               "observation_mode": ObservationModes.PARTIALLY_OBSERVABLE},
                              num_envs=B, seed=2026, auto_reset=True, sample_actions=True)
     cfg = VERSION_CONFIGS[GameVersions(version)]
