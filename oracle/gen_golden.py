@@ -20,6 +20,7 @@ Every array below is produced by reference code:
 """
 import os
 import sys
+import zlib
 
 import numpy as np
 
@@ -444,9 +445,73 @@ def side_channel_vectors(se):
     return out
 
 
+CUSTOM_TOYS = {
+    # small boards WITH scouts and lakes (the stock toy variants have neither); same dicts as tests/test_gpu_parity.py
+    "scouts_lakes_4x4": dict(rows=4, columns=4, max_turns=40, obstacle_locations=[(1, 1), (2, 2)],
+                             piece_amounts={2: 2, 3: 1, 11: 1}, initial_state_usable_rows=1),
+    "spy_scout_3x4": dict(rows=3, columns=4, max_turns=30, obstacle_locations=[],
+                          piece_amounts={1: 1, 2: 1, 10: 1, 11: 1}, initial_state_usable_rows=1),
+    "eight_pieces_4x4": dict(rows=4, columns=4, max_turns=60, obstacle_locations=[],
+                             piece_amounts={2: 3, 3: 1, 9: 1, 11: 1, 12: 2}, initial_state_usable_rows=2),
+}
+
+
+def custom_toy_vectors(se):
+    """Random-valid play of custom small variants through the reference's stateless facade (penv:38-173): states,
+    players, 1D actions, the next player's spatial mask (in that player's frame, maenv:452-454) and raw extended
+    observations (penv:166-173)."""
+    from stratego_env.game.stratego_procedural_env import StrategoProceduralEnv
+    out = {}
+    for tag, cfg in CUSTOM_TOYS.items():
+        R, C = cfg["rows"], cfg["columns"]
+        env = StrategoProceduralEnv(R, C)
+        rng = np.random.default_rng(zlib.crc32(tag.encode()))
+        obst = np.zeros((R, C), np.int64)
+        for rc in cfg["obstacle_locations"]:
+            obst[rc] = 1
+        pieces = [code for code, n in cfg["piece_amounts"].items() for _ in range(n)]
+        n_setup = cfg["initial_state_usable_rows"] * C
+        states, players, actions, next_mask, next_po, next_fo = [], [], [], [], [], []
+        while len(actions) < 640:
+            maps = []
+            for _ in range(2):
+                m = np.zeros((R, C), np.int64)
+                cells = rng.permutation(n_setup)[:len(pieces)]
+                for cell, code in zip(cells, pieces):
+                    m[cell // C, cell % C] = code
+                maps.append(m)
+            state = env.create_initial_state(obst, maps[0], maps[1], cfg["max_turns"])
+            player = 1
+            while env.get_game_ended(state, player) == 0 and len(actions) < 640:
+                valid = np.flatnonzero(env.get_valid_moves_as_1d_mask(state, player))
+                a = int(valid[rng.integers(len(valid))])
+                nxt, nplayer = env.get_next_state(state, player, a)
+                persp = env.get_state_from_player_perspective(nxt, nplayer)
+                states.append(state.astype(np.int16)); players.append(player); actions.append(a)
+                next_mask.append(pack_mask(env.get_valid_moves_as_spatial_mask(persp, 1)))
+                next_po.append(env.get_partially_observable_observation_extended_channels(nxt, nplayer).astype(np.float32))
+                next_fo.append(env.get_fully_observable_observation_extended_channels(nxt, nplayer).astype(np.float32))
+                state, player = nxt, nplayer
+            states.append(state.astype(np.int16)); players.append(player); actions.append(-1)  # end-of-game record
+            next_mask.append(next_mask[-1]); next_po.append(next_po[-1]); next_fo.append(next_fo[-1])
+        out["toy_%s_states" % tag] = np.stack(states)
+        out["toy_%s_players" % tag] = np.asarray(players, np.int8)
+        out["toy_%s_actions_1d" % tag] = np.asarray(actions, np.int32)
+        out["toy_%s_next_mask_bits" % tag] = np.stack(next_mask)
+        out["toy_%s_next_po" % tag] = np.stack(next_po)
+        out["toy_%s_next_fo" % tag] = np.stack(next_fo)
+    return out
+
+
 def main():
     se = import_reference()
     os.makedirs(OUT_DIR, exist_ok=True)
+    if "--custom-toys-only" in sys.argv:
+        data = custom_toy_vectors(se)
+        path = os.path.join(OUT_DIR, "custom_toys.npz")
+        np.savez_compressed(path, **data)
+        print("custom_toys.npz %7.1f KB (%d arrays)" % (os.path.getsize(path) / 1024, len(data)))
+        return
     if "--side-channels-only" in sys.argv:
         data = side_channel_vectors(se)
         path = os.path.join(OUT_DIR, "side_channels.npz")
@@ -481,6 +546,10 @@ def main():
     path = os.path.join(OUT_DIR, "side_channels.npz")
     np.savez_compressed(path, **data)
     print("side_channels.npz %7.1f KB (%d arrays)" % (os.path.getsize(path) / 1024, len(data)))
+    data = custom_toy_vectors(se)
+    path = os.path.join(OUT_DIR, "custom_toys.npz")
+    np.savez_compressed(path, **data)
+    print("custom_toys.npz %7.1f KB (%d arrays)" % (os.path.getsize(path) / 1024, len(data)))
 
 
 if __name__ == "__main__":

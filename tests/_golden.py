@@ -34,6 +34,10 @@ def side_channels():
     return load("side_channels")
 
 
+def custom_toys():
+    return load("custom_toys")
+
+
 def unpack_mask(bits, n):
     return np.unpackbits(bits, axis=-1)[..., :n]
 

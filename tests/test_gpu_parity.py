@@ -318,8 +318,9 @@ def test_toy_kernel_recorded_transitions_1d_actions(version):
 
 
 CUSTOM_TOYS = {
-    # stock toy variants have neither scouts nor lakes: these exercise the toy kernel's ray loop, lake handling,
-    # bombs / miners / spies and the 8-cell setup shuffle
+    # stock toy variants have neither scouts nor lakes: these exercise the toy kernel's ray loop, lake handling and
+    # spy / marshal / miner rules (the first two; the 8-piece one needs a 16-entry capture list and stays on the
+    # warp-level kernel, which it exercises with bombs and an 8-cell setup shuffle on a small board)
     "scouts_lakes_4x4": dict(rows=4, columns=4, max_turns=40, obstacle_locations=[(1, 1), (2, 2)],
                              piece_amounts={2: 2, 3: 1, 11: 1}, initial_state_usable_rows=1),
     "spy_scout_3x4": dict(rows=3, columns=4, max_turns=30, obstacle_locations=[],
@@ -438,3 +439,33 @@ def test_double_back_moves_with_and_without_oscillation(version):
                 nxt[b] = (r * C + c) * eng.spatial_channels + ch
         actions = torch.as_tensor(nxt, dtype=torch.int32, device="cuda:0")
     assert legal_seen > 50 and blocked_seen > 20
+
+
+@pytest.mark.parametrize("name", sorted(CUSTOM_TOYS))
+def test_toy_kernel_vs_reference_play_of_custom_variants(name):
+    """the thread-per-game kernel on transitions the REFERENCE played on small boards with scouts and lakes
+    (tests/golden/custom_toys.npz): next state, next player's mask, raw extended observations (penv:166-173)"""
+    from _golden import custom_toys
+    from stratego_env_b200.engine import StrategoEngine
+    g, cfg = custom_toys(), CUSTOM_TOYS[name]
+    R, C = cfg["rows"], cfg["columns"]
+    eng = StrategoEngine(cfg, device="cuda:0", normalize=False)
+    A = eng.spatial_channels
+    states, players, actions = (g["toy_%s_%s" % (name, k)] for k in ("states", "players", "actions_1d"))
+    idx = np.flatnonzero(actions >= 0)
+    idx = idx[:len(idx) // 32 * 32]  # whole groups of 32: every game goes through sx_toy_kernel
+    st = eng.import_ref_state(_t(states[idx].astype(np.int64), torch.int64), _t(players[idx], torch.int8))
+    out = eng.alloc_outputs(len(idx), partial=True, full=True, mask=True)
+    # up to 4 pieces per side (a capture list of 8 entries) step through sx_toy_kernel; the 8-piece variant needs 16
+    # entries and stays on the warp-level kernel
+    assert eng.launch_info(partial=True, full=True, mask=True)["thread_per_game"] == (0 if name == "eight_pieces_4x4" else 1)
+    eng.step_all(st, _t(actions[idx], torch.int32), out, one_d=True)
+    dense, player = eng.export_ref_state(st)
+    torch.cuda.synchronize()
+    assert not out["illegal"].any().item()
+    assert np.array_equal(dense.cpu().numpy(), states[idx + 1].astype(np.int64)), name
+    assert np.array_equal(player.cpu().numpy(), players[idx + 1])
+    assert np.array_equal(out["valid_mask"].cpu().numpy().reshape(len(idx), -1),
+                          unpack_mask(g["toy_%s_next_mask_bits" % name][idx], R * C * A))
+    assert np.array_equal(_bits(out["partial_obs"].cpu().numpy()), _bits(g["toy_%s_next_po" % name][idx]))
+    assert np.array_equal(_bits(out["full_obs"].cpu().numpy()), _bits(g["toy_%s_next_fo" % name][idx]))

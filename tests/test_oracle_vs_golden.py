@@ -5,7 +5,7 @@ import pytest
 from oracle.binding import OracleEnvLogic, OracleProceduralEnv
 from stratego_env_b200.config import VERSION_CONFIGS, as_version
 
-from _golden import VERSIONS, known, original_channels, side_channels, traj, transitions, unpack_mask
+from _golden import VERSIONS, custom_toys, known, original_channels, side_channels, traj, transitions, unpack_mask
 
 
 def bits_equal(a, b):
@@ -95,6 +95,29 @@ def test_side_channels(version):
     assert env.get_heuristic_rewards_from_move(states[0], 1, env.action_size - 1, matrix) == 0  # impl:866-868
     for i, text in zip(g["moves_%s_index" % version], g["moves_%s_json" % version]):
         assert env.get_dict_of_valid_moves_by_position(states[i], int(t["players"][i])) == json.loads(str(text))
+
+
+@pytest.mark.parametrize("tag,shape", [("scouts_lakes_4x4", (4, 4)), ("spy_scout_3x4", (3, 4)), ("eight_pieces_4x4", (4, 4))])
+def test_custom_small_variants_with_scouts_and_lakes(tag, shape):
+    """small boards WITH scouts and lakes (no stock variant has them), played by the reference's facade"""
+    g = custom_toys()
+    R, C = shape
+    env = OracleProceduralEnv(R, C)
+    A = env.spatial_action_size[2]
+    states, players, actions = (g["toy_%s_%s" % (tag, k)] for k in ("states", "players", "actions_1d"))
+    n = 0
+    for i in np.flatnonzero(actions >= 0):
+        st, p, a = states[i].astype(np.int64), int(players[i]), int(actions[i])
+        assert env.get_valid_moves_as_1d_mask(st, p)[a] == 1
+        ns, npl = env.get_next_state(st, p, a)
+        assert np.array_equal(ns, states[i + 1]) and npl == int(players[i + 1]), (tag, i)
+        persp = env.get_state_from_player_perspective(ns, npl)
+        assert np.array_equal(env.get_valid_moves_as_spatial_mask(persp, 1).reshape(-1),
+                              unpack_mask(g["toy_%s_next_mask_bits" % tag][i], R * C * A)), (tag, i)
+        assert bits_equal(env.get_partially_observable_observation_extended_channels(ns, npl), g["toy_%s_next_po" % tag][i])
+        assert bits_equal(env.get_fully_observable_observation_extended_channels(ns, npl), g["toy_%s_next_fo" % tag][i])
+        n += 1
+    assert n >= 500
 
 
 @pytest.mark.parametrize("tag", ["10x10", "3x4", "4x4"])
