@@ -327,6 +327,9 @@ CUSTOM_TOYS = {
                           piece_amounts={1: 1, 2: 1, 10: 1, 11: 1}, initial_state_usable_rows=1),
     "eight_pieces_4x4": dict(rows=4, columns=4, max_turns=60, obstacle_locations=[],
                              piece_amounts={2: 3, 3: 1, 9: 1, 11: 1, 12: 2}, initial_state_usable_rows=2),
+    # four pieces dealt over TWO setup rows: an 8-cell shuffle (two Philox blocks per side), bomb + miner
+    "two_rows_4x4": dict(rows=4, columns=4, max_turns=50, obstacle_locations=[],
+                         piece_amounts={2: 1, 3: 1, 11: 1, 12: 1}, initial_state_usable_rows=2),
 }
 
 

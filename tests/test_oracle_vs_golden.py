@@ -97,7 +97,8 @@ def test_side_channels(version):
         assert env.get_dict_of_valid_moves_by_position(states[i], int(t["players"][i])) == json.loads(str(text))
 
 
-@pytest.mark.parametrize("tag,shape", [("scouts_lakes_4x4", (4, 4)), ("spy_scout_3x4", (3, 4)), ("eight_pieces_4x4", (4, 4))])
+@pytest.mark.parametrize("tag,shape", [("scouts_lakes_4x4", (4, 4)), ("spy_scout_3x4", (3, 4)), ("eight_pieces_4x4", (4, 4)),
+                                       ("two_rows_4x4", (4, 4))])
 def test_custom_small_variants_with_scouts_and_lakes(tag, shape):
     """small boards WITH scouts and lakes (no stock variant has them), played by the reference's facade"""
     g = custom_toys()
