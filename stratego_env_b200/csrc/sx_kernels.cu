@@ -1028,6 +1028,12 @@ static bool toy_eligible(const sx_config *cfg, const KernelArgs &a, int mode)
     if (d.N > 16 || (d.N & 3) != 0 || d.A > 16 || d.board_stride != 16 || d.cap_stride != 8) return false;
     if (d.setup_len > 8 || d.n_pieces > 8 || d.original_channels) return false;
     if (a.player_override || a.reset_mask || a.setup_idx || a.mask1d) return false;
+    // the kernel moves state as 16-byte words and observations as bulk copies: everything must be 16-byte aligned
+    // (torch / cudaMalloc allocations and whole-game offsets into them always are)
+    const uintptr_t bits = reinterpret_cast<uintptr_t>(a.board) | reinterpret_cast<uintptr_t>(a.aux) |
+                           reinterpret_cast<uintptr_t>(a.cap) | reinterpret_cast<uintptr_t>(a.out.partial_obs) |
+                           reinterpret_cast<uintptr_t>(a.out.full_obs);
+    if (bits & 15) return false;
     return a.num_envs >= toy::GAMES;
 }
 
