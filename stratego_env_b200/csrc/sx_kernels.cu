@@ -991,7 +991,9 @@ static int plan_launch_uncached(const sx_config *cfg, uint32_t ops, int mode, lo
     // Measured on B200: throughput peaks when ~0.4 MB of output per SM is in flight and falls beyond it (more
     // resident warps only lengthen the TMA completion queue), so fewer warps for bigger per-game outputs.
     // 8 warps is a sharp optimum for one 10x10 observation + mask (7: -11 %, 9 and more: -3 to -12 %, not monotonic).
-    const int preferred = tile_bytes <= 8 * 1024 ? 32 : tile_bytes <= 32 * 1024 ? (cfg->dev.N >= 100 ? 8 : 10)
+    // Smaller boards carry less output per game, so more of them fit in the same bytes in flight: 8x8 (19 KB per game)
+    // 10 warps 218 M, 12 warps 237 M, 16 warps 255 M env-steps/s with the copy issued late.
+    const int preferred = tile_bytes <= 8 * 1024 ? 32 : tile_bytes <= 32 * 1024 ? (cfg->dev.N >= 100 ? 8 : 16)
                           : tile_bytes <= 64 * 1024 ? 6 : 4;
     int warps = std::min(max_warps, std::max(1, env_int("SX_WARPS", std::min(max_warps, preferred))));
     const int games = cfg->games_per_warp;  // each game of a warp has its own slice
@@ -1287,10 +1289,10 @@ extern "C" int sx_step_all(const sx_config *cfg, sx_state st, int64_t num_envs, 
     // policy, 8 skip sparse stores, 16/32 background issue point.  Sparse boards (Barrage-like) gain from issuing the
     // background at the top of the game; dense boards need it late so the sparse stores still hit L2 (see kernel).
     // B200 sweeps (tools/sweep_fused.py, profiles/r1k_sweep*.txt): a 10x10 board with ONE observation is fastest with the
-    // copy issued after the outcome (16) at 8 warps per SM; both observations and the toy boards issue late (0).
+    // copy issued after the outcome (16) at 8 warps per SM; both observations and the smaller boards issue late (0).
     const bool one_obs = (out.partial_obs != nullptr) != (out.full_obs != nullptr);
     const int n = cfg->dev.N;
-    const int tune = env_int("SX_DEBUG", (n >= 100 && n <= 128 && one_obs) ? 16 : (n >= 64 && 2 * cfg->dev.n_pieces <= 24) ? 32 : 0);
+    const int tune = env_int("SX_DEBUG", (n >= 100 && n <= 128 && one_obs) ? 16 : 0);
     a.flags = (flags & 0xffffu) | (uint32_t(tune) << 16);
     a.out = out;
     a.ops = step_all_ops(out, flags);
