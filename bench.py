@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """Benchmark of the hot path: env-steps/s of the fused step (mask + step + obs + auto-reset).
 
-    python bench.py --gpus N --steps K --warmup W [--workload barrage|micro|tiny|fives|octa|standard|standard_both]
+    python bench.py --gpus N --steps K --warmup W [--workload barrage|micro|tiny|fives|medium|octa|standard|standard_both]
     python bench.py --impl reference ...      # the CPU restatement of the reference on the host cores
 
 One "step" = one pass of the fused kernel over every game of the batch: each game applies one
@@ -41,6 +41,8 @@ WORKLOADS = {
                  desc="Tiny 4x4, 1M envs/GPU, random-valid self-play, auto-reset with shuffled setups, PO obs + mask"),
     "fives": dict(version="fives", table=None, envs=1048576, full=False, dephase=150,
                   desc="Fives 5x5, 1M envs/GPU, random-valid self-play, auto-reset with shuffled setups, PO obs + mask"),
+    "medium": dict(version="medium", table=None, envs=1048576, full=False, dephase=300,
+                   desc="Medium 6x6, 1M envs/GPU, random-valid self-play, shuffled setups, PO obs + mask"),
     "octa": dict(version="octa_barrage", table=None, envs=524288, full=False, dephase=800,
                  desc="Octa-Barrage 8x8, 512k envs/GPU, random-valid self-play, shuffled setups, PO obs + mask"),
     "standard": dict(version="standard", table="standard", envs=524288, full=False, dephase=3000,

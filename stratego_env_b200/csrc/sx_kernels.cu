@@ -993,7 +993,10 @@ static int plan_launch_uncached(const sx_config *cfg, uint32_t ops, int mode, lo
     // 8 warps is a sharp optimum for one 10x10 observation + mask (7: -11 %, 9 and more: -3 to -12 %, not monotonic).
     // Smaller boards carry less output per game, so more of them fit in the same bytes in flight: 8x8 (19 KB per game)
     // 10 warps 218 M, 12 warps 237 M, 16 warps 255 M env-steps/s with the copy issued late.
-    const int preferred = tile_bytes <= 8 * 1024 ? 32 : tile_bytes <= 32 * 1024 ? (cfg->dev.N >= 100 ? 8 : 16)
+    // 6x6 (10.4 KB per game): 10 warps 234 M, 16 warps 324 M, 24 warps 363 M, 32 warps 330 M.  Rule for boards below
+    // 10x10: about 300 KB of output in flight per SM, in multiples of 4 warps.
+    const int small_board = std::max(8, std::min(32, ((300 * 1024 / std::max(1, tile_bytes)) + 2) / 4 * 4));
+    const int preferred = tile_bytes <= 8 * 1024 ? 32 : tile_bytes <= 32 * 1024 ? (cfg->dev.N >= 100 ? 8 : small_board)
                           : tile_bytes <= 64 * 1024 ? 6 : 4;
     int warps = std::min(max_warps, std::max(1, env_int("SX_WARPS", std::min(max_warps, preferred))));
     const int games = cfg->games_per_warp;  // each game of a warp has its own slice
