@@ -50,3 +50,68 @@ def test_lockstep_random_play(version, human, steps):
                 assert np.array_equal(po.view(np.uint32),
                                       obs[p][OC.PARTIAL_OBSERVATION.value].astype(np.float32).view(np.uint32))
             obs = env.reset()
+
+
+@pytest.mark.parametrize("shape,n_states", [((10, 10), 150), ((4, 4), 150), ((3, 4), 100), ((6, 6), 80)])
+def test_random_synthetic_states_differential(shape, n_states):
+    """Differential test on SYNTHETIC boards (not reached by play): random pieces of every rank for both sides, lakes,
+    revealed / unrevealed ranks, still flags, recent-move markers of every code, random captured counters.  Every
+    facade function of the oracle must agree with the reference's: masks, move validity (both oscillation settings),
+    next state, perspective flip, all four observation functions, game-ended values."""
+    import_reference()
+    from stratego_env.game.stratego_procedural_env import StrategoProceduralEnv
+    from oracle.binding import OracleProceduralEnv
+    R, C = shape
+    ref, orc = StrategoProceduralEnv(R, C), OracleProceduralEnv(R, C)
+    rng = np.random.default_rng(R * 100 + C)
+    checked_moves = 0
+    for _ in range(n_states):
+        st = np.zeros((34, R, C), np.int64)
+        cells = rng.permutation(R * C)
+        n_obst = int(rng.integers(0, max(1, R * C // 8)))
+        n1 = int(rng.integers(1, max(2, R * C // 3)))
+        n2 = int(rng.integers(1, max(2, R * C // 3)))
+        for k, cell in enumerate(cells[:n_obst + n1 + n2]):
+            r, c = divmod(int(cell), C)
+            if k < n_obst:
+                st[2, r, c] = 1
+                continue
+            side = 0 if k < n_obst + n1 else 1
+            rank = int(rng.integers(1, 13))
+            st[side, r, c] = rank
+            st[3 + side, r, c] = rank if rng.random() < 0.4 else 13
+            st[32 + side, r, c] = int(rng.random() < 0.5)
+        for side in (0, 1):  # recent-move markers: came-from (+1) and arrived (-1 / -2 / -3) squares
+            if rng.random() < 0.7:
+                a, b = rng.choice(R * C, 2, replace=False)
+                st[6 + side][divmod(int(a), C)] = 1
+                st[6 + side][divmod(int(b), C)] = -int(rng.integers(1, 4))
+            for _ in range(int(rng.integers(0, 4))):  # captured counters
+                t = int(rng.integers(0, 12))
+                st[8 + 12 * side + t][divmod(int(rng.integers(R * C)), C)] += 1
+        st[5, 0, 0] = int(rng.integers(0, 30))
+        st[5, 1, 0] = 40
+        for player in (1, -1):
+            assert np.array_equal(orc.get_valid_moves_as_1d_mask(st, player), ref.get_valid_moves_as_1d_mask(st, player))
+            persp_r = ref.get_state_from_player_perspective(st, player)
+            assert np.array_equal(orc.get_state_from_player_perspective(st, player), persp_r)
+            assert np.array_equal(orc.get_valid_moves_as_spatial_mask(persp_r, 1), ref.get_valid_moves_as_spatial_mask(persp_r, 1))
+            for name in ("get_partially_observable_observation_extended_channels", "get_fully_observable_observation_extended_channels",
+                         "get_partially_observable_observation", "get_fully_observable_observation"):
+                a, b = getattr(orc, name)(st, player), getattr(ref, name)(st, player)
+                assert np.array_equal(np.asarray(a, np.float32).view(np.uint32), np.asarray(b, np.float32).view(np.uint32)), name
+            assert np.float32(orc.get_game_ended(st, player)) == np.float32(ref.get_game_ended(st, player))
+            mask = ref.get_valid_moves_as_1d_mask(st, player)
+            valid = np.flatnonzero(mask[:-1])
+            tries = list(rng.choice(valid, min(3, len(valid)), replace=False)) if len(valid) else []
+            tries += [int(x) for x in rng.integers(0, ref.action_size, 4)]
+            for a in tries:
+                for allow in (False, True):
+                    ok_r = bool(ref.is_move_valid_by_1d_index(st, player, int(a), allow_piece_oscillation=allow))
+                    assert orc.is_move_valid_by_1d_index(st, player, int(a), allow) == ok_r, (shape, a, allow)
+                    if ok_r:
+                        ns_r, _ = ref.get_next_state(st, player, int(a), allow_piece_oscillation=allow)
+                        ns_o, _ = orc.get_next_state(st, player, int(a), allow_piece_oscillation=allow)
+                        assert np.array_equal(ns_o, ns_r), (shape, a, allow)
+                        checked_moves += 1
+    assert checked_moves > n_states
