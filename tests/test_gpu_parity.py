@@ -472,3 +472,80 @@ def test_toy_kernel_vs_reference_play_of_custom_variants(name):
                           unpack_mask(g["toy_%s_next_mask_bits" % name][idx], R * C * A))
     assert np.array_equal(_bits(out["partial_obs"].cpu().numpy()), _bits(g["toy_%s_next_po" % name][idx]))
     assert np.array_equal(_bits(out["full_obs"].cpu().numpy()), _bits(g["toy_%s_next_fo" % name][idx]))
+
+
+def _synthetic_states(R, C, n, rng):
+    """random boards NOT reached by play but representable by the compact device state: pieces of every rank for both
+    sides, lakes, revealed / unrevealed ranks, still flags, recent-move markers, a few captured counters"""
+    states = np.zeros((n, 34, R, C), np.int64)
+    for st in states:
+        cells = rng.permutation(R * C)
+        n_obst = int(rng.integers(0, max(1, R * C // 8)))
+        n1, n2 = int(rng.integers(1, max(2, R * C // 3))), int(rng.integers(1, max(2, R * C // 3)))
+        for k, cell in enumerate(cells[:n_obst + n1 + n2]):
+            r, c = divmod(int(cell), C)
+            if k < n_obst:
+                st[2, r, c] = 1
+                continue
+            side = 0 if k < n_obst + n1 else 1
+            rank = int(rng.integers(1, 13))
+            st[side, r, c] = rank
+            st[3 + side, r, c] = rank if rng.random() < 0.4 else 13
+            st[32 + side, r, c] = int(rng.random() < 0.5 and st[3 + side, r, c] == 13)
+        for side in (0, 1):
+            if rng.random() < 0.7:
+                a, b = rng.choice(R * C, 2, replace=False)
+                st[6 + side][divmod(int(a), C)] = 1
+                st[6 + side][divmod(int(b), C)] = -int(rng.integers(1, 4))
+            for _ in range(int(rng.integers(0, 3))):
+                st[8 + 12 * side + int(rng.integers(0, 12))][divmod(int(rng.integers(R * C)), C)] += 1
+        st[5, 0, 0] = int(rng.integers(0, 30))
+        st[5, 1, 0] = 40
+    return states
+
+
+@pytest.mark.parametrize("shape", [(10, 10), (4, 4), (3, 4), (6, 6)])
+def test_fused_step_on_synthetic_states_vs_oracle(shape):
+    """the fused step on synthetic boards (every rank on every board size, incl. scouts / bombs / spies on the toy boards
+    through the thread-per-game kernel): legality, next state, next mask and raw observations against the oracle"""
+    from oracle.binding import OracleProceduralEnv
+    from stratego_env_b200.engine import StrategoEngine
+    R, C = shape
+    rng = np.random.default_rng(R * 1000 + C)
+    n = 256
+    cfg = {'rows': R, 'columns': C, 'max_turns': 40, 'obstacle_locations': [], 'piece_amounts': {},
+           'initial_state_usable_rows': 1}
+    eng = StrategoEngine(cfg, device="cuda:0", normalize=False, capture_capacity=8 if R * C <= 16 else R * C)
+    orc = OracleProceduralEnv(R, C)
+    states = _synthetic_states(R, C, n, rng)
+    players = rng.choice([1, -1], n).astype(np.int8)
+    actions = np.zeros(n, np.int32)
+    for b in range(n):
+        valid = np.flatnonzero(orc.get_valid_moves_as_1d_mask(states[b], int(players[b])))
+        actions[b] = int(valid[rng.integers(len(valid))]) if rng.random() < 0.8 else int(rng.integers(0, orc.action_size))
+    st = eng.import_ref_state(_t(states, torch.int64), _t(players, torch.int8))
+    out = eng.alloc_outputs(n, partial=True, full=True, mask=True)
+    eng.step_all(st, _t(actions, torch.int32), out, one_d=True)
+    dense, to_move = (x.cpu().numpy() for x in eng.export_ref_state(st))
+    torch.cuda.synchronize()
+    res = {k: v.cpu().numpy() for k, v in out.items()}
+    legal_seen = 0
+    for b in range(n):
+        p, a = int(players[b]), int(actions[b])
+        ok = orc.is_move_valid_by_1d_index(states[b], p, a)
+        assert bool(res["illegal"][b]) == (not ok), (shape, b)
+        if ok:
+            ns, npl = orc.get_next_state(states[b], p, a)
+            legal_seen += 1
+        else:
+            ns, npl = states[b], p
+        assert np.array_equal(dense[b], ns) and int(to_move[b]) == npl, (shape, b)
+        over = orc.get_game_ended(ns, npl) != 0
+        assert bool(res["done"][b]) == bool(ok and over), (shape, b)
+        persp = orc.get_state_from_player_perspective(ns, npl)
+        assert np.array_equal(res["valid_mask"][b], orc.get_valid_moves_as_spatial_mask(persp, 1)), (shape, b)
+        assert np.array_equal(_bits(res["partial_obs"][b]),
+                              _bits(orc.get_partially_observable_observation_extended_channels(ns, npl))), (shape, b)
+        assert np.array_equal(_bits(res["full_obs"][b]),
+                              _bits(orc.get_fully_observable_observation_extended_channels(ns, npl))), (shape, b)
+    assert legal_seen > n // 2
