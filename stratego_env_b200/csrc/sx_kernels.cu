@@ -1288,9 +1288,10 @@ extern "C" int sx_step_all(const sx_config *cfg, sx_state st, int64_t num_envs, 
     KernelArgs a;
     base_args(a, st, num_envs, env_base);
     a.actions = actions_d; a.action_format = action_format;
-    // bits 16+: tuning / experiment switches (SX_DEBUG overrides): 1 skip TMA, 2 skip wait + sparse stores, 4 plain L2
-    // policy, 8 skip sparse stores, 16/32 background issue point.  Sparse boards (Barrage-like) gain from issuing the
-    // background at the top of the game; dense boards need it late so the sparse stores still hit L2 (see kernel).
+    // bits 16+: tuning / experiment switches (SX_DEBUG overrides; they exist for tools/sweep_fused.py, results are WRONG
+    // with 1, 2, 8, 64 or 128): 1 skip TMA, 2 skip wait + sparse stores, 4 plain L2 policy, 8 skip sparse stores, 16 / 32
+    // background issue point (after the outcome / top of the game; default late), 64 no state write-back, 128 output
+    // skeleton only.
     // B200 sweeps (tools/sweep_fused.py, profiles/r1k_sweep*.txt): a 10x10 board with ONE observation is fastest with the
     // copy issued after the outcome (16) at 8 warps per SM; both observations and the smaller boards issue late (0).
     const bool one_obs = (out.partial_obs != nullptr) != (out.full_obs != nullptr);
