@@ -18,6 +18,7 @@ from typing import Tuple
 import numpy as np
 import torch
 
+from .console import board_to_text
 from .engine import StrategoEngine
 from .enums import NUM_STATE_LAYERS, SP
 
@@ -256,4 +257,4 @@ class StrategoProceduralEnv(object):
         return dumps(self.get_partially_observable_observation(state, 1))    # penv:179-181
 
     def print_board_to_console(self, state, partially_observable=False, hide_still_piece_markers=True):
-        raise NotImplementedError("the console printer (penv:183-232) is a debugging aid outside the accelerated path")
+        print(board_to_text(state, partially_observable, hide_still_piece_markers), end="")   # penv:183-216

@@ -150,3 +150,22 @@ def test_valid_move_dict_raises_on_noop_only_mask_like_reference():
     for env in (StrategoProceduralEnv(3, 4), OracleProceduralEnv(3, 4)):
         with pytest.raises(ValueError):
             env.get_dict_of_valid_moves_by_position(state, 1)
+
+
+def test_console_board_text_equals_reference_printer(capsys):
+    """penv:183-216 prints the board; console.board_to_text builds the same text (both frames of truth, with and
+    without the still-piece markers, square and non-square boards)"""
+    import_reference()
+    from stratego_env.game.stratego_procedural_env import StrategoProceduralEnv
+    from stratego_env_b200.console import board_to_text
+    from _golden import traj
+    for version in ("barrage", "micro", "standard2"):
+        t = traj(version)
+        env = StrategoProceduralEnv(int(t["rows"]), int(t["columns"]))
+        for k in (0, len(t["states"]) // 2, len(t["states"]) - 1):
+            state = t["states"][k].astype(np.int64)
+            for po in (False, True):
+                for hide in (True, False):
+                    capsys.readouterr()
+                    env.print_board_to_console(state, partially_observable=po, hide_still_piece_markers=hide)
+                    assert board_to_text(state, po, hide) == capsys.readouterr().out, (version, k, po, hide)
