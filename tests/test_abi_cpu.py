@@ -56,6 +56,36 @@ def test_config_validation_without_gpu():
     assert b"at least 3" in lib.sx_last_error()
 
 
+def test_original_channel_mode_layout_without_gpu():
+    """obs_channel_mode = SX_CHANNELS_ORIGINAL: 32 / 33 channels (impl:1148, impl:1070), and the two extra tables are
+    required"""
+    from stratego_env_b200 import _lib
+    from stratego_env_b200.config import (MICRO_STRATEGO_CONFIG as CFG, original_captured_lut, original_po_rank_lut,
+                                          original_rank_lut, original_unit_lut, piece_amounts_array, recent_moves_lut)
+    lib = _lib.load()
+    desc = _lib.SxConfigDesc()
+    desc.rows, desc.cols, desc.max_turns, desc.usable_rows = CFG["rows"], CFG["columns"], CFG["max_turns"], 1
+    for code, n in enumerate(piece_amounts_array(CFG["piece_amounts"])):
+        desc.piece_amounts[code] = int(n)
+    keep = [np.zeros(12, np.uint8), original_captured_lut(CFG["piece_amounts"]), recent_moves_lut(), original_unit_lut(),
+            original_rank_lut(), original_po_rank_lut()]
+    desc.obstacles, desc.captured_lut, desc.recent_lut, desc.unit_lut = (k.ctypes.data for k in keep[:4])
+    desc.obs_channel_mode = _lib.SX_CHANNELS_ORIGINAL
+    handle = ctypes.c_void_p()
+    assert lib.sx_config_create(ctypes.byref(desc), ctypes.byref(handle)) != 0   # rank tables missing
+    assert b"rank_lut" in lib.sx_last_error()
+    desc.rank_lut, desc.po_rank_lut = keep[4].ctypes.data, keep[5].ctypes.data
+    assert lib.sx_config_create(ctypes.byref(desc), ctypes.byref(handle)) == 0
+    lay = _lib.SxLayout()
+    assert lib.sx_config_layout(handle, ctypes.byref(lay)) == 0
+    assert (lay.po_channels, lay.fo_channels, lay.po_floats, lay.fo_floats) == (32, 33, 12 * 32, 12 * 33)
+    lib.sx_config_destroy(handle)
+    desc.obs_channel_mode = 7
+    assert lib.sx_config_create(ctypes.byref(desc), ctypes.byref(handle)) != 0
+    # the normalised tables themselves: rank / 12 and PO rank / 13 mapped to [-1, 1] (maenv:87-199, 388-396, 499-508)
+    assert keep[4][0] == -1.0 and keep[4][12] == 1.0 and keep[5][13] == 1.0 and keep[3].tolist() == [-1.0, 0.0]
+
+
 @pytest.mark.skipif(torch.cuda.is_available(), reason="checks the no-GPU failure mode")
 def test_no_cpu_fallback():
     from stratego_env_b200 import BatchedStrategoEnv, GameVersions, StrategoMultiAgentEnv, StrategoProceduralEnv
