@@ -98,7 +98,10 @@ typedef struct {
     uint8_t *done;           /* [num_envs] game ended this step (maenv:772) */
     int8_t *winner;          /* [num_envs] +1 / -1 / 0, state[5,0,2] (impl:140) of the ended game */
     uint8_t *ending_invalid; /* [num_envs] impl:846-849 */
-    uint8_t *illegal;        /* [num_envs] action rejected, game left untouched (ValueError, impl:899-902) */
+    uint8_t *illegal;        /* [num_envs] 1 = action rejected, game left untouched (ValueError, impl:899-902);
+                                2 = the game's capture list overflowed: the compact state no longer matches what the
+                                reference's dense counters (impl:999-1009) would hold (sticky until the game is re-set;
+                                cannot happen in games played from the variant's own setups) */
     int8_t *player;          /* [num_envs] player the returned mask/obs are for (= player to move) */
     int32_t *next_action;    /* [num_envs] uniformly sampled valid spatial action for `player`
                                 (replaces maenv:830-834), written when SX_SAMPLE_NEXT is set */
@@ -113,7 +116,10 @@ enum {
     SX_AUTO_RESET = 1,          /* games that end are re-set in the same call; outputs show the new game */
     SX_SAMPLE_NEXT = 2,         /* also draw a uniformly random valid action into outputs.next_action */
     SX_ALLOW_OSCILLATION = 4,   /* allow_piece_oscillation=True (impl:771-777) */
-    SX_RESET_RANDOM_SHUFFLE = 8 /* (re)sets draw setups by shuffling the pieces (util:13-30) instead of a table */
+    SX_RESET_RANDOM_SHUFFLE = 8, /* (re)sets draw setups by shuffling the pieces (util:13-30) instead of a table */
+    SX_KERNEL_BASELINE = 16     /* run the general warp-per-game kernel even where a specialised one is eligible (the
+                                   thread-per-game kernel of the <= 16-cell boards, the ring-rendered 10x10 kernel).
+                                   Results are identical by contract; the cross-kernel parity tests use it */
 };
 
 const char *sx_last_error(void);

@@ -506,9 +506,81 @@ def custom_toy_vectors(se):
     return out
 
 
+SPATIAL_ALIAS_PLAN = {"barrage": 12, "micro": 24, "tiny": 16, "standard2": 6, "octa_barrage": 8}
+
+
+class _quiet_stdout:
+    """the reference prints a reason for every rejected move (impl:737-795) from compiled code: silence fd 1"""
+
+    def __enter__(self):
+        sys.stdout.flush()
+        self.saved = os.dup(1)
+        null = os.open(os.devnull, os.O_WRONLY)
+        os.dup2(null, 1)
+        os.close(null)
+
+    def __exit__(self, *exc):
+        os.dup2(self.saved, 1)
+        os.close(self.saved)
+
+
+def spatial_alias_vectors(se):
+    """EVERY flat spatial action 0 .. R*C*A-1 pushed through the reference's own conversion chain of maenv.step
+    (maenv:685-691: np.unravel_index -> get_action_1d_index_from_spatial_index -> get_action_1d_index_from_player_
+    perspective -> get_next_state) on states taken from the committed trajectories.  Targets off the board and the
+    noop channel are NOT rejected by that chain: they fold into 1D indices that alias other moves (impl:316-347,
+    264-277), so the set of accepted flat actions is larger than the mask.  Recorded: the 1D index each flat action
+    becomes, whether get_next_state accepted it, and the next state of every accepted action that is outside the mask."""
+    from stratego_env.game.stratego_procedural_env import StrategoProceduralEnv
+    out = {}
+    for version, n_states in SPATIAL_ALIAS_PLAN.items():
+        with np.load(os.path.join(OUT_DIR, "traj_%s.npz" % version)) as d:
+            states, players = d["states"].astype(np.int64), d["players"].astype(np.int64)
+        R, C = states.shape[2], states.shape[3]
+        env = StrategoProceduralEnv(R, C)
+        A = env.spatial_action_size[2]
+        pick = np.unique(np.linspace(0, len(states) - 1, n_states).astype(np.int64))
+        one_d = np.zeros((len(pick), R * C * A), np.int64)
+        accepted = np.zeros((len(pick), R * C * A), bool)
+        extra_state, extra_action, extra_next = [], [], []
+        with _quiet_stdout():
+            for j, i in enumerate(pick):
+                state, player = states[i], int(players[i])
+                persp = env.get_state_from_player_perspective(state, player)
+                mask = np.asarray(env.get_valid_moves_as_spatial_mask(persp, 1)).reshape(-1)
+                for a in range(R * C * A):
+                    idx = np.unravel_index(a, env.spatial_action_size)                       # maenv:685
+                    a1 = env.get_action_1d_index_from_spatial_index(idx)                      # maenv:686
+                    a1 = env.get_action_1d_index_from_player_perspective(action_index=a1, player=player)  # maenv:689
+                    one_d[j, a] = a1
+                    try:
+                        nxt, _ = env.get_next_state(state, player, a1)                        # maenv:691
+                    except ValueError:
+                        continue
+                    accepted[j, a] = True
+                    if not mask[a]:
+                        extra_state.append(j); extra_action.append(a); extra_next.append(nxt.astype(np.int16))
+        out["alias_%s_state_index" % version] = pick
+        out["alias_%s_one_d" % version] = one_d.astype(np.int32)
+        out["alias_%s_accepted_bits" % version] = np.packbits(accepted, axis=1)
+        out["alias_%s_extra_state" % version] = np.asarray(extra_state, np.int32)
+        out["alias_%s_extra_action" % version] = np.asarray(extra_action, np.int32)
+        out["alias_%s_extra_next" % version] = (np.stack(extra_next) if extra_next
+                                                 else np.zeros((0, 34, R, C), np.int16))
+        print("alias %-13s states=%2d accepted=%5d outside the mask=%4d" % (version, len(pick), accepted.sum(),
+                                                                          len(extra_action)), file=sys.stderr)
+    return out
+
+
 def main():
     se = import_reference()
     os.makedirs(OUT_DIR, exist_ok=True)
+    if "--spatial-alias-only" in sys.argv:  # adds spatial_alias.npz from the committed trajectories
+        data = spatial_alias_vectors(se)
+        path = os.path.join(OUT_DIR, "spatial_alias.npz")
+        np.savez_compressed(path, **data)
+        print("spatial_alias.npz %7.1f KB (%d arrays)" % (os.path.getsize(path) / 1024, len(data)))
+        return
     if "--custom-toys-only" in sys.argv:
         data = custom_toy_vectors(se)
         path = os.path.join(OUT_DIR, "custom_toys.npz")
@@ -553,6 +625,10 @@ def main():
     path = os.path.join(OUT_DIR, "custom_toys.npz")
     np.savez_compressed(path, **data)
     print("custom_toys.npz %7.1f KB (%d arrays)" % (os.path.getsize(path) / 1024, len(data)))
+    data = spatial_alias_vectors(se)
+    path = os.path.join(OUT_DIR, "spatial_alias.npz")
+    np.savez_compressed(path, **data)
+    print("spatial_alias.npz %7.1f KB (%d arrays)" % (os.path.getsize(path) / 1024, len(data)))
 
 
 if __name__ == "__main__":

@@ -6,7 +6,7 @@ import subprocess
 CSRC = os.path.join(os.path.dirname(os.path.abspath(__file__)), "csrc")
 LIB_PATH = os.path.join(CSRC, "libstratego_b200.so")
 SOURCES = ["sx_kernels.cu", "sx_policy.cu"]
-HEADERS = ["sx_device.cuh", os.path.join("..", "..", "include", "stratego_b200.h")]
+HEADERS = ["sx_device.cuh", "sx_toy.cuh", os.path.join("..", "..", "include", "stratego_b200.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "-shared"]
 
@@ -18,12 +18,20 @@ def _nvcc():
     raise RuntimeError("nvcc not found: the B200 Stratego engine has no CPU fallback and cannot be built")
 
 
+def dependencies():
+    """every file the library is built from: the listed ones plus anything else matching csrc/*.cu* (so a new header
+    can never be forgotten here)"""
+    import glob
+    deps = {os.path.normpath(os.path.join(CSRC, f)) for f in SOURCES + HEADERS}
+    deps.update(os.path.normpath(f) for f in glob.glob(os.path.join(CSRC, "*.cu*")))
+    return sorted(deps)
+
+
 def is_stale() -> bool:
     if not os.path.exists(LIB_PATH):
         return True
     built = os.path.getmtime(LIB_PATH)
-    deps = [os.path.join(CSRC, f) for f in SOURCES + HEADERS]
-    return any(os.path.getmtime(d) > built for d in deps)
+    return any(os.path.getmtime(d) > built for d in dependencies())
 
 
 def build_extension(force: bool = False, verbose: bool = False) -> str:

@@ -11,7 +11,7 @@ from . import _build
 _i32, _i64, _u32, _u64, _vp = C.c_int32, C.c_int64, C.c_uint32, C.c_uint64, C.c_void_p
 
 SX_ACTION_SPATIAL, SX_ACTION_1D = 0, 1
-SX_AUTO_RESET, SX_SAMPLE_NEXT, SX_ALLOW_OSCILLATION, SX_RESET_RANDOM_SHUFFLE = 1, 2, 4, 8
+SX_AUTO_RESET, SX_SAMPLE_NEXT, SX_ALLOW_OSCILLATION, SX_RESET_RANDOM_SHUFFLE, SX_KERNEL_BASELINE = 1, 2, 4, 8, 16
 OBS_PO, OBS_FO, OBS_MASK = 1, 2, 4
 SX_CHANNELS_EXTENDED, SX_CHANNELS_ORIGINAL = 0, 1
 
@@ -97,6 +97,15 @@ def load(build_if_missing: bool = True):
                 raise StrategoB200Error(
                     "CUDA extension %s is missing and could not be built (%s). The B200 Stratego engine has no "
                     "CPU fallback." % (path, exc)) from exc
+            # a library exists but is OLDER than its sources and the rebuild failed: running it would test code that
+            # is not in the tree.  Allowed only where there is no compiler at all (a GPU box that received the prebuilt
+            # library with fresh checkout timestamps); with nvcc present a failed build is an error.
+            import shutil
+            import warnings
+            if shutil.which("nvcc") or os.path.exists("/usr/local/cuda/bin/nvcc"):
+                raise StrategoB200Error("CUDA extension %s is stale and the rebuild failed: %s" % (path, exc)) from exc
+            warnings.warn("stratego_env_b200: %s is older than its sources and could not be rebuilt (%s); using it "
+                          "as is" % (path, exc), RuntimeWarning)
     if not os.path.exists(path):
         raise StrategoB200Error("CUDA extension %s is missing; run __graft_entry__.build(). There is no CPU "
                                 "fallback." % path)

@@ -74,6 +74,7 @@ struct Aux {
     int to_move;                // 0 = player +1, 1 = player -1
     int rfrom[2], rto[2], rcode[2];  // recent-move squares per player (NO_CELL = none); rcode = -code of `to` (1..3)
     int ncap;
+    int overflow;               // sticky: a capture did not fit the capture list -> the compact state lost information
     uint32_t episode;
 };
 
@@ -86,6 +87,7 @@ __device__ __forceinline__ void aux_unpack(const uint32_t w[4], Aux &a)
     a.invalid = (flags >> 1) & 1;
     a.winner = int((flags >> 2) & 3) - 1;
     a.to_move = (flags >> 4) & 1;
+    a.overflow = (flags >> 5) & 1;
     a.ncap = (w[1] >> 8) & 0xff;
     a.rfrom[0] = (w[1] >> 16) & 0xff;
     a.rto[0] = (w[1] >> 24) & 0xff;
@@ -100,7 +102,7 @@ __device__ __forceinline__ void aux_pack(const Aux &a, uint32_t w[4])
 {
     w[0] = uint32_t(a.turn & 0xffff) | (uint32_t(a.max_turns & 0xffff) << 16);
     const uint32_t flags = uint32_t(a.over) | (uint32_t(a.invalid) << 1) | (uint32_t(a.winner + 1) << 2) |
-                           (uint32_t(a.to_move) << 4);
+                           (uint32_t(a.to_move) << 4) | (uint32_t(a.overflow) << 5);
     w[1] = flags | (uint32_t(a.ncap) << 8) | (uint32_t(a.rfrom[0]) << 16) | (uint32_t(a.rto[0]) << 24);
     w[2] = uint32_t(a.rfrom[1]) | (uint32_t(a.rto[1]) << 8) | (uint32_t(a.rcode[0]) << 16) |
            (uint32_t(a.rcode[1]) << 24);
@@ -452,34 +454,8 @@ struct Move {
     bool noop, bad;
 };
 
-// flat spatial index in the mover's frame: maenv:685 (unravel) + impl:316-335 + impl:700-720.
-// The spatial noop channel never decodes to a playable move in the reference (it maps to a
-// zero-length or out-of-range 1D index), so it is rejected here as well.
-__device__ __forceinline__ Move decode_spatial(const DevConfig &cfg, int action, int flip)
-{
-    Move mv{0, 0, 0, 0, 0, 0, false, true};
-    if (action < 0 || action >= cfg.N * cfg.A) return mv;
-    const int cell = fast_div(action, cfg.magic_A), ch = action - cell * cfg.A;
-    const int r = fast_div(cell, cfg.magic_C), c = cell - r * cfg.C;
-    const int mr = cfg.R - 1, mc = cfg.C - 1;
-    int er = r, ec = c;
-    if (ch < mr) er = r + ch + 1;
-    else if (ch < 2 * mr) er = r - (ch - mr + 1);
-    else if (ch < 2 * mr + mc) ec = c + (ch - 2 * mr + 1);
-    else if (ch < 2 * mr + 2 * mc) ec = c - (ch - 2 * mr - mc + 1);
-    else return mv;
-    if (er < 0 || er >= cfg.R || ec < 0 || ec >= cfg.C) return mv;
-    mv.sr = flip ? cfg.R - 1 - r : r;
-    mv.sc = flip ? cfg.C - 1 - c : c;
-    mv.er = flip ? cfg.R - 1 - er : er;
-    mv.ec = flip ? cfg.C - 1 - ec : ec;
-    mv.start = mv.sr * cfg.C + mv.sc;
-    mv.end = mv.er * cfg.C + mv.ec;
-    mv.bad = false;
-    return mv;
-}
-
-// absolute 1D index (impl:352-383); the last index is the noop
+// absolute 1D index (impl:352-383); the last index is the noop.  Anything outside [0, action_size) decodes in the
+// reference (floor division) to a start square off the board, which impl:745-749 rejects.
 __device__ __forceinline__ Move decode_1d(const DevConfig &cfg, int action)
 {
     Move mv{0, 0, 0, 0, 0, 0, false, true};
@@ -491,6 +467,54 @@ __device__ __forceinline__ Move decode_1d(const DevConfig &cfg, int action)
     mv.sr = r; mv.sc = c; mv.er = er; mv.ec = ec;
     mv.start = cell;
     mv.end = er * cfg.C + ec;
+    mv.bad = false;
+    return mv;
+}
+
+// Python's // and % (numba int64 floor semantics) for a possibly negative numerator and d > 0
+__device__ __forceinline__ int floor_div(int x, int d) { const int q = x / d; return (x % d != 0 && x < 0) ? q - 1 : q; }
+__device__ __forceinline__ int floor_mod(int x, int d) { const int m = x % d; return m < 0 ? m + d : m; }
+
+// A spatial action whose target square is off the board, or that uses the noop channel.  The reference does NOT
+// reject these: impl:316-335 produces the unchecked target, impl:264-277 folds it into a 1D index that ALIASES another
+// move (or the 1D noop, or an index outside the action space), impl:700-720 rotates that index for player -1 with
+// floor division, and _get_next_state plays whatever it decodes to (impl:803-831).  Reproduced step by step; cold.
+static __device__ __noinline__ int alias_spatial_1d(const DevConfig *cfgp, int cell, int r, int er, int ec, int flip)
+{
+    const DevConfig &cfg = *cfgp;
+    int idx = cell * cfg.mpa + (er != r ? er : cfg.R + ec);  // impl:268-275
+    if (flip && idx != cfg.action_size - 1) {                // impl:700-720 (the noop index is perspective-invariant)
+        const int start = floor_div(idx, cfg.mpa), off = floor_mod(idx, cfg.mpa);  // impl:369-383
+        const int sr = floor_div(start, cfg.C), sc = floor_mod(start, cfg.C);
+        const int tr = off >= cfg.R ? sr : off, tc = off >= cfg.R ? off - cfg.R : sc;
+        const int fsr = cfg.R - 1 - sr, fsc = cfg.C - 1 - sc, fer = cfg.R - 1 - tr, fec = cfg.C - 1 - tc;  // impl:687-695
+        idx = (fsr * cfg.C + fsc) * cfg.mpa + (fer != fsr ? fer : cfg.R + fec);
+    }
+    return idx;
+}
+
+// flat spatial index in the mover's frame: maenv:685 (unravel; out of range raises) + impl:316-347 + impl:700-720.
+// Targets on the board take the direct route (identical to the reference's index arithmetic there); everything else
+// goes through the reference's unchecked 1D aliasing above.
+__device__ __forceinline__ Move decode_spatial(const DevConfig &cfg, int action, int flip)
+{
+    Move mv{0, 0, 0, 0, 0, 0, false, true};
+    if (action < 0 || action >= cfg.N * cfg.A) return mv;
+    const int cell = fast_div(action, cfg.magic_A), ch = action - cell * cfg.A;
+    const int r = fast_div(cell, cfg.magic_C), c = cell - r * cfg.C;
+    const int mr = cfg.R - 1, mc = cfg.C - 1;
+    int er = r, ec = c;
+    if (ch < mr) er = r + ch + 1;
+    else if (ch < 2 * mr) er = r - (ch - mr + 1);
+    else if (ch < 2 * mr + mc) ec = c + (ch - 2 * mr + 1);
+    else ec = c - (ch - 2 * mr - mc + 1);  // impl:331-333: the noop channel lands here too (ec = c - C)
+    if (er < 0 || er >= cfg.R || ec < 0 || ec >= cfg.C) return decode_1d(cfg, alias_spatial_1d(&cfg, cell, r, er, ec, flip));
+    mv.sr = flip ? cfg.R - 1 - r : r;
+    mv.sc = flip ? cfg.C - 1 - c : c;
+    mv.er = flip ? cfg.R - 1 - er : er;
+    mv.ec = flip ? cfg.C - 1 - ec : ec;
+    mv.start = mv.sr * cfg.C + mv.sc;
+    mv.end = mv.er * cfg.C + mv.ec;
     mv.bad = false;
     return mv;
 }
@@ -525,6 +549,10 @@ __device__ __forceinline__ bool move_is_legal(const DevConfig &cfg, const WarpMe
 }
 
 // records one captured piece (impl:999-1009) in the capture list; lanes search entries in parallel
+// A capture that does not fit (count beyond 8 in one entry, or more distinct entries than the list holds: neither can
+// happen in games played from a variant's own setups, whose list is sized 2 x pieces) is NOT dropped silently: the
+// game's sticky overflow flag is raised and the step reports it (`illegal` = 2), because the reference's dense int64
+// counters (impl:999-1009) would have kept counting.
 template <class GT>
 __device__ __forceinline__ void add_capture_inl(const DevConfig &cfg, const WarpMem &m, Aux &a, int cell, int owner, int type)
 {
@@ -535,16 +563,21 @@ __device__ __forceinline__ void add_capture_inl(const DevConfig &cfg, const Warp
         if ((uint32_t(m.cap[e]) & 0x1fffu) == key) hit = e;
     const bool vote = GT::any(hit >= 0);
     if (vote) {
-        if (hit >= 0 && (m.cap[hit] >> 13) < 7) m.cap[hit] = uint16_t(m.cap[hit] + (1u << 13));
+        const bool full = GT::any(hit >= 0 && (m.cap[hit] >> 13) >= 7);
+        if (full) a.overflow = 1;
+        else if (hit >= 0) m.cap[hit] = uint16_t(m.cap[hit] + (1u << 13));
     } else if (a.ncap < cfg.cap_stride) {
         if (lane == 0) m.cap[a.ncap] = uint16_t(key);
         a.ncap += 1;
+    } else {
+        a.overflow = 1;
     }
     GT::sync();
 }
 
 // Out-of-line entry (attacks are 2-4 % of moves): arguments and result by value so that the caller's
 // Aux stays in registers.
+// Returns the new entry count, or -1 - count when the capture did not fit.
 template <class GT>
 static __device__ __noinline__ int add_capture(const DevConfig *cfg, uint16_t *cap, int ncap, int cell, int owner, int type)
 {
@@ -553,7 +586,7 @@ static __device__ __noinline__ int add_capture(const DevConfig *cfg, uint16_t *c
     Aux a{};
     a.ncap = ncap;
     add_capture_inl<GT>(*cfg, m, a, cell, owner, type);
-    return a.ncap;
+    return a.overflow ? -1 - a.ncap : a.ncap;
 }
 
 // impl:897-1028: applies a decoded move for the player to move.  The opponent-stuck and max-turn
@@ -602,8 +635,14 @@ __device__ __forceinline__ StepStatus apply_move(const DevConfig &cfg, const War
     if (GT::lane() == 0) { m.board[mv.start] = uint8_t(new_start); m.board[mv.end] = uint8_t(new_end); }
     GT::sync();
     if (defender != 0) {  // impl:999-1009
-        if (!wins) a.ncap = add_capture<GT>(&cfg, m.cap, a.ncap, mv.end, me, rank);
-        if (wins || tie) a.ncap = add_capture<GT>(&cfg, m.cap, a.ncap, mv.end, me ^ 1, defender);
+        if (!wins) {
+            const int n = add_capture<GT>(&cfg, m.cap, a.ncap, mv.end, me, rank);
+            if (n < 0) { a.overflow = 1; a.ncap = -1 - n; } else a.ncap = n;
+        }
+        if (wins || tie) {
+            const int n = add_capture<GT>(&cfg, m.cap, a.ncap, mv.end, me ^ 1, defender);
+            if (n < 0) { a.overflow = 1; a.ncap = -1 - n; } else a.ncap = n;
+        }
     }
     // impl:1013-1028: the mover's recent-move record is rebuilt from scratch
     if (defender == 0) {
@@ -707,6 +746,7 @@ __device__ __forceinline__ void reset_game_inl(const DevConfig &cfg, const WarpM
     a.rto[0] = a.rto[1] = NO_CELL;
     a.rcode[0] = a.rcode[1] = 0;
     a.ncap = 0;
+    a.overflow = 0;
     a.episode = episode + 1;
 }
 

@@ -107,8 +107,56 @@ __host__ __device__ constexpr uint32_t mode_ops(int mode)
          : mode == MODE_OBSERVE_PO_MASK ? (OP_MASK | OP_PO) : 0u;
 }
 
+// end-of-run statistics: per-thread 32-bit counters, published once per launch
+struct StepCounters {
+    uint32_t games, p1, p2, invalid, illegal, steps, attacks, resets;
+    __device__ __forceinline__ void count_step(StepStatus status, bool done, const Aux &a)
+    {
+        if (status == STEP_ILLEGAL) illegal += 1;
+        else steps += 1;
+        if (done && status != STEP_UNCHANGED) {
+            games += 1;
+            p1 += a.winner == 1;
+            p2 += a.winner == -1;
+            invalid += a.invalid;
+        }
+    }
+    __device__ __forceinline__ void warp_sum()  // one game per lane (toy kernel): add the lanes' counters up
+    {
+        for (int off = 16; off > 0; off >>= 1) {
+            games += __shfl_xor_sync(FULL, games, off); p1 += __shfl_xor_sync(FULL, p1, off);
+            p2 += __shfl_xor_sync(FULL, p2, off); invalid += __shfl_xor_sync(FULL, invalid, off);
+            illegal += __shfl_xor_sync(FULL, illegal, off); steps += __shfl_xor_sync(FULL, steps, off);
+            attacks += __shfl_xor_sync(FULL, attacks, off); resets += __shfl_xor_sync(FULL, resets, off);
+        }
+    }
+    __device__ __forceinline__ void publish(long long *stats) const
+    {
+        const uint32_t v[8] = {games, p1, p2, invalid, illegal, steps, attacks, resets};
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+            if (v[i]) atomicAdd(reinterpret_cast<unsigned long long *>(stats + i), (unsigned long long)v[i]);
+    }
+};
+// out.illegal: 0 ok, 1 action rejected (game untouched), 2 the game's capture list overflowed (add_capture_inl)
+__device__ __forceinline__ uint8_t illegal_code(StepStatus status, const Aux &a)
+{
+    return status == STEP_ILLEGAL ? 1 : (a.overflow ? 2 : 0);
+}
+constexpr int MAX_REDRAWS = 8;  // re-draws of an unplayable setup (first player without a move) per reset
+
 #ifndef SX_MAX_THREADS
 #define SX_MAX_THREADS 512
+#endif
+// Experiment switches (flag bits 16-19 and 22-23 of KernelArgs::flags, and the SX_DEBUG / SX_WARPS / SX_BLOCKS /
+// SX_TOY / SX_TOY_WARPS / SX_GAMES_PER_WARP environment variables) exist only in builds made with -DSX_EXPERIMENTS
+// (tools/sweep_fused.py builds its own copy of the library): several of them produce WRONG results by design (skip
+// the copies, skip the sparse stores, no state write-back), so the shipped library neither reads the environment nor
+// contains those branches.  Bits 20-21 (where a game's background copy is issued) are result-preserving and stay.
+#ifdef SX_EXPERIMENTS
+#define SX_EXP(flags, bit) (((flags) & (bit)) != 0)
+#else
+#define SX_EXP(flags, bit) false
 #endif
 // K = board cells per lane, G = games per warp (Grp<G>): 10x10 -> K 4, G 1; 3x4 / 4x4 -> K 2, G 4.
 template <int K, int MODE, int G>
@@ -150,7 +198,7 @@ __global__ void __launch_bounds__(K <= 2 ? 1024 : SX_MAX_THREADS, 1) sx_fused_ke
     }
     __syncthreads();
 
-    const bool hints = !(flags & 0x40000u);
+    const bool hints = !SX_EXP(flags, 0x40000u);
     const uint64_t pol_keep = l2_policy(hints ? 1 : 0), pol_stream = l2_policy(hints ? 2 : 0);
 
     // ---- software pipeline -----------------------------------------------------------------------------
@@ -174,7 +222,7 @@ __global__ void __launch_bounds__(K <= 2 ? 1024 : SX_MAX_THREADS, 1) sx_fused_ke
         pf.action = do_step ? args.actions[e] : 0;
     };
     auto issue_background = [&](long long e) {
-        if (flags & 0x10000u) return;  // experiment switch
+        if (SX_EXP(flags, 0x10000u)) return;  // experiment: no background copies
         // the small mask copy goes first (measured: +3 % over observation-first at 10 warps per SM)
         if (do_mask) {
             uint8_t *gmask = args.out.valid_mask + e * cfg.mask_bytes;
@@ -195,7 +243,7 @@ __global__ void __launch_bounds__(K <= 2 ? 1024 : SX_MAX_THREADS, 1) sx_fused_ke
         if (lane == 0) bulk_commit();
     };
 
-    long long n_games = 0, n_p1 = 0, n_p2 = 0, n_invalid = 0, n_illegal = 0;
+    StepCounters cnt{};
     const long long total_warps = (long long)gridDim.x * warps_per_block;
     long long env = (long long)blockIdx.x * warps_per_block + warp;
     Prefetched pf;
@@ -228,7 +276,7 @@ __global__ void __launch_bounds__(K <= 2 ? 1024 : SX_MAX_THREADS, 1) sx_fused_ke
         const bool has_next = next_env < args.num_envs;
         if (has_next) load_state(next_env, pf);
         if (do_tile && issue_at == 2) issue_background(env);
-        if (flags & 0x800000u) {  // experiment: output skeleton only (no rules): background copy + wait
+        if (SX_EXP(flags, 0x800000u)) {  // experiment: output skeleton only (no rules): background copy + wait
             if (do_tile && issue_at != 2) issue_background(env);
             if (lane == 0) bulk_wait_all();
             GT::sync();
@@ -252,7 +300,11 @@ __global__ void __launch_bounds__(K <= 2 ? 1024 : SX_MAX_THREADS, 1) sx_fused_ke
             return gen_moves_cold<K, GT>(&cfg, warp_base, make_uint4(w[0], w[1], w[2], w[3]), me);
         };
         if (MODE == MODE_GENERIC && (ops & OP_RESET) && (args.reset_mask == nullptr || args.reset_mask[env] != 0)) {
-            do_reset();
+            // drawn setups only (explicit setup_idx rows are the caller's choice): see the auto-reset below
+            for (int tries = 0; tries < MAX_REDRAWS; ++tries) {
+                do_reset();
+                if (args.setup_idx != nullptr || regen_moves(a.to_move)) break;
+            }
             dirty = true;
         }
 
@@ -267,6 +319,7 @@ __global__ void __launch_bounds__(K <= 2 ? 1024 : SX_MAX_THREADS, 1) sx_fused_ke
             int attack;
             status = apply_move<GT>(cfg, m, a, mv, allow_osc, attack);
             dirty |= status != STEP_ILLEGAL;
+            cnt.attacks += attack;
         }
 
         // ---- move list of the player the outputs are for -------------------------------------------
@@ -291,22 +344,24 @@ __global__ void __launch_bounds__(K <= 2 ? 1024 : SX_MAX_THREADS, 1) sx_fused_ke
                 if (args.out.done) args.out.done[env] = done ? 1 : 0;
                 if (args.out.winner) args.out.winner[env] = int8_t(done ? w : 0);
                 if (args.out.ending_invalid) args.out.ending_invalid[env] = (done && a.invalid) ? 1 : 0;
-                if (args.out.illegal) args.out.illegal[env] = status == STEP_ILLEGAL ? 1 : 0;
+                if (args.out.illegal) args.out.illegal[env] = illegal_code(status, a);
                 if (args.out.reward) args.out.reward[env] = (done && !a.invalid) ? float(w) : 0.0f;  // maenv:777-801
             }
-            if (status == STEP_ILLEGAL) n_illegal += 1;
-            if (done && status != STEP_UNCHANGED) {
-                n_games += 1;
-                n_p1 += a.winner == 1;
-                n_p2 += a.winner == -1;
-                n_invalid += a.invalid;
-            }
+            cnt.count_step(status, done, a);
         }
 
         if (done && (flags & SX_AUTO_RESET)) {
-            do_reset();
-            viewer = a.to_move;
-            if (need_moves) any = regen_moves(viewer);
+            // A drawn setup in which the player to move has no move cannot be played in the reference either (the only
+            // entry of its mask is the noop, which maenv.step rejects: impl:316-347 decodes it to an illegal move), so
+            // such a draw -- 2e-6 of Standard shuffles, none of the human tables -- is drawn again (next episode number).
+            for (int tries = 0; tries < MAX_REDRAWS; ++tries) {
+                do_reset();
+                cnt.resets += 1;
+                viewer = a.to_move;
+                if (!need_moves) break;
+                any = regen_moves(viewer);
+                if (any) break;
+            }
         }
         if (args.out.player && lane == 0) args.out.player[env] = viewer == 0 ? 1 : -1;
         if (do_tile && issue_at == 1) issue_background(env);
@@ -317,7 +372,7 @@ __global__ void __launch_bounds__(K <= 2 ? 1024 : SX_MAX_THREADS, 1) sx_fused_ke
             if (!any && lane == 0) row[cfg.action_size - 1] = 1;  // impl:639-640
         }
 
-        if ((ops & OP_WRITE_STATE) && dirty && !(flags & 0x400000u)) {  // (0x400000: experiment, no state write-back)
+        if ((ops & OP_WRITE_STATE) && dirty && !SX_EXP(flags, 0x400000u)) {  // (0x400000: experiment, no state write-back)
             uint32_t *gb = reinterpret_cast<uint32_t *>(args.board + env * cfg.board_stride);
             for (int i = lane; i < (cfg.board_stride >> 2); i += GT::L)
                 st_hint(gb + i, reinterpret_cast<const uint32_t *>(m.board)[i], pol_keep);
@@ -339,10 +394,10 @@ __global__ void __launch_bounds__(K <= 2 ? 1024 : SX_MAX_THREADS, 1) sx_fused_ke
 
         // ---- render: sparse entries on top of the (by now written) background ---------------------------
         if (do_tile && issue_at == 0) issue_background(env);
-        if (do_tile && !(flags & 0x20000u)) {
+        if (do_tile && !SX_EXP(flags, 0x20000u)) {
             if (lane == 0) bulk_wait_all();  // this game's background is in global memory
             GT::sync();
-            if (flags & 0x80000u) continue;  // experiment: wait but skip the sparse stores
+            if (SX_EXP(flags, 0x80000u)) continue;  // experiment: wait but skip the sparse stores
             if (original) {
                 if (do_po) patch_obs<K, GT, true>(cfg, m, a, args.out.partial_obs + env * cfg.po_floats, pom, viewer, pol_stream);
                 if (do_fo) patch_obs<K, GT, true>(cfg, m, a, args.out.full_obs + env * cfg.fo_floats, fom, viewer, pol_stream);
@@ -359,15 +414,7 @@ __global__ void __launch_bounds__(K <= 2 ? 1024 : SX_MAX_THREADS, 1) sx_fused_ke
         GT::sync();
     }
 
-    if (args.stats) {
-        if (lane == 0) {  // all lanes carry identical counters; lane 0 publishes
-            if (n_games) atomicAdd(reinterpret_cast<unsigned long long *>(args.stats + 0), (unsigned long long)n_games);
-            if (n_p1) atomicAdd(reinterpret_cast<unsigned long long *>(args.stats + 1), (unsigned long long)n_p1);
-            if (n_p2) atomicAdd(reinterpret_cast<unsigned long long *>(args.stats + 2), (unsigned long long)n_p2);
-            if (n_invalid) atomicAdd(reinterpret_cast<unsigned long long *>(args.stats + 3), (unsigned long long)n_invalid);
-            if (n_illegal) atomicAdd(reinterpret_cast<unsigned long long *>(args.stats + 4), (unsigned long long)n_illegal);
-        }
-    }
+    if (args.stats && lane == 0) cnt.publish(args.stats);  // all lanes of a game carry identical counters
 }
 
 
@@ -423,7 +470,7 @@ __global__ void __launch_bounds__(512, 1) sx_toy_kernel(const __grid_constant__ 
     __syncwarp();
 
     const toy::Geometry geo = toy::make_geometry(cfg);
-    long long n_games = 0, n_p1 = 0, n_p2 = 0, n_invalid = 0, n_illegal = 0;
+    StepCounters cnt{};
     const long long n_groups = args.num_envs / toy::GAMES;
     // the next group's state loads are issued before this group is rendered, so they never stall the rules
     uint4 pf_b = make_uint4(0, 0, 0, 0), pf_c = pf_b, pf_a = pf_b;
@@ -467,9 +514,11 @@ __global__ void __launch_bounds__(512, 1) sx_toy_kernel(const __grid_constant__ 
         // nothing else is, impl:809-814), pass 1 for the next player (stuck check, impl:1031-1036), pass 2 for the fresh
         // game of an auto-reset.
 #pragma unroll 1
-        for (int pass = (move.noop && !move.bad && !a.over) ? 0 : 1; pass < 3; ++pass) {
+        for (int pass = (move.noop && !move.bad && !a.over) ? 0 : 1; pass < 2 + MAX_REDRAWS; ++pass) {
             if (pass == 1) {
+                const uint32_t end_before = move.bad || move.noop ? 0u : toy::cell_get(s, move.end);
                 status = toy::apply_move(cfg, s, a, move, allow_osc);
+                cnt.attacks += (status == STEP_MOVED && (end_before & CELL_RANK) != 0) ? 1 : 0;
                 viewer = a.to_move;
             }
             const int who = pass == 0 ? mover : viewer;
@@ -478,7 +527,13 @@ __global__ void __launch_bounds__(512, 1) sx_toy_kernel(const __grid_constant__ 
                 if (total > 0) move.bad = true;
                 continue;
             }
-            if (pass == 2) break;
+            if (pass >= 2) {  // fresh game: an unplayable draw (first player without a move) is drawn again, see sx_fused_kernel
+                if (total > 0 || pass - 1 >= MAX_REDRAWS) break;
+                toy::reset_game(cfg, s, a, args.setups, args.n_setups, (flags & SX_RESET_RANDOM_SHUFFLE) != 0, args.key, gid);
+                cnt.resets += 1;
+                viewer = a.to_move;
+                continue;
+            }
             if (status == STEP_MOVED) {
                 if (total == 0 && !a.over) { a.over = 1; a.winner = mover == 0 ? 1 : -1; }
                 if (a.turn >= a.max_turns && !a.over) {  // impl:1040-1043; terminal masks are noop-only
@@ -494,17 +549,12 @@ __global__ void __launch_bounds__(512, 1) sx_toy_kernel(const __grid_constant__ 
             if (args.out.done) args.out.done[env] = done ? 1 : 0;
             if (args.out.winner) args.out.winner[env] = int8_t(done ? w : 0);
             if (args.out.ending_invalid) args.out.ending_invalid[env] = (done && a.invalid) ? 1 : 0;
-            if (args.out.illegal) args.out.illegal[env] = status == STEP_ILLEGAL ? 1 : 0;
+            if (args.out.illegal) args.out.illegal[env] = illegal_code(status, a);
             if (args.out.reward) args.out.reward[env] = (done && !a.invalid) ? float(w) : 0.0f;  // maenv:777-801
-            if (status == STEP_ILLEGAL) n_illegal += 1;
-            if (done && status != STEP_UNCHANGED) {
-                n_games += 1;
-                n_p1 += w == 1;
-                n_p2 += w == -1;
-                n_invalid += a.invalid;
-            }
+            cnt.count_step(status, done, a);
             if (!(done && (flags & SX_AUTO_RESET))) break;
             toy::reset_game(cfg, s, a, args.setups, args.n_setups, (flags & SX_RESET_RANDOM_SHUFFLE) != 0, args.key, gid);
+            cnt.resets += 1;
             viewer = a.to_move;
         }
         if (args.out.player) args.out.player[env] = viewer == 0 ? 1 : -1;
@@ -578,20 +628,8 @@ __global__ void __launch_bounds__(512, 1) sx_toy_kernel(const __grid_constant__ 
     if (do_tile && lane == 0) bulk_wait_read();  // shared memory must outlive the copies
 
     if (args.stats) {
-        for (int off = 16; off > 0; off >>= 1) {
-            n_games += __shfl_xor_sync(FULL, n_games, off);
-            n_p1 += __shfl_xor_sync(FULL, n_p1, off);
-            n_p2 += __shfl_xor_sync(FULL, n_p2, off);
-            n_invalid += __shfl_xor_sync(FULL, n_invalid, off);
-            n_illegal += __shfl_xor_sync(FULL, n_illegal, off);
-        }
-        if (lane == 0) {
-            if (n_games) atomicAdd(reinterpret_cast<unsigned long long *>(args.stats + 0), (unsigned long long)n_games);
-            if (n_p1) atomicAdd(reinterpret_cast<unsigned long long *>(args.stats + 1), (unsigned long long)n_p1);
-            if (n_p2) atomicAdd(reinterpret_cast<unsigned long long *>(args.stats + 2), (unsigned long long)n_p2);
-            if (n_invalid) atomicAdd(reinterpret_cast<unsigned long long *>(args.stats + 3), (unsigned long long)n_invalid);
-            if (n_illegal) atomicAdd(reinterpret_cast<unsigned long long *>(args.stats + 4), (unsigned long long)n_illegal);
-        }
+        cnt.warp_sum();
+        if (lane == 0) cnt.publish(args.stats);
     }
 }
 
@@ -721,6 +759,7 @@ __global__ void sx_import_kernel(DevConfig cfg, uint8_t *board, int16_t *aux, ui
     a.winner = winner > 0 ? 1 : winner < 0 ? -1 : 0;
     a.to_move = (player && player[env] == -1) ? 1 : 0;
     a.ncap = min(ncap, cfg.cap_stride);
+    a.overflow = 0;
     a.episode = 0;
     if (lane == 0) {
         uint32_t w[4];
@@ -818,10 +857,16 @@ static int fail(const std::string &msg)
 int sx_set_error(const std::string &msg) { return fail(msg); }  // for the other translation units of the library
 static int cuda_fail(const char *what, cudaError_t e) { return fail(std::string(what) + ": " + cudaGetErrorString(e)); }
 
+// tuning knobs: read from the environment only in -DSX_EXPERIMENTS builds (see SX_EXP above)
 static int env_int(const char *name, int fallback)
 {
+#ifdef SX_EXPERIMENTS
     const char *v = std::getenv(name);
     return (v && *v) ? std::atoi(v) : fallback;
+#else
+    (void)name;
+    return fallback;
+#endif
 }
 
 extern "C" const char *sx_last_error(void) { return g_error.c_str(); }
@@ -1028,7 +1073,7 @@ static int plan_launch_uncached(const sx_config *cfg, uint32_t ops, int mode, lo
 static bool toy_eligible(const sx_config *cfg, const KernelArgs &a, int mode)
 {
     const DevConfig &d = cfg->dev;
-    if (env_int("SX_TOY", 1) == 0) return false;
+    if (env_int("SX_TOY", 1) == 0 || (a.flags & SX_KERNEL_BASELINE)) return false;
     if (mode != MODE_STEP_PO_MASK && mode != MODE_STEP_PO_FO_MASK && mode != MODE_STEP_LEAN) return false;
     if (d.N > 16 || (d.N & 3) != 0 || d.A > 16 || d.board_stride != 16 || d.cap_stride != 8) return false;
     if (d.setup_len > 8 || d.n_pieces > 8 || d.original_channels) return false;

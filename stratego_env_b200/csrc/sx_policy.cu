@@ -29,6 +29,14 @@ __device__ __forceinline__ float load_logit<__half>(const __half *p) { return __
 
 constexpr uint32_t RNG_POLICY = 0x504f4c59u;
 
+// 23 random bits -> (k + 0.5) / 2^23: every value is exactly representable in float32 (k + 0.5 needs 24 significant
+// bits) and lies strictly inside (0, 1), so -log(-log(u)) is always finite.  (24 bits + 0.5 rounds to 1.0 for the top
+// value, which made that entry win regardless of its logit once in 2^24 draws.)
+__host__ __device__ __forceinline__ float uniform_open01(uint32_t bits)
+{
+    return (float(bits >> 9) + 0.5f) * (1.0f / 8388608.0f);
+}
+
 template <typename T>
 __global__ void __launch_bounds__(256) sx_sample_logits_kernel(const T *logits, const uint8_t *mask, long long num_envs,
                                                                int n_actions, long long env_base, uint2 key, uint32_t step,
@@ -48,7 +56,7 @@ __global__ void __launch_bounds__(256) sx_sample_logits_kernel(const T *logits, 
     auto visit = [&](int i) {
         const float z = load_logit<T>(lrow + i) * inv_temperature;
         const uint4 r = philox4x32_10(make_uint4(uint32_t(gid), uint32_t(gid >> 32), RNG_POLICY ^ step, uint32_t(i)), key);
-        const float u = (float(r.x >> 8) + 0.5f) * (1.0f / 16777216.0f);  // (0, 1), never 0 or 1
+        const float u = uniform_open01(r.x);
         const float score = z - __logf(-__logf(u));
         if (score > best || best_i < 0) { best = score; best_i = i; best_logit = z; }
         if (z > run_max) { run_sum = run_sum * __expf(run_max - z) + 1.0f; run_max = z; }

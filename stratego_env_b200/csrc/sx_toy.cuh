@@ -201,9 +201,12 @@ __device__ __forceinline__ void add_capture(const DevConfig &cfg, State &s, Aux 
     if (hit >= 0) {
         const uint32_t ent = cap_get(s, hit);
         if ((ent >> 13) < 7) cap_set(s, hit, ent + (1u << 13));
+        else a.overflow = 1;  // see add_capture_inl (sx_device.cuh): never silent
     } else if (a.ncap < cfg.cap_stride) {
         cap_set(s, a.ncap, key);
         a.ncap += 1;
+    } else {
+        a.overflow = 1;
     }
 }
 
@@ -344,6 +347,7 @@ __device__ __forceinline__ void reset_game(const DevConfig &cfg, State &s, Aux &
     a.rto[0] = a.rto[1] = NO_CELL;
     a.rcode[0] = a.rcode[1] = 0;
     a.ncap = 0;
+    a.overflow = 0;
     a.episode = episode + 1;
 }
 

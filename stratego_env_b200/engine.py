@@ -264,11 +264,13 @@ class StrategoEngine:
     def step_all(self, state: DeviceState, actions: torch.Tensor, out: dict, one_d: bool = False, env_base: int = 0,
                  auto_reset: bool = False, sample_next: bool = False, allow_piece_oscillation: bool = False,
                  setups: Optional[torch.Tensor] = None, shuffle: bool = False, seed: int = 0,
-                 stats: Optional[torch.Tensor] = None) -> dict:
+                 stats: Optional[torch.Tensor] = None, baseline_kernel: bool = False) -> dict:
+        """baseline_kernel=True runs the general warp-per-game kernel even where a specialised kernel is eligible
+        (identical results; the cross-kernel parity tests use it)."""
         assert actions.dtype == torch.int32 and actions.is_contiguous() and actions.shape == (state.num_envs,)
         flags = ((_lib.SX_AUTO_RESET if auto_reset else 0) | (_lib.SX_SAMPLE_NEXT if sample_next else 0) |
                  (_lib.SX_ALLOW_OSCILLATION if allow_piece_oscillation else 0) |
-                 (_lib.SX_RESET_RANDOM_SHUFFLE if shuffle else 0))
+                 (_lib.SX_RESET_RANDOM_SHUFFLE if shuffle else 0) | (_lib.SX_KERNEL_BASELINE if baseline_kernel else 0))
         if stats is not None:
             assert stats.dtype == torch.int64 and stats.numel() >= 8
         with torch.cuda.device(self.device):

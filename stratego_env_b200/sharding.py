@@ -13,7 +13,7 @@ import torch
 import torch.distributed as dist
 
 STAT_NAMES = ("games_finished", "player_1_wins", "player_2_wins", "invalid_endings", "illegal_actions",
-              "reserved_5", "reserved_6", "reserved_7")
+              "steps", "attacks", "resets")
 
 
 def shard_bounds(global_envs: int, world_size: int, rank: int) -> Tuple[int, int]:

@@ -38,6 +38,13 @@ def custom_toys():
     return load("custom_toys")
 
 
+def spatial_alias():
+    return load("spatial_alias")
+
+
+ALIAS_VERSIONS = ["barrage", "micro", "tiny", "standard2", "octa_barrage"]
+
+
 def unpack_mask(bits, n):
     return np.unpackbits(bits, axis=-1)[..., :n]
 

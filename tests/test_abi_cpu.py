@@ -106,3 +106,17 @@ def test_product_package_never_imports_the_oracle():
                 text = open(os.path.join(dirpath, f)).read()
                 assert not re.search(r"^\s*(from|import)\s+oracle\b", text, flags=re.M), f
                 assert "stratego_oracle" not in text, f
+
+
+def test_policy_uniform_is_strictly_inside_the_unit_interval():
+    """sx_policy.cu uniform_open01: (k + 0.5) / 2^23 for the 23 top bits k of a Philox word, in float32 arithmetic.
+    Both extremes stay strictly inside (0, 1), so the Gumbel score -log(-log(u)) is finite (the previous 24-bit form
+    rounded to exactly 1.0 for the top value)."""
+    import numpy as np
+    for word in (0x00000000, 0x000001FF, 0xFFFFFFFF, 0xFFFFFE00, 0x80000000):
+        k = np.float32(word >> 9)
+        u = (k + np.float32(0.5)) * np.float32(1.0 / 8388608.0)
+        assert u.dtype == np.float32 and np.float32(0.0) < u < np.float32(1.0), (hex(word), u)
+        assert np.isfinite(-np.log(-np.log(u)))
+    old = (np.float32(0xFFFFFFFF >> 8) + np.float32(0.5)) * np.float32(1.0 / 16777216.0)
+    assert old == np.float32(1.0)  # what the fix removes

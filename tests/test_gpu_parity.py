@@ -257,7 +257,7 @@ def test_original_channels_raw_facade_getters():
 
 # ---- toy boards: the thread-per-game kernel (sx_toy_kernel) against the warp-level kernel -------------------------
 @pytest.mark.parametrize("version,full", [("micro", False), ("micro", True), ("tiny", False), ("tiny", True)])
-def test_toy_kernel_equals_warp_level_kernel(version, full, monkeypatch):
+def test_toy_kernel_equals_warp_level_kernel(version, full):
     """Same seeds, same actions: the two implementations of the fused step must agree on every output and on the
     state after every step -- rules, auto-reset (same Philox streams), sampling order, rendering.  167 games = five
     whole groups of 32 for the toy kernel + 7 games that always take the warp-level kernel."""
@@ -267,7 +267,6 @@ def test_toy_kernel_equals_warp_level_kernel(version, full, monkeypatch):
     B, steps = 167, 70
     runs = {}
     for toy_on in ("1", "0"):
-        monkeypatch.setenv("SX_TOY", toy_on)
         eng = StrategoEngine(cfg, device="cuda:0")
         st = eng.alloc_state(B)
         eng.reset(st, seed=5, env_base=1000, shuffle=True)
@@ -277,7 +276,8 @@ def test_toy_kernel_equals_warp_level_kernel(version, full, monkeypatch):
         stats = torch.zeros(8, dtype=torch.int64, device="cuda:0")
         trace = []
         for s in range(steps):
-            eng.step_all(st, actions, out, env_base=1000, auto_reset=True, sample_next=True, shuffle=True, seed=5, stats=stats)
+            eng.step_all(st, actions, out, env_base=1000, auto_reset=True, sample_next=True, shuffle=True, seed=5, stats=stats,
+                         baseline_kernel=toy_on == "0")
             dense, player = eng.export_ref_state(st)
             torch.cuda.synchronize()
             trace.append({k: v.cpu().numpy().copy() for k, v in out.items()} | {"dense": dense.cpu().numpy(),
@@ -334,7 +334,7 @@ CUSTOM_TOYS = {
 
 
 @pytest.mark.parametrize("name", sorted(CUSTOM_TOYS))
-def test_toy_kernel_custom_variants_vs_warp_level_kernel_and_oracle(name, monkeypatch):
+def test_toy_kernel_custom_variants_vs_warp_level_kernel_and_oracle(name):
     from oracle.binding import OracleEnvLogic
     from stratego_env_b200.engine import StrategoEngine
     cfg = CUSTOM_TOYS[name]
@@ -342,7 +342,6 @@ def test_toy_kernel_custom_variants_vs_warp_level_kernel_and_oracle(name, monkey
     B, steps = 96, 60
     runs = {}
     for toy_on in ("1", "0"):
-        monkeypatch.setenv("SX_TOY", toy_on)
         eng = StrategoEngine(cfg, device="cuda:0")
         st = eng.alloc_state(B)
         eng.reset(st, seed=9, shuffle=True)
@@ -353,7 +352,8 @@ def test_toy_kernel_custom_variants_vs_warp_level_kernel_and_oracle(name, monkey
         trace = []
         for s in range(steps):
             dense0, player0 = (x.cpu().numpy() for x in eng.export_ref_state(st))
-            eng.step_all(st, actions, out, auto_reset=True, sample_next=True, shuffle=True, seed=9, stats=stats)
+            eng.step_all(st, actions, out, auto_reset=True, sample_next=True, shuffle=True, seed=9, stats=stats,
+                         baseline_kernel=toy_on == "0")
             dense1, player1 = (x.cpu().numpy() for x in eng.export_ref_state(st))
             rec = {k: v.cpu().numpy().copy() for k, v in out.items()}
             rec.update(dense=dense1, to_move=player1)

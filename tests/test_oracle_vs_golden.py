@@ -5,7 +5,8 @@ import pytest
 from oracle.binding import OracleEnvLogic, OracleProceduralEnv
 from stratego_env_b200.config import VERSION_CONFIGS, as_version
 
-from _golden import VERSIONS, custom_toys, known, original_channels, side_channels, traj, transitions, unpack_mask
+from _golden import (ALIAS_VERSIONS, VERSIONS, custom_toys, known, original_channels, side_channels, spatial_alias, traj,
+                     transitions, unpack_mask)
 
 
 def bits_equal(a, b):
@@ -148,6 +149,43 @@ def test_known_answer_cases(tag):
         assert np.array_equal(d1, unpack_mask(k["ka_%s_next_1d_mask_bits" % tag][i], env.action_size)), name
         assert np.float32(env.get_game_ended(ns, nxt)) == k["ka_%s_next_reward" % tag][i], name
         assert env.get_game_result_is_invalid(ns) == bool(k["ka_%s_next_invalid" % tag][i]), name
+
+
+@pytest.mark.parametrize("version", ALIAS_VERSIONS)
+def test_every_flat_spatial_action_like_the_reference(version):
+    """maenv:685-691 does not bounds-check spatial actions: targets off the board and the noop channel fold into 1D
+    indices that alias other moves (impl:316-347, 264-277).  For EVERY flat index of the recorded states: same 1D
+    index, same accept / reject, same next state as the reference (tests/golden/spatial_alias.npz)."""
+    g, t = spatial_alias(), traj(version)
+    R, C, A = int(t["rows"]), int(t["columns"]), int(t["channels"])
+    logic = OracleEnvLogic(R, C, VERSION_CONFIGS[as_version(version)]["piece_amounts"])
+    env = logic.base_env
+    states, players = t["states"].astype(np.int64), t["players"]
+    pick = g["alias_%s_state_index" % version]
+    accepted = unpack_mask(g["alias_%s_accepted_bits" % version], R * C * A).astype(bool)
+    extra = {(int(j), int(a)): k for k, (j, a) in enumerate(zip(g["alias_%s_extra_state" % version],
+                                                                g["alias_%s_extra_action" % version]))}
+    outside = 0
+    for j, i in enumerate(pick):
+        state, player = states[i], int(players[i])
+        mask = logic.current_obs(state, player, obs_mode=0)[0].reshape(-1)
+        for a in range(R * C * A):
+            r, c, ch = np.unravel_index(a, (R, C, A))
+            one_d = env.get_action_1d_index_from_player_perspective(env.get_action_1d_index_from_spatial_index((r, c, ch)), player)
+            assert one_d == g["alias_%s_one_d" % version][j, a], (version, i, a)
+            try:
+                ns, _ = logic.apply_spatial_action(state, player, a)
+                ok = True
+            except ValueError:
+                ok = False
+            assert ok == accepted[j, a], (version, i, a)
+            # everything in the mask is accepted -- except the lone noop entry of a finished / stuck game, which the
+            # reference's chain decodes to an illegal move (SURVEY.md 8(a) a6 quirk)
+            assert ok or not mask[a] or (a == A - 1 and mask.sum() == 1), (version, i, a)
+            if ok and not mask[a]:
+                assert np.array_equal(ns, g["alias_%s_extra_next" % version][extra[(j, a)]].astype(np.int64)), (version, i, a)
+                outside += 1
+    assert outside == len(extra) and outside > 0
 
 
 @pytest.mark.parametrize("tag", ["3x4", "4x4", "5x5", "6x6", "8x8", "10x10", "15x15"])

@@ -43,7 +43,8 @@ def test_reduce_stats_without_group_is_identity():
     assert torch.equal(sharding.reduce_stats(t.clone()), t)
     assert sharding.max_over_ranks(3.5) == 3.5
     assert sharding.stats_dict(t) == {"games_finished": 0, "player_1_wins": 1, "player_2_wins": 2,
-                                      "invalid_endings": 3, "illegal_actions": 4}
+                                      "invalid_endings": 3, "illegal_actions": 4, "steps": 5, "attacks": 6,
+                                      "resets": 7}
     with pytest.raises(TypeError):
         sharding.reduce_stats(torch.zeros(8, dtype=torch.int32))
 
