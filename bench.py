@@ -296,7 +296,7 @@ def run_gpu_arm(args):
     def step(outputs):
         nonlocal actions
         eng.step_all(st, actions, outputs, env_base=env_base, auto_reset=True, sample_next=True, setups=setups,
-                     shuffle=shuffle, seed=seed, stats=stats)
+                     shuffle=shuffle, seed=seed, stats=stats, baseline_kernel=args.baseline_kernel)
         actions, outputs["next_action"] = outputs["next_action"], actions
 
     # de-phase the games (steady-state mix of early/mid/late positions) without rendering
@@ -375,7 +375,9 @@ def run_gpu_arm(args):
                        "dephase_steps": args.dephase if args.dephase is not None else w["dephase"]},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": recorded_traffic(args.workload, B), "peak_source": peak_src,
-                         "kernel": "sx_toy_kernel" if info.get("thread_per_game") else "sx_fused_kernel",
+                         "kernel": ("sx_fused_kernel (general)" if args.baseline_kernel else
+                                    "sx_toy_kernel" if info.get("thread_per_game") else
+                                    "sx_fused_kernel (ring renderer)" if info.get("ring_slots") else "sx_fused_kernel"),
                          "algorithmic_bytes_per_env_step": bytes_step,
                          "kernel_ms": kernel_ms, "launch": info},
             "e2e": e2e,
@@ -429,6 +431,8 @@ def main():
     ap.add_argument("--ref-seconds", type=float, default=20.0, help="--impl reference: upper bound of one step's sample")
     ap.add_argument("--also", default="micro,standard",
                     help="other workloads summarised in the same line at N=1 (comma list, '' = none)")
+    ap.add_argument("--baseline-kernel", action="store_true",
+                    help="time the general warp-per-game kernel instead of the specialised one (A/B aid)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()

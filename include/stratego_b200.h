@@ -188,6 +188,16 @@ int sx_sample_logits(const void *logits_d, int32_t logits_dtype, const uint8_t *
                      int32_t n_actions, int64_t env_base, uint64_t seed, uint32_t step, float temperature,
                      int32_t *actions_d, float *logprob_d, void *stream);
 
+/* The same draw taken straight from the game STATE instead of a mask: the valid entries of the player to move are
+ * regenerated from the compact state (~0.3 KB per game instead of the 3.7 KB mask row of a 10x10 board), then the
+ * identical Gumbel-max runs over them -- same Philox key per (seed, env_base + b, step, entry), so for the same key it
+ * returns the SAME action as sx_sample_logits on that state's mask.  logits_d is [num_envs][R*C*A] in the mover's
+ * frame (what a policy fed with sx_step_all's observations emits).  A finished game or stuck player yields the noop
+ * entry A-1 with log-probability 0 (impl:514-515). */
+int sx_sample_policy(const sx_config *cfg, sx_state st, int64_t num_envs, int64_t env_base, const void *logits_d,
+                     int32_t logits_dtype, uint64_t seed, uint32_t step, float temperature, int32_t *actions_d,
+                     float *logprob_d, void *stream);
+
 /* impl:854-891 (_get_heuristic_rewards_from_move): rewards_d[b] = reward_matrix[rank of the mover's piece on the
  * start square][rank of the opponent's piece on the end square, 0 = empty] for the action game b is about to play
  * (call it BEFORE the step).  reward_matrix_d is float32 [13][13] on the device; a no-op scores 0.  Like the
@@ -200,6 +210,8 @@ typedef struct {
     int32_t warps_per_block, blocks_per_sm, smem_bytes_per_block, num_sms, grid_blocks, regs_per_thread;
     int32_t background_bytes; /* shared-memory background images of a block (DESIGN.md "Rendering") */
     int32_t thread_per_game;  /* 1: the variant steps through sx_toy_kernel (one thread per game, boards of <= 16 cells) */
+    int32_t ring_slots;       /* > 0: outputs are rendered in a per-warp ring of this many shared-memory chunk slots and
+                                 written by TMA bulk copies only (DESIGN.md "Ring renderer") */
 } sx_launch_info;
 int sx_step_all_launch_info(const sx_config *cfg, uint32_t obs_mask /*1 po, 2 fo, 4 mask*/, sx_launch_info *out);
 

@@ -40,7 +40,8 @@ class SxOutputs(C.Structure):
 
 class SxLaunchInfo(C.Structure):
     _fields_ = [(n, _i32) for n in ("warps_per_block", "blocks_per_sm", "smem_bytes_per_block", "num_sms",
-                                    "grid_blocks", "regs_per_thread", "background_bytes", "thread_per_game")]
+                                    "grid_blocks", "regs_per_thread", "background_bytes", "thread_per_game",
+                                    "ring_slots")]
 
 
 # every symbol include/stratego_b200.h declares: name -> (restype, argtypes)
@@ -60,6 +61,7 @@ SYMBOLS = {
     "sx_step_all": (C.c_int, [_vp, SxState, _i64, _i64, _vp, _i32, _u32, _vp, _i32, _u64, SxOutputs, _vp, _vp]),
     "sx_sample_valid": (C.c_int, [_vp, _i64, _i32, _i64, _u64, _u32, _vp, _vp]),
     "sx_sample_logits": (C.c_int, [_vp, _i32, _vp, _i64, _i32, _i64, _u64, _u32, C.c_float, _vp, _vp, _vp]),
+    "sx_sample_policy": (C.c_int, [_vp, SxState, _i64, _i64, _vp, _i32, _u64, _u32, C.c_float, _vp, _vp, _vp]),
     "sx_heuristic_rewards": (C.c_int, [_vp, SxState, _i64, _vp, _i32, _vp, _vp, _vp]),
     "sx_step_all_launch_info": (C.c_int, [_vp, _u32, C.POINTER(SxLaunchInfo)]),
     "sx_host_env_create": (C.c_int, [_vp, _i64, _i64, _u32, _u32, _vp, _i32, _u64, _i32, C.POINTER(_vp)]),

@@ -131,7 +131,8 @@ class BatchedStrategoEnv:
         """masked-logit sampling for the current observation's mask (one kernel; the policy's logits stay on the
         GPU).  logits: [num_envs, R*C*A] or [num_envs, R, C, A], float32 / bfloat16 / float16."""
         self._policy_step = getattr(self, "_policy_step", 0) + 1
-        return self.engine.sample_logits(logits, self.out["valid_mask"], seed=self.seed, step=self._policy_step,
+        # drawn from the compact state (sx_sample_policy): the mask the step kernel just wrote is not read back
+        return self.engine.sample_policy(self.state, logits, seed=self.seed, step=self._policy_step,
                                          env_base=self.env_base, temperature=temperature,
                                          return_logprob=return_logprob)
 

@@ -788,9 +788,10 @@ __device__ __forceinline__ int align_rows(int channels, int a)
 }
 
 // fills a tile with what an empty board looks like after normalisation
-static __device__ __noinline__ void fill_background(const DevConfig &cfg, float *tile, const ObsMap om, int first, int stride)
+static __device__ __noinline__ void fill_background(const DevConfig &cfg, float *tile, const ObsMap om, int first, int stride,
+                                                    int cells)
 {
-    const int total = (cfg.N + 3) * om.channels;  // + 3 cell rows of alignment slack (see carve_tile)
+    const int total = cells * om.channels;
 #pragma unroll 1
     for (int i = first; i < total; i += stride) {
         const int ch = i % om.channels;

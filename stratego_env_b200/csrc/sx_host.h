@@ -1,0 +1,27 @@
+// sx_host.h -- host-side objects shared by the translation units of the library (not part of the C ABI).
+#pragma once
+
+#include <map>
+#include <mutex>
+#include <string>
+
+#include "../../include/stratego_b200.h"
+#include "sx_device.cuh"
+
+struct LaunchPlan {
+    int warps_per_block, blocks_per_sm, smem_per_block, num_sms, grid, regs;
+    int warp_bytes, tile_bytes;
+};
+
+struct sx_config {
+    sx::DevConfig dev;
+    sx_layout layout;
+    int cells_per_lane;  // K
+    int games_per_warp;  // G
+    // launch shapes already worked out, keyed by (device, ops, mode): the occupancy / attribute queries cost tens
+    // of microseconds, which matters for the one-game API
+    mutable std::mutex plan_mutex;
+    mutable std::map<uint64_t, LaunchPlan> plans;
+};
+
+int sx_set_error(const std::string &msg);  // records the text sx_last_error() returns; always returns -1

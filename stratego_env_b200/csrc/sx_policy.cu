@@ -15,6 +15,7 @@
 
 #include "../../include/stratego_b200.h"
 #include "sx_device.cuh"
+#include "sx_host.h"
 
 namespace sx {
 
@@ -109,9 +110,116 @@ __global__ void __launch_bounds__(256) sx_sample_logits_kernel(const T *logits, 
     }
 }
 
-}  // namespace sx
+// ---- the same draw straight from the game STATE ---------------------------------------------------------------------
+// sx_sample_logits streams the 1-byte mask (3 700 bytes per 10x10 game) to find the ~14-25 valid entries.  The mask is a
+// pure function of the compact state (~0.3 KB per game), so this kernel regenerates the mover's move sets from the state
+// with the engine's own move generator (gen_moves: occupancy bit-lines), lists the valid flat indices in shared memory
+// (balanced over the lanes: an entry costs a Philox block and two transcendentals, a scout would otherwise pile ten of
+// them on one lane) and runs the identical Gumbel-max / log-sum-exp per entry.  Same Philox key per (game, step, entry)
+// and the same tie rule as the mask kernel, so both return the SAME action for the same key.
+template <typename T, int K>
+__global__ void __launch_bounds__(256) sx_sample_policy_kernel(const __grid_constant__ DevConfig cfg, const uint8_t *board,
+                                                               const int16_t *aux, long long num_envs, long long env_base,
+                                                               const T *logits, uint2 key, uint32_t step, float inv_temperature,
+                                                               int32_t *actions, float *logprob, int warp_bytes, int list_cap)
+{
+    using GT = Grp<1>;
+    extern __shared__ __align__(16) uint8_t smem[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const long long env = (long long)blockIdx.x * (blockDim.x >> 5) + warp;
+    if (env >= num_envs) return;
+    uint8_t *warp_base = smem + size_t(warp) * warp_bytes;
+    WarpMem m;
+    const int slice = carve_warp(cfg, warp_base, &m);
+    uint16_t *list = reinterpret_cast<uint16_t *>(warp_base + slice);
 
-extern int sx_set_error(const std::string &msg);
+    const uint32_t *gb = reinterpret_cast<const uint32_t *>(board + env * cfg.board_stride);
+    for (int i = lane; i < (cfg.board_stride >> 2); i += 32) reinterpret_cast<uint32_t *>(m.board)[i] = gb[i];
+    const uint4 aw = *reinterpret_cast<const uint4 *>(aux + env * 8);
+    Aux a;
+    {
+        const uint32_t w[4] = {aw.x, aw.y, aw.z, aw.w};
+        aux_unpack(w, a);
+    }
+    __syncwarp();
+    const bool any = gen_moves<K, GT>(cfg, m, a, a.to_move, false);  // the mover's frame, like the mask (maenv:452-454)
+    if (!any) {  // finished game or stuck player: the mask holds the noop entry [0,0,A-1] only (impl:514-515)
+        if (lane == 0) {
+            actions[env] = cfg.A - 1;
+            if (logprob) logprob[env] = 0.0f;
+        }
+        return;
+    }
+    // list the valid flat indices, ascending, at this lane's offset
+    int mine = 0;
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+        const int p = lane * K + k;
+        if (p < cfg.N) mine += __popc(m.moves[p].x) + __popc(m.moves[p].y);
+    }
+    int incl = mine;
+#pragma unroll
+    for (int off = 1; off < 32; off <<= 1) {
+        const int v = __shfl_up_sync(FULL, incl, off);
+        if (lane >= off) incl += v;
+    }
+    const int total = __shfl_sync(FULL, incl, 31);
+    int pos = incl - mine;
+#pragma unroll 1
+    for (int k = 0; k < K; ++k) {
+        const int p = lane * K + k;
+        if (p >= cfg.N) break;
+        unsigned long long bits = (unsigned long long)m.moves[p].x | ((unsigned long long)m.moves[p].y << 32);
+#pragma unroll 1
+        for (; bits != 0; bits &= bits - 1, ++pos)
+            if (pos < list_cap) list[pos] = uint16_t(p * cfg.A + __ffsll((long long)bits) - 1);
+    }
+    __syncwarp();
+
+    const T *lrow = logits + env * (long long)(cfg.N * cfg.A);
+    const uint64_t gid = uint64_t(env_base + env);
+    float best = -INFINITY, best_logit = 0.0f, run_max = -INFINITY, run_sum = 0.0f;
+    int best_i = -1;
+    auto visit = [&](int i) {
+        const float z = load_logit<T>(lrow + i) * inv_temperature;
+        const uint4 r = philox4x32_10(make_uint4(uint32_t(gid), uint32_t(gid >> 32), RNG_POLICY ^ step, uint32_t(i)), key);
+        const float score = z - __logf(-__logf(uniform_open01(r.x)));
+        if (score > best || best_i < 0 || (score == best && i < best_i)) { best = score; best_i = i; best_logit = z; }
+        if (z > run_max) { run_sum = run_sum * __expf(run_max - z) + 1.0f; run_max = z; }
+        else run_sum += __expf(z - run_max);
+    };
+    const int listed = min(total, list_cap);
+    for (int t = lane; t < listed; t += 32) visit(list[t]);
+    if (total > list_cap) {  // more moves than the list holds (never on stock boards): the owning lanes visit the rest
+        pos = incl - mine;
+#pragma unroll 1
+        for (int k = 0; k < K; ++k) {
+            const int p = lane * K + k;
+            if (p >= cfg.N) break;
+            unsigned long long bits = (unsigned long long)m.moves[p].x | ((unsigned long long)m.moves[p].y << 32);
+#pragma unroll 1
+            for (; bits != 0; bits &= bits - 1, ++pos)
+                if (pos >= list_cap) visit(p * cfg.A + __ffsll((long long)bits) - 1);
+        }
+    }
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+        const float ob = __shfl_xor_sync(FULL, best, off), ol = __shfl_xor_sync(FULL, best_logit, off);
+        const int oi = __shfl_xor_sync(FULL, best_i, off);
+        const bool take = oi >= 0 && (best_i < 0 || ob > best || (ob == best && oi < best_i));
+        if (take) { best = ob; best_i = oi; best_logit = ol; }
+        const float om = __shfl_xor_sync(FULL, run_max, off), os = __shfl_xor_sync(FULL, run_sum, off);
+        const float nm = fmaxf(run_max, om);
+        if (nm > -INFINITY) run_sum = run_sum * __expf(run_max - nm) + os * __expf(om - nm);
+        run_max = nm;
+    }
+    if (lane == 0) {
+        actions[env] = best_i;
+        if (logprob) logprob[env] = best_logit - (run_max + __logf(run_sum));
+    }
+}
+
+}  // namespace sx
 
 extern "C" int sx_sample_logits(const void *logits_d, int32_t logits_dtype, const uint8_t *mask_d, int64_t num_envs,
                                 int32_t n_actions, int64_t env_base, uint64_t seed, uint32_t step, float temperature,
@@ -146,4 +254,54 @@ extern "C" int sx_sample_logits(const void *logits_d, int32_t logits_dtype, cons
     }
     const cudaError_t e = cudaGetLastError();
     return e == cudaSuccess ? 0 : sx_set_error(std::string("sx_sample_logits_kernel: ") + cudaGetErrorString(e));
+}
+
+template <typename T>
+static cudaError_t launch_policy(const sx_config *cfg, sx_state st, int64_t num_envs, int64_t env_base, const T *logits, uint2 key,
+                                 uint32_t step, float inv_t, int32_t *actions, float *logprob, cudaStream_t s)
+{
+    using namespace sx;
+    const DevConfig &d = cfg->dev;
+    const int wpb = 8, list_cap = 4 * d.N;
+    const int warp_bytes = carve_warp(d, nullptr, nullptr) + round16(list_cap * 2);
+    const unsigned grid = unsigned((num_envs + wpb - 1) / wpb);
+    const size_t smem = size_t(wpb) * warp_bytes;
+    if (d.N <= 64)
+        sx_sample_policy_kernel<T, 2><<<grid, wpb * 32, smem, s>>>(d, st.board, st.aux, num_envs, env_base, logits, key, step, inv_t,
+                                                                   actions, logprob, warp_bytes, list_cap);
+    else if (d.N <= 128)
+        sx_sample_policy_kernel<T, 4><<<grid, wpb * 32, smem, s>>>(d, st.board, st.aux, num_envs, env_base, logits, key, step, inv_t,
+                                                                   actions, logprob, warp_bytes, list_cap);
+    else
+        sx_sample_policy_kernel<T, 8><<<grid, wpb * 32, smem, s>>>(d, st.board, st.aux, num_envs, env_base, logits, key, step, inv_t,
+                                                                   actions, logprob, warp_bytes, list_cap);
+    return cudaGetLastError();
+}
+
+extern "C" int sx_sample_policy(const sx_config *cfg, sx_state st, int64_t num_envs, int64_t env_base, const void *logits_d,
+                                int32_t logits_dtype, uint64_t seed, uint32_t step, float temperature, int32_t *actions_d,
+                                float *logprob_d, void *stream)
+{
+    if (!cfg || !st.board || !st.aux || !logits_d || !actions_d) return sx_set_error("sx_sample_policy: null argument");
+    if (!(temperature > 0.0f)) return sx_set_error("sx_sample_policy: temperature must be > 0");
+    if (num_envs <= 0) return 0;
+    const uint2 key = make_uint2(uint32_t(seed), uint32_t(seed >> 32));
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    const float inv_t = 1.0f / temperature;
+    cudaError_t e;
+    switch (logits_dtype) {
+    case SX_DTYPE_F32:
+        e = launch_policy(cfg, st, num_envs, env_base, static_cast<const float *>(logits_d), key, step, inv_t, actions_d, logprob_d, s);
+        break;
+    case SX_DTYPE_BF16:
+        e = launch_policy(cfg, st, num_envs, env_base, static_cast<const __nv_bfloat16 *>(logits_d), key, step, inv_t, actions_d,
+                          logprob_d, s);
+        break;
+    case SX_DTYPE_F16:
+        e = launch_policy(cfg, st, num_envs, env_base, static_cast<const __half *>(logits_d), key, step, inv_t, actions_d, logprob_d, s);
+        break;
+    default:
+        return sx_set_error("sx_sample_policy: unknown logits dtype");
+    }
+    return e == cudaSuccess ? 0 : sx_set_error(std::string("sx_sample_policy_kernel: ") + cudaGetErrorString(e));
 }

@@ -20,7 +20,11 @@
 namespace sx {
 namespace ring {
 
-constexpr int CHUNK_CELLS = 20;  // cells per chunk: a multiple of 4 (16-byte granularity of bulk copies), at most 32 (one cell per lane)
+#ifndef SX_CHUNK_CELLS
+#define SX_CHUNK_CELLS 20
+#endif
+constexpr int CHUNK_CELLS = SX_CHUNK_CELLS;  // cells per chunk: a multiple of 4 (16-byte granularity of bulk copies), at most 32 (one cell per lane)
+static_assert(CHUNK_CELLS % 4 == 0 && CHUNK_CELLS >= 4 && CHUNK_CELLS <= 32, "chunk = 4..32 cells in multiples of 4");
 
 __host__ __device__ inline int chunk_bytes(int channels) { return CHUNK_CELLS * channels * 4; }
 

@@ -311,6 +311,23 @@ class StrategoEngine:
                        "sx_sample_logits")
         return (actions, logprob) if return_logprob else actions
 
+    def sample_policy(self, state: DeviceState, logits: torch.Tensor, seed: int = 0, step: int = 0, env_base: int = 0,
+                      temperature: float = 1.0, return_logprob: bool = False):
+        """The draw of ``sample_logits`` taken from the game state instead of a mask (sx_sample_policy): the valid
+        entries of the player to move are regenerated from the ~0.3 KB compact state, so the 3.7 KB mask row is never
+        re-read.  Same Philox key => same action as ``sample_logits`` on that state's mask."""
+        B = state.num_envs
+        flat_logits = logits.reshape(B, -1)
+        assert flat_logits.is_contiguous() and flat_logits.shape[1] == self.layout.spatial_actions, flat_logits.shape
+        dtype = {torch.float32: 0, torch.bfloat16: 1, torch.float16: 2}[flat_logits.dtype]
+        actions = torch.empty(B, dtype=torch.int32, device=self.device)
+        logprob = torch.empty(B, dtype=torch.float32, device=self.device) if return_logprob else None
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.sx_sample_policy(self._cfg, state.as_struct(), B, env_base, flat_logits.data_ptr(), dtype,
+                                                 seed & (2 ** 64 - 1), step & 0xffffffff, float(temperature),
+                                                 actions.data_ptr(), _ptr(logprob), _stream()), "sx_sample_policy")
+        return (actions, logprob) if return_logprob else actions
+
     def heuristic_rewards(self, state: DeviceState, actions: torch.Tensor, reward_matrix: torch.Tensor,
                           one_d: bool = False) -> torch.Tensor:
         """impl:854-891 batched: reward_matrix[mover's rank at start, opponent's rank at end] of the action each game

@@ -94,3 +94,45 @@ def test_policy_rollout_through_batched_env():
             actions = env.sample_actions_from_logits(logits)
             obs, rewards, dones, infos = env.step(actions)
             assert not infos["illegal_action"].any().item()
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("version,table", [("barrage", "barrage"), ("standard", "standard"), ("micro", None),
+                                           ("octa_barrage", None), ("standard2", None)])
+def test_state_based_sampler_draws_the_same_action_as_the_mask_based_one(version, table, dtype):
+    """sx_sample_policy regenerates the valid entries from the compact game state instead of streaming the mask;
+    for the same Philox key (seed, env id, step) it must return exactly the action sx_sample_logits returns on that
+    state's mask -- mid-game, freshly re-set and finished games alike -- and the same log-probability (2e-5; the
+    log-sum-exp is accumulated in a different order)."""
+    from stratego_env_b200.config import VERSION_CONFIGS, as_version
+    from stratego_env_b200.engine import StrategoEngine, load_setup_table
+    eng = StrategoEngine(VERSION_CONFIGS[as_version(version)], device="cuda:0", p2_rot180=table is None)
+    setups = eng.upload_setups(load_setup_table(table)) if table else None
+    B = 3000
+    R, C, A = eng.spatial_action_size
+    st = eng.alloc_state(B)
+    eng.reset(st, seed=21, env_base=77, setups=setups, shuffle=setups is None)
+    out = eng.alloc_outputs(B, partial=False, full=False, mask=True, sample=True)
+    eng.observe(st, out=out, partial=False, full=False, mask=True)
+    actions = eng.sample_valid(out["valid_mask"], seed=21, step=0, env_base=77)
+    g = torch.Generator(device="cuda").manual_seed(5)
+    finished = 0
+    for s in range(40):
+        # no auto-reset: finished games stay finished (noop-only mask) and must sample the noop entry
+        eng.step_all(st, actions, out, env_base=77, auto_reset=False, sample_next=True, seed=21)
+        logits = (torch.randn(B, R * C * A, generator=g, device="cuda") * 2).to(dtype)
+        a_mask, lp_mask = eng.sample_logits(logits, out["valid_mask"], seed=9, step=s, env_base=77, temperature=0.8,
+                                            return_logprob=True)
+        a_state, lp_state = eng.sample_policy(st, logits, seed=9, step=s, env_base=77, temperature=0.8,
+                                              return_logprob=True)
+        assert torch.equal(a_mask, a_state), (version, s)
+        assert torch.allclose(lp_mask, lp_state, atol=2e-5, rtol=0), float((lp_mask - lp_state).abs().max())
+        over = out["valid_mask"].reshape(B, -1).sum(1) == 1
+        over &= out["valid_mask"].reshape(B, -1)[:, A - 1] == 1
+        assert (a_state[over] == A - 1).all()
+        finished = int(over.sum())
+        # keep playing the games that are still running with the sampled actions; finished ones get the noop entry,
+        # which the step rejects (illegal, state untouched) exactly like the reference
+        actions = a_state.clone()
+    if version in ("micro", "octa_barrage"):
+        assert finished > 0
