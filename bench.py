@@ -376,8 +376,7 @@ def run_gpu_arm(args):
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": recorded_traffic(args.workload, B), "peak_source": peak_src,
                          "kernel": ("sx_fused_kernel (general)" if args.baseline_kernel else
-                                    "sx_toy_kernel" if info.get("thread_per_game") else
-                                    "sx_fused_kernel (ring renderer)" if info.get("ring_slots") else "sx_fused_kernel"),
+                                    "sx_toy_kernel" if info.get("thread_per_game") else "sx_fused_kernel"),
                          "algorithmic_bytes_per_env_step": bytes_step,
                          "kernel_ms": kernel_ms, "launch": info},
             "e2e": e2e,

@@ -118,8 +118,8 @@ enum {
     SX_ALLOW_OSCILLATION = 4,   /* allow_piece_oscillation=True (impl:771-777) */
     SX_RESET_RANDOM_SHUFFLE = 8, /* (re)sets draw setups by shuffling the pieces (util:13-30) instead of a table */
     SX_KERNEL_BASELINE = 16     /* run the general warp-per-game kernel even where a specialised one is eligible (the
-                                   thread-per-game kernel of the <= 16-cell boards, the ring-rendered 10x10 kernel).
-                                   Results are identical by contract; the cross-kernel parity tests use it */
+                                   thread-per-game kernel of the <= 16-cell boards).  Results are identical by
+                                   contract; the cross-kernel parity tests use it */
 };
 
 const char *sx_last_error(void);
@@ -210,8 +210,6 @@ typedef struct {
     int32_t warps_per_block, blocks_per_sm, smem_bytes_per_block, num_sms, grid_blocks, regs_per_thread;
     int32_t background_bytes; /* shared-memory background images of a block (DESIGN.md "Rendering") */
     int32_t thread_per_game;  /* 1: the variant steps through sx_toy_kernel (one thread per game, boards of <= 16 cells) */
-    int32_t ring_slots;       /* > 0: outputs are rendered in a per-warp ring of this many shared-memory chunk slots and
-                                 written by TMA bulk copies only (DESIGN.md "Ring renderer") */
 } sx_launch_info;
 int sx_step_all_launch_info(const sx_config *cfg, uint32_t obs_mask /*1 po, 2 fo, 4 mask*/, sx_launch_info *out);
 

@@ -40,8 +40,7 @@ class SxOutputs(C.Structure):
 
 class SxLaunchInfo(C.Structure):
     _fields_ = [(n, _i32) for n in ("warps_per_block", "blocks_per_sm", "smem_bytes_per_block", "num_sms",
-                                    "grid_blocks", "regs_per_thread", "background_bytes", "thread_per_game",
-                                    "ring_slots")]
+                                    "grid_blocks", "regs_per_thread", "background_bytes", "thread_per_game")]
 
 
 # every symbol include/stratego_b200.h declares: name -> (restype, argtypes)

@@ -21,7 +21,6 @@
 #include "../../include/stratego_b200.h"
 #include "sx_device.cuh"
 #include "sx_host.h"
-#include "sx_ring.cuh"
 #include "sx_toy.cuh"
 
 namespace sx {
@@ -161,14 +160,10 @@ constexpr int MAX_REDRAWS = 8;  // re-draws of an unplayable setup (first player
 #define SX_EXP(flags, bit) false
 #endif
 // K = board cells per lane, G = games per warp (Grp<G>): 10x10 -> K 4, G 1; 3x4 / 4x4 -> K 2, G 4.
-// RING = 0: outputs as "background by TMA + sparse stores to global memory" (any board, any launch type);
-// RING = 2, 3: outputs rendered in a per-warp ring of RING shared-memory chunk slots and written ONLY by the TMA
-// engine (sx_ring.cuh) -- boards whose cell count is a multiple of 4, one game per warp, extended channels.
-template <int K, int MODE, int G, int RING = 0>
+template <int K, int MODE, int G>
 __global__ void __launch_bounds__(K <= 2 ? 1024 : SX_MAX_THREADS, 1) sx_fused_kernel(const __grid_constant__ KernelArgs args)
 {
     using GT = Grp<G>;
-    static_assert(RING == 0 || G == 1, "the ring renderer serves one game per warp");
     extern __shared__ __align__(16) uint8_t smem[];
     const DevConfig &cfg = args.cfg;
     // `lane` is the lane within this game's group and `warp` the game slot within the block
@@ -193,30 +188,16 @@ __global__ void __launch_bounds__(K <= 2 ? 1024 : SX_MAX_THREADS, 1) sx_fused_ke
 
     // the block's read-only background images
     Tile bg;
-    if (RING) {  // CHUNK_CELLS cells of each observation (the background is periodic in the cell); no mask image
-        bg.po = reinterpret_cast<float *>(smem);
-        bg.fo = reinterpret_cast<float *>(smem + (do_po ? ring::chunk_bytes(cfg.po_ch) : 0));
-        bg.mask = nullptr;
-        if (do_po) fill_background(cfg, bg.po, pom, threadIdx.x, blockDim.x, ring::CHUNK_CELLS);
-        if (do_fo) fill_background(cfg, bg.fo, fom, threadIdx.x, blockDim.x, ring::CHUNK_CELLS);
-    } else {
-        carve_tile(cfg, ops, smem, &bg);
-        if (do_tile) {
-            if (do_po) fill_background(cfg, bg.po, pom, threadIdx.x, blockDim.x, cfg.N + 3);  // + 3 rows: see carve_tile
-            if (do_fo) fill_background(cfg, bg.fo, fom, threadIdx.x, blockDim.x, cfg.N + 3);
-            if (do_mask)
-                for (int i = threadIdx.x; i < (mask_tile_bytes >> 4); i += blockDim.x)
-                    reinterpret_cast<uint4 *>(bg.mask)[i] = make_uint4(0, 0, 0, 0);
-            fence_async_smem();  // generic-proxy writes above -> visible to the TMA engine (async proxy)
-        }
+    carve_tile(cfg, ops, smem, &bg);
+    if (do_tile) {
+        if (do_po) fill_background(cfg, bg.po, pom, threadIdx.x, blockDim.x, cfg.N + 3);  // + 3 rows: see carve_tile
+        if (do_fo) fill_background(cfg, bg.fo, fom, threadIdx.x, blockDim.x, cfg.N + 3);
+        if (do_mask)
+            for (int i = threadIdx.x; i < (mask_tile_bytes >> 4); i += blockDim.x)
+                reinterpret_cast<uint4 *>(bg.mask)[i] = make_uint4(0, 0, 0, 0);
+        fence_async_smem();  // generic-proxy writes above -> visible to the TMA engine (async proxy)
     }
     __syncthreads();
-    // this warp's ring: [mask slot][RING chunk slots], behind its working slice
-    uint8_t *const ring_mask = warp_base + carve_warp(cfg, nullptr, nullptr);
-    uint8_t *const ring_slots = ring_mask + ring::mask_slot_bytes(cfg, do_mask);
-    const int ring_slot_bytes = ring::slot_bytes(cfg, do_po, do_fo);
-    int ring_next = 0;  // slot the next chunk goes to
-
     const bool hints = !SX_EXP(flags, 0x40000u);
     const uint64_t pol_keep = l2_policy(hints ? 1 : 0), pol_stream = l2_policy(hints ? 2 : 0);
 
@@ -294,8 +275,8 @@ __global__ void __launch_bounds__(K <= 2 ? 1024 : SX_MAX_THREADS, 1) sx_fused_ke
         const long long next_env = env + total_warps;
         const bool has_next = next_env < args.num_envs;
         if (has_next) load_state(next_env, pf);
-        if (!RING && do_tile && issue_at == 2) issue_background(env);
-        if (!RING && SX_EXP(flags, 0x800000u)) {  // experiment: output skeleton only (no rules): background copy + wait
+        if (do_tile && issue_at == 2) issue_background(env);
+        if (SX_EXP(flags, 0x800000u)) {  // experiment: output skeleton only (no rules): background copy + wait
             if (do_tile && issue_at != 2) issue_background(env);
             if (lane == 0) bulk_wait_all();
             GT::sync();
@@ -383,7 +364,7 @@ __global__ void __launch_bounds__(K <= 2 ? 1024 : SX_MAX_THREADS, 1) sx_fused_ke
             }
         }
         if (args.out.player && lane == 0) args.out.player[env] = viewer == 0 ? 1 : -1;
-        if (!RING && do_tile && issue_at == 1) issue_background(env);
+        if (do_tile && issue_at == 1) issue_background(env);
 
         if ((ops & OP_MASK_1D) != 0) {
             uint8_t *row = args.mask1d + env * cfg.action_size;
@@ -411,51 +392,9 @@ __global__ void __launch_bounds__(K <= 2 ? 1024 : SX_MAX_THREADS, 1) sx_fused_ke
             if (lane == 0) args.out.next_action[env] = act;
         }
 
-        // ---- render through the warp's ring of shared-memory chunks (sx_ring.cuh) -------------------------
-        if (RING && do_tile) {
-            constexpr int SLOTS = RING ? RING : 1;
-            uint8_t *gmask = do_mask ? args.out.valid_mask + env * cfg.mask_bytes : nullptr;
-            uint8_t *mask_row = ring_mask + (reinterpret_cast<uintptr_t>(gmask) & 15);  // source congruent to the destination mod 16
-            if (lane == 0) ring::wait_slot_free<SLOTS>();  // also frees the mask slot: its copy left >= 5 groups ago
-            __syncwarp();
-            if (do_mask) {
-                for (int i = lane; i < (ring::mask_slot_bytes(cfg, true) >> 4); i += 32)
-                    reinterpret_cast<uint4 *>(ring_mask)[i] = make_uint4(0, 0, 0, 0);
-                __syncwarp();
-                mark_spatial<K, GT>(cfg, m, mask_row, pol_stream);
-                if (!any && lane == 0) mask_row[cfg.A - 1] = 1;  // [0,0,A-1], impl:514-515
-            }
-            float *po_dst = do_po ? args.out.partial_obs + env * cfg.po_floats : nullptr;
-            float *fo_dst = do_fo ? args.out.full_obs + env * cfg.fo_floats : nullptr;
-            const int po_slot = do_po ? ring::chunk_bytes(cfg.po_ch) : 0;
-#pragma unroll 1
-            for (int c0 = 0; c0 < cfg.N; c0 += ring::CHUNK_CELLS) {
-                const int n = min(ring::CHUNK_CELLS, cfg.N - c0);
-                if (c0 > 0) {
-                    if (lane == 0) ring::wait_slot_free<SLOTS>();
-                    __syncwarp();
-                }
-                uint8_t *slot = ring_slots + ring_next * ring_slot_bytes;
-                ring_next = ring_next + 1 == SLOTS ? 0 : ring_next + 1;
-                if (do_po) ring::copy16(slot, reinterpret_cast<const uint8_t *>(bg.po), n * cfg.po_ch * 4, lane);
-                if (do_fo) ring::copy16(slot + po_slot, reinterpret_cast<const uint8_t *>(bg.fo), n * cfg.fo_ch * 4, lane);
-                __syncwarp();
-                if (do_po) ring::patch_chunk(cfg, m, a, reinterpret_cast<float *>(slot), pom, viewer, c0, n);
-                if (do_fo) ring::patch_chunk(cfg, m, a, reinterpret_cast<float *>(slot + po_slot), fom, viewer, c0, n);
-                fence_async_smem();  // generic-proxy stores (this chunk, and the mask row before the first one) -> async proxy
-                __syncwarp();
-                if (c0 == 0 && do_mask) emit_tile<GT>(gmask, mask_row, cfg.mask_bytes, pol_stream);
-                if (lane == 0) {
-                    if (do_po) bulk_store(po_dst + c0 * cfg.po_ch, slot, uint32_t(n * cfg.po_ch * 4), pol_stream);
-                    if (do_fo) bulk_store(fo_dst + c0 * cfg.fo_ch, slot + po_slot, uint32_t(n * cfg.fo_ch * 4), pol_stream);
-                    bulk_commit();
-                }
-            }
-        }
-
         // ---- render: sparse entries on top of the (by now written) background ---------------------------
-        if (!RING && do_tile && issue_at == 0) issue_background(env);
-        if (!RING && do_tile && !SX_EXP(flags, 0x20000u)) {
+        if (do_tile && issue_at == 0) issue_background(env);
+        if (do_tile && !SX_EXP(flags, 0x20000u)) {
             if (lane == 0) bulk_wait_all();  // this game's background is in global memory
             GT::sync();
             if (SX_EXP(flags, 0x80000u)) continue;  // experiment: wait but skip the sparse stores
@@ -475,7 +414,6 @@ __global__ void __launch_bounds__(K <= 2 ? 1024 : SX_MAX_THREADS, 1) sx_fused_ke
         GT::sync();
     }
 
-    if (RING && do_tile && lane == 0) bulk_wait_read();  // shared memory must outlive the copies that read it
     if (args.stats && lane == 0) cnt.publish(args.stats);  // all lanes of a game carry identical counters
 }
 
@@ -995,14 +933,6 @@ extern "C" int sx_config_layout(const sx_config *cfg, sx_layout *out)
 }
 
 typedef void (*fused_fn)(const KernelArgs);
-// ring-rendered instantiations (sx_ring.cuh): the two hot step modes of one-game-per-warp boards, 2 or 3 chunk slots
-template <int K>
-static fused_fn ring_for_mode(int mode, int slots)
-{
-    if (mode == MODE_STEP_PO_FO_MASK)
-        return slots == 3 ? sx_fused_kernel<K, MODE_STEP_PO_FO_MASK, 1, 3> : sx_fused_kernel<K, MODE_STEP_PO_FO_MASK, 1, 2>;
-    return slots == 3 ? sx_fused_kernel<K, MODE_STEP_PO_MASK, 1, 3> : sx_fused_kernel<K, MODE_STEP_PO_MASK, 1, 2>;
-}
 template <int K, int G>
 static fused_fn fused_for_mode(int mode)
 {
@@ -1017,10 +947,9 @@ static fused_fn fused_for_mode(int mode)
 }
 // (cells per lane, games per warp) instantiations: (2,4) boards up to 4x4, (2,2) up to 5x5 (both dimensions must fit
 // in half a group's lanes), (2,1) up to 64 cells, (4,1) 10x10, (8,1) 15x15
-static fused_fn fused_for(const sx_config *cfg, int mode, int ring_slots = 0)
+static fused_fn fused_for(const sx_config *cfg, int mode)
 {
     const int k = cfg->cells_per_lane, g = cfg->games_per_warp;
-    if (ring_slots) return k == 2 ? ring_for_mode<2>(mode, ring_slots) : ring_for_mode<4>(mode, ring_slots);
     if (g == 4) return fused_for_mode<2, 4>(mode);
     if (g == 2) return fused_for_mode<2, 2>(mode);
     switch (k) {
@@ -1045,39 +974,22 @@ static int mode_for(const sx_config *cfg, const KernelArgs &a)
 
 
 
-// Ring renderer (sx_ring.cuh): chunk slots per warp for this launch, 0 = not eligible.  Eligible: the two hot step
-// modes, one game per warp, a cell count that is a multiple of 4 (16-byte bulk copies) with at least three chunks per
-// game (a slot -- and the mask slot -- must not come up for reuse within one game's own groups), extended channels,
-// 16-byte aligned observation tensors.
-static int ring_slots_for(const sx_config *cfg, const KernelArgs &a, int mode)
-{
-    const DevConfig &d = cfg->dev;
-    if (a.flags & SX_KERNEL_BASELINE) return 0;
-    if (mode != MODE_STEP_PO_MASK && mode != MODE_STEP_PO_FO_MASK) return 0;
-    if (cfg->games_per_warp != 1 || cfg->cells_per_lane > 4 || (d.N & 3) != 0 || d.N < 3 * ring::CHUNK_CELLS) return 0;
-    if (d.original_channels) return 0;
-    const uintptr_t bits = reinterpret_cast<uintptr_t>(a.out.partial_obs) | reinterpret_cast<uintptr_t>(a.out.full_obs);
-    if (bits & 15) return 0;
-    // one observation: 3 slots (16 KB of chunks per warp, 10 warps per SM); both: 2 slots of 11.7 KB
-    return std::max(2, std::min(3, env_int("SX_RING_SLOTS", mode == MODE_STEP_PO_MASK ? 3 : 2)));
-}
-
 // Block shape: one block per SM with as many warps as the register file allows (SX_WARPS overrides; a
 // tuning aid); the block's shared memory is the background images plus one small slice per warp.
-static int plan_launch_uncached(const sx_config *cfg, uint32_t ops, int mode, int ring_slots, long long num_envs, LaunchPlan *plan);
+static int plan_launch_uncached(const sx_config *cfg, uint32_t ops, int mode, long long num_envs, LaunchPlan *plan);
 
-static int plan_launch(const sx_config *cfg, uint32_t ops, int mode, int ring_slots, long long num_envs, LaunchPlan *plan)
+static int plan_launch(const sx_config *cfg, uint32_t ops, int mode, long long num_envs, LaunchPlan *plan)
 {
     int device = 0;
     cudaError_t e = cudaGetDevice(&device);
     if (e != cudaSuccess) return cuda_fail("cudaGetDevice", e);
-    const uint64_t key = (uint64_t(uint32_t(device)) << 40) | (uint64_t(ring_slots) << 36) | (uint64_t(ops) << 8) | uint64_t(mode);
+    const uint64_t key = (uint64_t(uint32_t(device)) << 40) | (uint64_t(ops) << 8) | uint64_t(mode);
     {
         std::lock_guard<std::mutex> lock(cfg->plan_mutex);
         auto it = cfg->plans.find(key);
         if (it == cfg->plans.end()) {
             LaunchPlan full;
-            if (int rc = plan_launch_uncached(cfg, ops, mode, ring_slots, 1LL << 40, &full)) return rc;
+            if (int rc = plan_launch_uncached(cfg, ops, mode, 1LL << 40, &full)) return rc;
             it = cfg->plans.emplace(key, full).first;
         }
         *plan = it->second;
@@ -1088,13 +1000,11 @@ static int plan_launch(const sx_config *cfg, uint32_t ops, int mode, int ring_sl
     return 0;
 }
 
-static int plan_launch_uncached(const sx_config *cfg, uint32_t ops, int mode, int ring_slots, long long num_envs, LaunchPlan *plan)
+static int plan_launch_uncached(const sx_config *cfg, uint32_t ops, int mode, long long num_envs, LaunchPlan *plan)
 {
-    const bool po = ops & OP_PO, fo = ops & OP_FO, mask = ops & OP_MASK;
-    const int warp_bytes = carve_warp(cfg->dev, nullptr, nullptr) +
-                           (ring_slots ? ring::warp_ring_bytes(cfg->dev, po, fo, mask, ring_slots) : 0);
-    const int tile_bytes = ring_slots ? ring::background_bytes(cfg->dev, po, fo) : carve_tile(cfg->dev, ops, nullptr, nullptr);
-    fused_fn fn = fused_for(cfg, mode, ring_slots);
+    const int warp_bytes = carve_warp(cfg->dev, nullptr, nullptr);
+    const int tile_bytes = carve_tile(cfg->dev, ops, nullptr, nullptr);
+    fused_fn fn = fused_for(cfg, mode);
     int device = 0;
     cudaError_t e = cudaGetDevice(&device);
     if (e != cudaSuccess) return cuda_fail("cudaGetDevice", e);
@@ -1118,8 +1028,6 @@ static int plan_launch_uncached(const sx_config *cfg, uint32_t ops, int mode, in
     const int preferred = tile_bytes <= 8 * 1024 ? 32 : tile_bytes <= 32 * 1024 ? (cfg->dev.N >= 100 ? 8 : small_board)
                           : tile_bytes <= 64 * 1024 ? 6 : 4;
     int warps = std::min(max_warps, std::max(1, env_int("SX_WARPS", std::min(max_warps, preferred))));
-    // ring renderer: nothing waits for L2, so residency is limited by shared memory only (the loop below trims)
-    if (ring_slots) warps = std::min(max_warps, std::max(1, env_int("SX_RING_WARPS", 16)));
     const int games = cfg->games_per_warp;  // each game of a warp has its own slice
     while (warps > 1 && tile_bytes + warps * games * warp_bytes > max_smem_optin) --warps;
     const int smem = tile_bytes + warps * games * warp_bytes;
@@ -1128,7 +1036,7 @@ static int plan_launch_uncached(const sx_config *cfg, uint32_t ops, int mode, in
     e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks, fn, warps * 32, size_t(smem));
     if (e != cudaSuccess) return cuda_fail("cudaOccupancyMaxActiveBlocksPerMultiprocessor", e);
     if (blocks < 1) return fail("fused kernel cannot be resident on this device");
-    blocks = std::max(1, std::min(blocks, env_int("SX_BLOCKS", (ring_slots || tile_bytes > 8 * 1024) ? 1 : blocks)));
+    blocks = std::max(1, std::min(blocks, env_int("SX_BLOCKS", tile_bytes > 8 * 1024 ? 1 : blocks)));
     plan->warps_per_block = warps;
     plan->blocks_per_sm = blocks;
     plan->smem_per_block = smem;
@@ -1252,8 +1160,7 @@ static int launch_fused(const sx_config *cfg, KernelArgs &args, cudaStream_t str
         if (o.player) o.player += whole;
         if (o.next_action) o.next_action += whole;
     }
-    const int ring_slots = ring_slots_for(cfg, args, mode);
-    if (int rc = plan_launch(cfg, args.ops, mode, ring_slots, args.num_envs, &plan)) return rc;
+    if (int rc = plan_launch(cfg, args.ops, mode, args.num_envs, &plan)) return rc;
     args.cfg = cfg->dev;
     args.warp_bytes = plan.warp_bytes;
     args.tile_bytes = plan.tile_bytes;
@@ -1261,7 +1168,7 @@ static int launch_fused(const sx_config *cfg, KernelArgs &args, cudaStream_t str
     // stream loses ~8 % when the ~0.2 KB/game state reads come from DRAM (tools/probes/probe_write.cu), but any L2
     // set-aside large enough to hold the state takes capacity from the output lines that wait for their sparse
     // stores: 25-30 % of the maximum was neutral, 35 % and more cost 15-35 %.)
-    fused_for(cfg, mode, ring_slots)<<<plan.grid, plan.warps_per_block * 32, plan.smem_per_block, stream>>>(args);
+    fused_for(cfg, mode)<<<plan.grid, plan.warps_per_block * 32, plan.smem_per_block, stream>>>(args);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return cuda_fail("sx fused kernel launch", e);
     return 0;
@@ -1467,7 +1374,6 @@ extern "C" int sx_step_all_launch_info(const sx_config *cfg, uint32_t obs_mask, 
     probe.ops = ops;
     probe.num_envs = 1LL << 40;
     out->thread_per_game = 0;
-    out->ring_slots = 0;
     if (toy_eligible(cfg, probe, mode_for(cfg, probe))) {  // the toy boards step through sx_toy_kernel
         ToyPlan tp;
         if (int rc = plan_toy(cfg, ops, &tp)) return rc;
@@ -1480,9 +1386,7 @@ extern "C" int sx_step_all_launch_info(const sx_config *cfg, uint32_t obs_mask, 
         out->thread_per_game = 1;
         return 0;
     }
-    const int ring_slots = ring_slots_for(cfg, probe, mode_for(cfg, probe));
-    if (int rc = plan_launch(cfg, ops, mode_for(cfg, probe), ring_slots, 1LL << 40, &plan)) return rc;
-    out->ring_slots = ring_slots;
+    if (int rc = plan_launch(cfg, ops, mode_for(cfg, probe), 1LL << 40, &plan)) return rc;
     out->warps_per_block = plan.warps_per_block; out->blocks_per_sm = plan.blocks_per_sm;
     out->smem_bytes_per_block = plan.smem_per_block; out->num_sms = plan.num_sms; out->grid_blocks = plan.grid;
     out->regs_per_thread = plan.regs;

@@ -255,62 +255,6 @@ def test_original_channels_raw_facade_getters():
                                       _bits(orc.get_fully_observable_observation(states[i], p)))
 
 
-# ---- ring renderer (sx_ring.cuh) against the general kernel ---------------------------------------------------------
-@pytest.mark.parametrize("version,table,full", [("barrage", "barrage", False), ("barrage", "barrage", True),
-                                                ("standard", "standard", False), ("standard", "standard", True),
-                                                ("octa_barrage", None, False), ("octa_barrage", None, True),
-                                                ("short_barrage", "barrage", False)])
-def test_ring_kernel_equals_general_kernel(version, table, full):
-    """Same seeds, same actions: the ring-rendered fused step (outputs built in shared-memory chunks, written by TMA
-    only) and the general kernel (TMA background + sparse stores) must agree on every output and on the state after
-    every step -- incl. auto-reset and the sampled actions.  333 games on a persistent grid: several games per warp, so
-    every ring slot is reused many times per launch."""
-    from stratego_env_b200.config import VERSION_CONFIGS, as_version
-    from stratego_env_b200.engine import StrategoEngine, load_setup_table
-    cfg = VERSION_CONFIGS[as_version(version)]
-    eng = StrategoEngine(cfg, device="cuda:0", p2_rot180=table is None)
-    info = eng.launch_info(partial=True, full=full, mask=True)
-    assert info["ring_slots"] in (2, 3) and info["thread_per_game"] == 0
-    setups = eng.upload_setups(load_setup_table(table)) if table else None
-    B, steps = 333, 150 if version == "short_barrage" else 60
-    runs = {}
-    for baseline in (False, True):
-        st = eng.alloc_state(B)
-        eng.reset(st, seed=5, env_base=1000, setups=setups, shuffle=setups is None)
-        out = eng.alloc_outputs(B, partial=True, full=full, mask=True, sample=True)
-        for t in out.values():
-            if t.dtype == torch.float32:
-                t.fill_(float("nan"))  # every output byte must be written
-            else:
-                t.fill_(77)
-        eng.observe(st, out=out, partial=True, full=full, mask=True)
-        actions = eng.sample_valid(out["valid_mask"], seed=5, step=0, env_base=1000)
-        stats = torch.zeros(8, dtype=torch.int64, device="cuda:0")
-        trace = []
-        for s in range(steps):
-            if s % 7 == 0:
-                out["partial_obs"].fill_(float("nan"))
-                out["valid_mask"].fill_(77)
-            eng.step_all(st, actions, out, env_base=1000, auto_reset=True, sample_next=True, setups=setups,
-                         shuffle=setups is None, seed=5, stats=stats, baseline_kernel=baseline)
-            torch.cuda.synchronize()
-            trace.append({k: v.cpu().numpy().copy() for k, v in out.items()} |
-                         {"board": st.board.cpu().numpy().copy(), "aux": st.aux.cpu().numpy().copy(),
-                          "cap": st.captured.cpu().numpy().copy()})
-            actions = out["next_action"].clone()
-        runs[baseline] = (trace, stats.cpu().numpy())
-    (ring, ring_stats), (ref, ref_stats) = runs[False], runs[True]
-    assert np.array_equal(ring_stats, ref_stats)
-    if version == "short_barrage":
-        assert ring_stats[0] > B  # games ended (turn limit 100) and were re-set on the device
-    for s in range(steps):
-        for key in ref[s]:
-            a, b = ring[s][key], ref[s][key]
-            if a.dtype == np.float32:
-                a, b = a.view(np.uint32), b.view(np.uint32)
-            assert np.array_equal(a, b), (version, full, s, key)
-
-
 # ---- toy boards: the thread-per-game kernel (sx_toy_kernel) against the warp-level kernel -------------------------
 @pytest.mark.parametrize("version,full", [("micro", False), ("micro", True), ("tiny", False), ("tiny", True)])
 def test_toy_kernel_equals_warp_level_kernel(version, full):

@@ -6,7 +6,7 @@ whatever that index decodes to.  "Same state + same action => same result" there
 not only for the ones in the mask.  Two pins:
   * tests/golden/spatial_alias.npz -- the unmodified reference run over every flat index of recorded states;
   * the C oracle (itself pinned to that file) over >= 64 states per board size.
-Both the specialised kernels (thread-per-game toy kernel, 10x10 ring kernel) and the general warp-per-game kernel.
+Both the specialised kernel (thread-per-game, boards of <= 16 cells) and the general warp-per-game kernel.
 """
 import numpy as np
 import pytest
