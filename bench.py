@@ -184,8 +184,27 @@ class CpuSelfplay:
                 "seconds": dt, "steps": steps}
 
 
+def reference_bytes_step(workload):
+    """algorithmic bytes per env-step of a workload, from the variant tables alone (no GPU, no engine)"""
+    from stratego_env_b200.config import VERSION_CONFIGS, as_version, piece_amounts_array
+    w = WORKLOADS[workload]
+    cfg = VERSION_CONFIGS[as_version(w["version"])]
+    R, Cc = cfg["rows"], cfg["columns"]
+    return algorithmic_bytes_per_step(R * Cc, 2 * (R - 1) + 2 * (Cc - 1) + 1, int(piece_amounts_array(cfg["piece_amounts"]).sum()),
+                                      w["full"])
+
+
 def cpu_selfplay(workload, budget_s, threads=None):
     return CpuSelfplay(workload, threads).run(budget_s)
+
+
+def bench_config(workload, envs_per_gpu, world, bytes_step, dephase):
+    """the `config` object of the JSON line -- identical keys and values from the GPU arm and the reference arm"""
+    w = WORKLOADS[workload]
+    return {"workload": workload, "description": w["desc"], "envs_per_gpu": envs_per_gpu,
+            "global_envs": envs_per_gpu * world, "sharding": "env index, no data-path collective",
+            "l2": "outputs per step (%.1f GB) exceed the 126 MB L2; no flush needed" % (envs_per_gpu * bytes_step / 1e9),
+            "dephase_steps": dephase}
 
 
 def run_reference_arm(args):
@@ -208,7 +227,8 @@ def run_reference_arm(args):
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * total_s / max(1, args.steps), "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
-        "config": {"workload": args.workload, "description": w["desc"]},
+        "config": bench_config(args.workload, args.envs or w["envs"], max(1, args.gpus), reference_bytes_step(args.workload),
+                               args.dephase if args.dephase is not None else w["dephase"]),
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": last["cores"], "kind": "port",
                          "sample": "%d samples; each: %s" % (args.steps, last["sample"])},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -245,11 +265,137 @@ def run_e2e(torch, eng, w, B, env_base, seed, steps, warmup, full, copy_obs=True
         env.close()
 
 
+class DeviceLeg:
+    """Device-resident random-valid self-play of one workload on this rank's GPU: state, actions and outputs stay in
+    HBM; one step = one launch of the fused kernel over all games (auto-reset, sampled next action)."""
+
+    def __init__(self, torch, name, device, rank, seed, envs=None, dephase=None, baseline_kernel=False):
+        from stratego_env_b200.config import VERSION_CONFIGS, as_version
+        from stratego_env_b200.engine import StrategoEngine, load_setup_table
+        self.torch, self.name, self.w = torch, name, WORKLOADS[name]
+        w = self.w
+        self.B = envs or w["envs"]
+        self.full = w["full"]
+        self.eng = StrategoEngine(VERSION_CONFIGS[as_version(w["version"])], device=device, p2_rot180=w["table"] is None)
+        eng = self.eng
+        self.setups = eng.upload_setups(load_setup_table(w["table"])) if w["table"] else None
+        self.shuffle = self.setups is None
+        self.env_base = rank * self.B  # games shard by env index; Philox streams are keyed by the global env id
+        self.seed, self.baseline_kernel = seed, baseline_kernel
+        self.st = eng.alloc_state(self.B)
+        eng.reset(self.st, seed=seed, env_base=self.env_base, setups=self.setups, shuffle=self.shuffle)
+        self.out = eng.alloc_outputs(self.B, partial=True, full=self.full, mask=True, sample=True)
+        eng.observe(self.st, out=self.out)
+        self.actions = eng.sample_valid(self.out["valid_mask"], seed=seed, step=0, env_base=self.env_base)
+        self.stats = torch.zeros(8, dtype=torch.int64, device=device)
+        # de-phase the games (steady-state mix of early / mid / late positions) without rendering
+        self.dephase = dephase if dephase is not None else w["dephase"]
+        lean = eng.alloc_outputs(self.B, partial=False, full=False, mask=False, sample=True)
+        lean["next_action"] = self.out["next_action"]
+        for _ in range(self.dephase):
+            self.step(lean)
+        self.out["next_action"] = lean["next_action"]
+
+    def step(self, outputs=None):
+        outputs = self.out if outputs is None else outputs
+        self.eng.step_all(self.st, self.actions, outputs, env_base=self.env_base, auto_reset=True, sample_next=True,
+                          setups=self.setups, shuffle=self.shuffle, seed=self.seed, stats=self.stats,
+                          baseline_kernel=self.baseline_kernel)
+        self.actions, outputs["next_action"] = outputs["next_action"], self.actions
+
+    def run(self, steps, warmup, barrier):
+        """(total ms of `steps` launches, per-launch ms) -- CUDA events on the launching stream, barrier on both sides"""
+        torch = self.torch
+        for _ in range(warmup):
+            self.step()
+        self.stats.zero_()
+        events = [torch.cuda.Event(enable_timing=True) for _ in range(steps + 1)]
+        barrier()
+        events[0].record()
+        for i in range(steps):
+            self.step()
+            events[i + 1].record()
+        barrier()
+        assert int(self.out["illegal"].sum().item()) == 0, "sampled actions must be legal"
+        return events[0].elapsed_time(events[-1]), [events[i].elapsed_time(events[i + 1]) for i in range(steps)]
+
+    def roofline(self, launch_ms):
+        lay = self.eng.layout
+        bytes_step = algorithmic_bytes_per_step(lay.cells, lay.spatial_channels, lay.pieces_per_side, self.full)
+        peak, peak_src = measured_peak()
+        kernel_ms = statistics.mean(launch_ms)
+        achieved = self.B * bytes_step / (kernel_ms * 1e-3) / 1e9
+        info = self.eng.launch_info(partial=True, full=self.full, mask=True)
+        return {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                "traffic": recorded_traffic(self.name, self.B), "peak_source": peak_src,
+                "kernel": ("sx_fused_kernel (general, forced)" if self.baseline_kernel and info.get("thread_per_game")
+                           else "sx_toy_kernel" if info.get("thread_per_game") else "sx_fused_kernel"),
+                "algorithmic_bytes_per_env_step": bytes_step, "kernel_ms": kernel_ms, "launch": info}
+
+
+class RolloutLeg:
+    """BASELINE config 5: Standard Stratego rollout feeding a torch conv policy, all on the GPU.  Per step: observation
+    [B,R,C,67] (viewed as channels-last NCHW, no copy) -> 3-layer conv policy in bf16 (cuDNN: library code, not ours) ->
+    logits [B,R,C,A] -> masked categorical draw from the game state (sx_sample_policy) -> fused env step (sx_step_all)."""
+
+    def __init__(self, torch, device, rank, seed, envs, both):
+        from stratego_env_b200 import BatchedStrategoEnv, GameVersions, ObservationModes
+        self.torch, self.B, self.both = torch, envs, both
+        mode = ObservationModes.BOTH_OBSERVATIONS if both else ObservationModes.PARTIALLY_OBSERVABLE
+        self.env = BatchedStrategoEnv({"version": GameVersions.STANDARD, "human_inits": True, "observation_mode": mode},
+                                      num_envs=envs, device=device, seed=seed, env_base=rank * envs)
+        A = self.env.spatial_action_size[2]
+        torch.manual_seed(0)
+        ch = 64
+        self.policy = torch.nn.Sequential(
+            torch.nn.Conv2d(67, ch, 3, padding=1), torch.nn.ReLU(), torch.nn.Conv2d(ch, ch, 3, padding=1), torch.nn.ReLU(),
+            torch.nn.Conv2d(ch, A, 3, padding=1)).to(device, torch.bfloat16).to(memory_format=torch.channels_last)
+        self.obs = self.env.reset()
+
+    def step(self, ev=None):
+        torch = self.torch
+        if ev:
+            ev[0].record()
+        x = self.obs["partial_observation"].permute(0, 3, 1, 2).to(torch.bfloat16)
+        logits = self.policy(x).permute(0, 2, 3, 1).contiguous()
+        if ev:
+            ev[1].record()
+        actions = self.env.sample_actions_from_logits(logits)
+        if ev:
+            ev[2].record()
+        self.obs, _, _, infos = self.env.step(actions)
+        if ev:
+            ev[3].record()
+        return infos
+
+    def run(self, steps, warmup, barrier):
+        torch = self.torch
+        with torch.no_grad():
+            for _ in range(warmup):
+                self.step()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            barrier()
+            e0.record()
+            for _ in range(steps):
+                infos = self.step()
+            e1.record()
+            barrier()
+            assert not infos["illegal_action"].any().item()
+            total_ms = e0.elapsed_time(e1)
+            parts = {"policy_ms": 0.0, "sampler_ms": 0.0, "env_ms": 0.0}
+            ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
+            n = 5
+            for _ in range(n):
+                self.step(ev)
+                torch.cuda.synchronize()
+                for k, (a, b) in zip(parts, ((0, 1), (1, 2), (2, 3))):
+                    parts[k] += ev[a].elapsed_time(ev[b]) / n
+        return total_ms, parts
+
+
 def run_gpu_arm(args):
     import torch
     import torch.distributed as dist
-    from stratego_env_b200.config import VERSION_CONFIGS, as_version
-    from stratego_env_b200.engine import StrategoEngine, load_setup_table
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -276,134 +422,112 @@ def run_gpu_arm(args):
             os.dup2(saved_stdout, 1)
             os.close(saved_stdout)
 
-    w = WORKLOADS[args.workload]
-    B = args.envs or w["envs"]
-    full = w["full"]
-    cfg = VERSION_CONFIGS[as_version(w["version"])]
-    eng = StrategoEngine(cfg, device=device, p2_rot180=w["table"] is None)
-    setups = eng.upload_setups(load_setup_table(w["table"])) if w["table"] else None
-    shuffle = setups is None
-    env_base = rank * B  # games shard by env index; Philox streams are keyed by the global env id
-    seed = args.seed
-
-    st = eng.alloc_state(B)
-    eng.reset(st, seed=seed, env_base=env_base, setups=setups, shuffle=shuffle)
-    out = eng.alloc_outputs(B, partial=True, full=full, mask=True, sample=True)
-    eng.observe(st, out=out)
-    actions = eng.sample_valid(out["valid_mask"], seed=seed, step=0, env_base=env_base)
-    stats = torch.zeros(8, dtype=torch.int64, device=device)
-
-    def step(outputs):
-        nonlocal actions
-        eng.step_all(st, actions, outputs, env_base=env_base, auto_reset=True, sample_next=True, setups=setups,
-                     shuffle=shuffle, seed=seed, stats=stats, baseline_kernel=args.baseline_kernel)
-        actions, outputs["next_action"] = outputs["next_action"], actions
-
-    # de-phase the games (steady-state mix of early/mid/late positions) without rendering
-    lean = eng.alloc_outputs(B, partial=False, full=False, mask=False, sample=True)
-    lean["next_action"] = out["next_action"]
-    for _ in range(args.dephase if args.dephase is not None else w["dephase"]):
-        step(lean)
-    out["next_action"] = lean["next_action"]
-    for _ in range(args.warmup):
-        step(out)
-    stats.zero_()
-
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    sampler = ClockSampler(physical_gpu_index(local_rank)) if rank == 0 else None
-    events = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
-    barrier()
-    events[0].record()
-    for i in range(args.steps):
-        step(out)
-        events[i + 1].record()
-    barrier()
-    clocks = sampler.stop() if sampler else None
-    launch_ms = [events[i].elapsed_time(events[i + 1]) for i in range(args.steps)]
-    total_ms = events[0].elapsed_time(events[-1])
-    illegal = int(out["illegal"].sum().item())
-    assert illegal == 0, "sampled actions must be legal"
-    if world > 1:
-        t = torch.tensor([total_ms], dtype=torch.float64, device=device)
+    def max_over_ranks(value):
+        if world == 1:
+            return float(value)
+        t = torch.tensor([value], dtype=torch.float64, device=device)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        total_ms = float(t.item())
+        return float(t.item())
+
+    seed = args.seed
+    w = WORKLOADS[args.workload]
+    leg = DeviceLeg(torch, args.workload, device, rank, seed, envs=args.envs, dephase=args.dephase,
+                    baseline_kernel=args.baseline_kernel)
+    B, full = leg.B, leg.full
+    sampler = ClockSampler(physical_gpu_index(local_rank)) if rank == 0 else None
+    total_ms, launch_ms = leg.run(args.steps, args.warmup, barrier)
+    clocks = sampler.stop() if sampler else None
+    total_ms = max_over_ranks(total_ms)
+    stats = leg.stats.clone()
+    if world > 1:
         dist.all_reduce(stats, op=dist.ReduceOp.SUM)  # the only collective: end-of-run statistics
     value = world * B * args.steps / (total_ms * 1e-3)
+    roofline = leg.roofline(launch_ms) if rank == 0 else None
+    eng = leg.eng
+    del leg
+    torch.cuda.empty_cache()
 
     # ---- end to end through host buffers ----------------------------------------------------------------
     e2e = e2e_device_obs = None
     if not args.no_e2e:
-        del lean
         e2e_steps = max(1, min(args.steps, args.e2e_steps))
         e2e_B = args.e2e_envs or B
+
         def one(copy_obs, what):
             secs, d2h, h2d = run_e2e(torch, eng, w, e2e_B, rank * e2e_B, seed, e2e_steps, max(1, min(args.warmup, 3)),
                                      full, copy_obs=copy_obs)
-            t = torch.tensor([secs], dtype=torch.float64, device=device)
-            if world > 1:
-                dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            return {"value": world * e2e_B * e2e_steps / float(t.item()), "unit": UNIT,
+            secs = max_over_ranks(secs)
+            return {"value": world * e2e_B * e2e_steps / secs, "unit": UNIT,
                     "h2d_bytes_per_step": h2d * world, "d2h_bytes_per_step": d2h * world, "steps": e2e_steps,
-                    "envs_per_gpu": e2e_B, "what": what}
+                    "envs_per_gpu": e2e_B, "d2h_GBps_aggregate": d2h * world * e2e_steps / secs / 1e9, "what": what}
 
         e2e = one(True, "HostBufferEnv.step (sx_host_env_step): int32 actions from pinned host memory, every output "
                         "(obs, mask, reward, done, winner, flags, sampled action) copied back to pinned host memory, "
-                        "16 pipelined chunks; PCIe-bound")
+                        "pipelined chunks; bound by the host link (profiles/: tools/probes/probe_d2h.cu)")
         # the same call when the consumer of obs/mask is on the GPU (a policy network): only the per-game scalars
         # cross PCIe.  Reported for context; `e2e` above is the contract's number.
         e2e_device_obs = one(False, "same call (4 chunks), observations and mask stay in HBM; actions H2D, scalars D2H")
+    del eng
+    torch.cuda.empty_cache()
+
+    # ---- the other configurations of BASELINE.json, every rank takes part (max-over-ranks timing) -----------------
+    # configs[1] micro, configs[3] standard 512k envs/GPU, configs[4] the conv-policy rollout (PO and PO + full)
+    others = {}
+    for name in [n for n in args.also.split(",") if n and n != args.workload]:
+        try:
+            if name in ("standard_rollout", "standard_rollout_both"):
+                envs = args.rollout_envs
+                r = RolloutLeg(torch, device, rank, seed, envs, both=name.endswith("both"))
+                ms, parts = r.run(min(args.steps, 20), 3, barrier)
+                ms = max_over_ranks(ms)
+                steps = min(args.steps, 20)
+                others[name] = {
+                    "value": world * envs * steps / (ms * 1e-3), "unit": UNIT, "ms_per_step": ms / steps,
+                    "envs_per_gpu": envs, **{k: round(v, 4) for k, v in parts.items()},
+                    "engine_share_of_step": (parts["sampler_ms"] + parts["env_ms"]) / max(1e-9, sum(parts.values())),
+                    "description": "Standard 10x10 rollout: obs -> 3-layer conv policy (64 ch, bf16, cuDNN) -> masked "
+                                   "categorical draw from the game state (sx_sample_policy) -> fused step; %s; value "
+                                   "includes the policy" % ("PO + full obs" if name.endswith("both") else "PO obs")}
+                del r
+            else:
+                other = DeviceLeg(torch, name, device, rank, seed)
+                steps = min(args.steps, 30)
+                ms, lms = other.run(steps, args.warmup, barrier)
+                ms = max_over_ranks(ms)
+                rf = other.roofline(lms)
+                others[name] = {"value": world * other.B * steps / (ms * 1e-3), "unit": UNIT, "ms_per_step": ms / steps,
+                                "envs_per_gpu": other.B, "n_gpus": world, "roofline_frac": rf["frac"],
+                                "achieved_GBps": rf["achieved"], "kernel": rf["kernel"],
+                                "algorithmic_bytes_per_env_step": rf["algorithmic_bytes_per_env_step"],
+                                "description": WORKLOADS[name]["desc"]}
+                del other
+        except Exception as exc:  # noqa: BLE001
+            others[name] = {"error": repr(exc)[:300]}
+        torch.cuda.empty_cache()
 
     if rank == 0:
-        lay = eng.layout
-        bytes_step = algorithmic_bytes_per_step(lay.cells, lay.spatial_channels, lay.pieces_per_side, full)
-        peak, peak_src = measured_peak()
-        kernel_ms = statistics.mean(launch_ms)
-        achieved = B * bytes_step / (kernel_ms * 1e-3) / 1e9
-        info = eng.launch_info(partial=True, full=full, mask=True)
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "u8", "data": "synthetic",
-            "config": {"workload": args.workload, "description": w["desc"], "envs_per_gpu": B,
-                       "global_envs": B * world, "sharding": "env index, no data-path collective",
-                       "l2": "outputs per step (%.1f GB) exceed the 126 MB L2; no flush needed" %
-                             (B * bytes_step / 1e9),
-                       "dephase_steps": args.dephase if args.dephase is not None else w["dephase"]},
-            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": recorded_traffic(args.workload, B), "peak_source": peak_src,
-                         "kernel": ("sx_fused_kernel (general)" if args.baseline_kernel else
-                                    "sx_toy_kernel" if info.get("thread_per_game") else "sx_fused_kernel"),
-                         "algorithmic_bytes_per_env_step": bytes_step,
-                         "kernel_ms": kernel_ms, "launch": info},
+            "config": bench_config(args.workload, B, world, roofline["algorithmic_bytes_per_env_step"],
+                                   args.dephase if args.dephase is not None else w["dephase"]),
+            "roofline": roofline,
             "e2e": e2e,
             "e2e_device_obs": e2e_device_obs,
             "gpu_launches": args.steps,
             "clocks": clocks,
             "games_finished": int(stats[0].item()),
+            "stats": {"steps": int(stats[5].item()), "attacks": int(stats[6].item()), "resets": int(stats[7].item()),
+                      "illegal_actions": int(stats[4].item())},
         }
-        if world == 1 and args.also:
-            # the other single-GPU configurations of BASELINE.json (configs[1] micro, configs[3] standard): short
-            # device-resident runs in a child process, summarised here so one line shows every workload
-            torch.cuda.empty_cache()
-            line["other_workloads"] = {}
-            for name in [n for n in args.also.split(",") if n and n != args.workload]:
-                try:
-                    child = subprocess.run([sys.executable, os.path.abspath(__file__), "--workload", name, "--steps",
-                                            str(min(args.steps, 30)), "--warmup", str(args.warmup), "--no-e2e",
-                                            "--no-cpu", "--also", ""], capture_output=True, text=True, timeout=600)
-                    d = json.loads(child.stdout.strip().splitlines()[-1])
-                    line["other_workloads"][name] = {
-                        "value": d["value"], "unit": UNIT, "ms_per_step": d["ms_per_step"],
-                        "envs_per_gpu": d["config"]["envs_per_gpu"], "roofline_frac": d["roofline"]["frac"],
-                        "achieved_GBps": d["roofline"]["achieved"],
-                        "algorithmic_bytes_per_env_step": d["roofline"]["algorithmic_bytes_per_env_step"],
-                        "description": d["config"]["description"]}
-                except Exception as exc:  # noqa: BLE001
-                    line["other_workloads"][name] = {"error": str(exc)[:200]}
+        if others:
+            line["other_workloads"] = others
         if world == 1 and not args.no_cpu:
             line["cpu_baseline"] = {k: v for k, v in cpu_selfplay(args.workload, args.cpu_seconds).items()
                                     if k not in ("seconds", "steps")}
@@ -428,8 +552,9 @@ def main():
     ap.add_argument("--e2e-envs", type=int, default=None)
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     ap.add_argument("--ref-seconds", type=float, default=20.0, help="--impl reference: upper bound of one step's sample")
-    ap.add_argument("--also", default="micro,standard",
-                    help="other workloads summarised in the same line at N=1 (comma list, '' = none)")
+    ap.add_argument("--also", default="micro,standard,standard_rollout,standard_rollout_both",
+                    help="other workloads summarised in the same line, run by every rank (comma list, '' = none)")
+    ap.add_argument("--rollout-envs", type=int, default=131072, help="games per GPU of the conv-policy rollout legs")
     ap.add_argument("--baseline-kernel", action="store_true",
                     help="time the general warp-per-game kernel instead of the specialised one (A/B aid)")
     ap.add_argument("--no-e2e", action="store_true")

@@ -117,7 +117,7 @@ __global__ void __launch_bounds__(256) sx_sample_logits_kernel(const T *logits, 
 // (balanced over the lanes: an entry costs a Philox block and two transcendentals, a scout would otherwise pile ten of
 // them on one lane) and runs the identical Gumbel-max / log-sum-exp per entry.  Same Philox key per (game, step, entry)
 // and the same tie rule as the mask kernel, so both return the SAME action for the same key.
-template <typename T, int K>
+template <typename T, int K, bool LOGPROB>
 __global__ void __launch_bounds__(256) sx_sample_policy_kernel(const __grid_constant__ DevConfig cfg, const uint8_t *board,
                                                                const int16_t *aux, long long num_envs, long long env_base,
                                                                const T *logits, uint2 key, uint32_t step, float inv_temperature,
@@ -185,8 +185,10 @@ __global__ void __launch_bounds__(256) sx_sample_policy_kernel(const __grid_cons
         const uint4 r = philox4x32_10(make_uint4(uint32_t(gid), uint32_t(gid >> 32), RNG_POLICY ^ step, uint32_t(i)), key);
         const float score = z - __logf(-__logf(uniform_open01(r.x)));
         if (score > best || best_i < 0 || (score == best && i < best_i)) { best = score; best_i = i; best_logit = z; }
-        if (z > run_max) { run_sum = run_sum * __expf(run_max - z) + 1.0f; run_max = z; }
-        else run_sum += __expf(z - run_max);
+        if (LOGPROB) {  // online log-sum-exp over the valid entries, only when the log-probability is asked for
+            if (z > run_max) { run_sum = run_sum * __expf(run_max - z) + 1.0f; run_max = z; }
+            else run_sum += __expf(z - run_max);
+        }
     };
     const int listed = min(total, list_cap);
     for (int t = lane; t < listed; t += 32) visit(list[t]);
@@ -208,14 +210,16 @@ __global__ void __launch_bounds__(256) sx_sample_policy_kernel(const __grid_cons
         const int oi = __shfl_xor_sync(FULL, best_i, off);
         const bool take = oi >= 0 && (best_i < 0 || ob > best || (ob == best && oi < best_i));
         if (take) { best = ob; best_i = oi; best_logit = ol; }
-        const float om = __shfl_xor_sync(FULL, run_max, off), os = __shfl_xor_sync(FULL, run_sum, off);
-        const float nm = fmaxf(run_max, om);
-        if (nm > -INFINITY) run_sum = run_sum * __expf(run_max - nm) + os * __expf(om - nm);
-        run_max = nm;
+        if (LOGPROB) {
+            const float om = __shfl_xor_sync(FULL, run_max, off), os = __shfl_xor_sync(FULL, run_sum, off);
+            const float nm = fmaxf(run_max, om);
+            if (nm > -INFINITY) run_sum = run_sum * __expf(run_max - nm) + os * __expf(om - nm);
+            run_max = nm;
+        }
     }
     if (lane == 0) {
         actions[env] = best_i;
-        if (logprob) logprob[env] = best_logit - (run_max + __logf(run_sum));
+        if (LOGPROB) logprob[env] = best_logit - (run_max + __logf(run_sum));
     }
 }
 
@@ -266,15 +270,14 @@ static cudaError_t launch_policy(const sx_config *cfg, sx_state st, int64_t num_
     const int warp_bytes = carve_warp(d, nullptr, nullptr) + round16(list_cap * 2);
     const unsigned grid = unsigned((num_envs + wpb - 1) / wpb);
     const size_t smem = size_t(wpb) * warp_bytes;
-    if (d.N <= 64)
-        sx_sample_policy_kernel<T, 2><<<grid, wpb * 32, smem, s>>>(d, st.board, st.aux, num_envs, env_base, logits, key, step, inv_t,
-                                                                   actions, logprob, warp_bytes, list_cap);
-    else if (d.N <= 128)
-        sx_sample_policy_kernel<T, 4><<<grid, wpb * 32, smem, s>>>(d, st.board, st.aux, num_envs, env_base, logits, key, step, inv_t,
-                                                                   actions, logprob, warp_bytes, list_cap);
-    else
-        sx_sample_policy_kernel<T, 8><<<grid, wpb * 32, smem, s>>>(d, st.board, st.aux, num_envs, env_base, logits, key, step, inv_t,
-                                                                   actions, logprob, warp_bytes, list_cap);
+    auto launch = [&](auto kernel) {
+        kernel<<<grid, wpb * 32, smem, s>>>(d, st.board, st.aux, num_envs, env_base, logits, key, step, inv_t, actions, logprob,
+                                            warp_bytes, list_cap);
+    };
+    const bool lp = logprob != nullptr;
+    if (d.N <= 64) lp ? launch(sx_sample_policy_kernel<T, 2, true>) : launch(sx_sample_policy_kernel<T, 2, false>);
+    else if (d.N <= 128) lp ? launch(sx_sample_policy_kernel<T, 4, true>) : launch(sx_sample_policy_kernel<T, 4, false>);
+    else lp ? launch(sx_sample_policy_kernel<T, 8, true>) : launch(sx_sample_policy_kernel<T, 8, false>);
     return cudaGetLastError();
 }
 
