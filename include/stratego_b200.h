@@ -105,6 +105,13 @@ typedef struct {
     int8_t *player;          /* [num_envs] player the returned mask/obs are for (= player to move) */
     int32_t *next_action;    /* [num_envs] uniformly sampled valid spatial action for `player`
                                 (replaces maenv:830-834), written when SX_SAMPLE_NEXT is set */
+    /* maenv:772-773: when a game ends, BOTH players get their observation of the final position.  With SX_AUTO_RESET the
+     * regular outputs already show the next game, so these optional side buffers receive the terminal observations:
+     * [num_envs][2][R][C][channels], index 0 = player +1's view, 1 = player -1's; only rows of games with done = 1 are
+     * written.  (The terminal valid-action mask is the lone noop entry [0,0,A-1] for both players, impl:414 / 514-515.)
+     * Each needs its regular counterpart (partial_obs / full_obs) to be requested in the same call. */
+    float *terminal_partial_obs;
+    float *terminal_full_obs;
 } sx_outputs;
 
 enum {
@@ -117,6 +124,10 @@ enum {
     SX_SAMPLE_NEXT = 2,         /* also draw a uniformly random valid action into outputs.next_action */
     SX_ALLOW_OSCILLATION = 4,   /* allow_piece_oscillation=True (impl:771-777) */
     SX_RESET_RANDOM_SHUFFLE = 8, /* (re)sets draw setups by shuffling the pieces (util:13-30) instead of a table */
+    SX_SAME_SETUP = 32,         /* same_start_pos_everytime (maenv:352-354): every game of an env starts from the setup
+                                   its first draw produced */
+    SX_REPEAT_OTHER_SIDE = 64,  /* repeat_games_from_other_side (maenv:530-534): every second game of an env repeats the
+                                   previous game's initial position as player -1 sees it (impl:646-675), player -1 first */
     SX_KERNEL_BASELINE = 16     /* run the general warp-per-game kernel even where a specialised one is eligible (the
                                    thread-per-game kernel of the <= 16-cell boards).  Results are identical by
                                    contract; the cross-kernel parity tests use it */

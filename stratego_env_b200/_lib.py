@@ -12,6 +12,7 @@ _i32, _i64, _u32, _u64, _vp = C.c_int32, C.c_int64, C.c_uint32, C.c_uint64, C.c_
 
 SX_ACTION_SPATIAL, SX_ACTION_1D = 0, 1
 SX_AUTO_RESET, SX_SAMPLE_NEXT, SX_ALLOW_OSCILLATION, SX_RESET_RANDOM_SHUFFLE, SX_KERNEL_BASELINE = 1, 2, 4, 8, 16
+SX_SAME_SETUP, SX_REPEAT_OTHER_SIDE = 32, 64
 OBS_PO, OBS_FO, OBS_MASK = 1, 2, 4
 SX_CHANNELS_EXTENDED, SX_CHANNELS_ORIGINAL = 0, 1
 
@@ -35,7 +36,8 @@ class SxState(C.Structure):
 
 class SxOutputs(C.Structure):
     _fields_ = [(n, _vp) for n in ("partial_obs", "full_obs", "valid_mask", "reward", "done", "winner",
-                                   "ending_invalid", "illegal", "player", "next_action")]
+                                   "ending_invalid", "illegal", "player", "next_action", "terminal_partial_obs",
+                                   "terminal_full_obs")]
 
 
 class SxLaunchInfo(C.Structure):

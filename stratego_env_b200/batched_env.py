@@ -10,8 +10,13 @@ Semantics that differ from the one-game API because many games advance at once:
   * obs / mask / ``player`` are always for the player to move next in each game, in that player's frame;
   * when a game ends during ``step`` the returned ``done`` / ``winner`` / ``game_result_was_invalid`` / rewards
     describe the finished game, and (with ``auto_reset=True``) the observation is already the first
-    observation of the next game -- the terminal observations the reference hands to both players
-    (maenv:772-773) are available from ``observe(player=...)`` when auto-reset is off;
+    observation of the next game.  The terminal observations the reference hands to BOTH players (maenv:772-773)
+    arrive in ``infos['terminal_observation']`` when the env is built with ``terminal_observations=True``
+    (rows of games with ``done``; written by the same kernel launch, before the re-set);
+  * ``same_start_pos_everytime`` (maenv:352-354) fixes ONE setup per env (the reference has one env), ``repeat_games_
+    from_other_side`` (maenv:530-534) replays every env's previous initial position from the other side on its odd
+    episodes, ``random_player_assignment`` (maenv:537-543) draws a +-1 agent map per env and game: ``player``, the
+    reward dict and ``infos['winner']`` are then expressed in agent ids, ``infos['player_map']`` holds the map;
   * an illegal action leaves that game untouched and sets ``illegal_action`` (the reference raises
     ``ValueError``, impl:899-902); pass ``raise_on_illegal=True`` to get the exception (costs a host sync).
 """
@@ -30,16 +35,21 @@ OC = ObservationComponents
 
 class BatchedStrategoEnv:
     def __init__(self, env_config=None, num_envs: int = 1024, device=None, seed: int = 0, env_base: int = 0,
-                 auto_reset: bool = True, sample_actions: bool = False, raise_on_illegal: bool = False):
+                 auto_reset: bool = True, sample_actions: bool = False, raise_on_illegal: bool = False,
+                 terminal_observations: bool = False):
         cfg = with_base_config(DEFAULT_CONFIG, env_config if env_config else {})
         cfg['version'] = as_version(cfg['version'])
         self.version = cfg['version']
         version_config = VERSION_CONFIGS[self.version]
         cfg = with_base_config(version_config, cfg)
-        for key in ('vs_human', 'vs_bot', 'curriculum_start_states_path', 'repeat_games_from_other_side',
-                    'random_player_assignment', 'same_start_pos_everytime'):
+        for key in ('vs_human', 'vs_bot', 'curriculum_start_states_path'):
             if cfg[key]:
                 raise NotImplementedError("%s is a single-game option (use StrategoMultiAgentEnv)" % key)
+        self.same_start_pos_everytime = bool(cfg['same_start_pos_everytime'])
+        self.repeat_games_from_other_side = bool(cfg['repeat_games_from_other_side'])
+        self.random_player_assignment = bool(cfg['random_player_assignment'])
+        assert not (self.random_player_assignment and self.repeat_games_from_other_side)  # maenv:358
+        self.terminal_observations = bool(terminal_observations)
         mode = cfg['observation_mode']
         mode = mode if isinstance(mode, ObservationModes) else ObservationModes(mode)
         self.observation_mode = mode
@@ -62,7 +72,11 @@ class BatchedStrategoEnv:
                        if self.human_inits else None)
         self.state: DeviceState = self.engine.alloc_state(self.num_envs)
         self.out = self.engine.alloc_outputs(self.num_envs, partial=self._po, full=self._fo, mask=True,
-                                             sample=sample_actions)
+                                             sample=sample_actions, terminal=self.terminal_observations)
+        # random_player_assignment: agent id of internal player +1, per env and game (maenv:537-543)
+        self.player_map = torch.ones(self.num_envs, dtype=torch.int8, device=self.device)
+        self._map_rng = torch.Generator(device=self.device)
+        self._map_rng.manual_seed((self.seed * 1000003 + self.env_base) & (2 ** 62 - 1))
         self.stats = torch.zeros(8, dtype=torch.int64, device=self.device)
         self._spare_actions = torch.zeros(self.num_envs, dtype=torch.int32, device=self.device) if sample_actions else None
 
@@ -77,8 +91,15 @@ class BatchedStrategoEnv:
         return env
 
     # ---- observation dict ---------------------------------------------------------------------------
+    def _draw_player_map(self, where: Optional[torch.Tensor] = None):
+        """np.random.random() < 0.5 -> identity, else swapped (maenv:538-543), per env; `where` selects the envs whose
+        game just (re)started"""
+        new = torch.where(torch.rand(self.num_envs, generator=self._map_rng, device=self.device) < 0.5, 1, -1).to(torch.int8)
+        self.player_map = new if where is None else torch.where(where, new, self.player_map)
+
     def _obs(self) -> dict:
-        d = {OC.VALID_ACTIONS_MASK.value: self.out["valid_mask"], "player": self.out["player"]}
+        player = self.out["player"] * self.player_map if self.random_player_assignment else self.out["player"]
+        d = {OC.VALID_ACTIONS_MASK.value: self.out["valid_mask"], "player": player}
         if self._po:
             d[OC.PARTIAL_OBSERVATION.value] = self.out["partial_obs"]
         if self._fo:
@@ -92,7 +113,10 @@ class BatchedStrategoEnv:
     def reset(self, reset_mask: Optional[torch.Tensor] = None) -> dict:
         """(re)starts every game (or those with reset_mask[b] != 0) from freshly sampled setups"""
         self.engine.reset(self.state, seed=self.seed, env_base=self.env_base, reset_mask=reset_mask,
-                          setups=self.setups, shuffle=self.setups is None)
+                          setups=self.setups, shuffle=self.setups is None, same_setup=self.same_start_pos_everytime,
+                          repeat_other_side=self.repeat_games_from_other_side)
+        if self.random_player_assignment:
+            self._draw_player_map(None if reset_mask is None else reset_mask != 0)
         self.engine.observe(self.state, out=self.out, partial=self._po, full=self._fo, mask=True)
         if self.sample_actions:
             self.out["next_action"] = self.engine.sample_valid(self.out["valid_mask"], seed=self.seed, step=0,
@@ -109,7 +133,8 @@ class BatchedStrategoEnv:
             self.out["next_action"], self._spare_actions = self._spare_actions, self.out["next_action"]
         self.engine.step_all(self.state, actions, self.out, env_base=self.env_base, auto_reset=self.auto_reset,
                              sample_next=self.sample_actions, setups=self.setups, shuffle=self.setups is None,
-                             seed=self.seed, stats=self.stats)
+                             seed=self.seed, stats=self.stats, same_setup=self.same_start_pos_everytime,
+                             repeat_other_side=self.repeat_games_from_other_side)
         out = self.out
         if self.raise_on_illegal and bool(out["illegal"].any().item()):
             bad = torch.nonzero(out["illegal"]).flatten().tolist()[:8]
@@ -125,7 +150,30 @@ class BatchedStrategoEnv:
         dones = out["done"]
         infos = {"winner": out["winner"], "game_result_was_invalid": out["ending_invalid"],
                  "illegal_action": out["illegal"]}
-        return self._obs(), rewards, dones, infos
+        if self.random_player_assignment:  # maenv:807-811: everything keyed by player is re-keyed by agent id
+            m = self.player_map
+            rewards = {1: torch.where(m == 1, reward_p1, reward_p2), -1: torch.where(m == 1, reward_p2, reward_p1)}
+            infos["winner"] = out["winner"] * m
+            infos["player_map"] = m
+        if self.terminal_observations:
+            # index 0 / 1 of the side buffers = player +1 / -1 (or agent +1 / -1 under random_player_assignment)
+            term = {}
+            for key, name in ((OC.PARTIAL_OBSERVATION.value, "terminal_partial_obs"), (OC.FULL_OBSERVATION.value, "terminal_full_obs")):
+                if name in out:
+                    t = out[name]
+                    if self.random_player_assignment:
+                        swap = (self.player_map == -1).view(-1, 1, 1, 1, 1)
+                        t = torch.where(swap, t.flip(1), t)
+                    term[key] = t
+            infos["terminal_observation"] = {1: {k: v[:, 0] for k, v in term.items()}, -1: {k: v[:, 1] for k, v in term.items()}}
+        obs = self._obs()
+        if self.random_player_assignment and self.auto_reset:
+            # the games that ended have been re-set inside the kernel: their next game gets a fresh agent map (the obs
+            # returned above still carries the old map's `player` for ... no: the observation already belongs to the
+            # NEW game, so its `player` must use the new map)
+            self._draw_player_map(dones != 0)
+            obs["player"] = self.out["player"] * self.player_map
+        return obs, rewards, dones, infos
 
     def sample_actions_from_logits(self, logits: torch.Tensor, temperature: float = 1.0, return_logprob: bool = False):
         """masked-logit sampling for the current observation's mask (one kernel; the policy's logits stay on the

@@ -677,7 +677,7 @@ __device__ __forceinline__ void place_side(const DevConfig &cfg, const WarpMem &
 
 template <class GT>
 __device__ __forceinline__ void shuffle_side(const DevConfig &cfg, const WarpMem &m, uint8_t *perm, uint8_t *own_map,
-                                             uint2 key, uint64_t gid, uint32_t episode, int side)
+                                             uint2 key, uint64_t gid, uint32_t episode, int side, uint32_t attempt)
 {
     // util:13-30: shuffle the usable cells, then deal pieces in piece-code order
     const int n = cfg.setup_len;
@@ -689,7 +689,7 @@ __device__ __forceinline__ void shuffle_side(const DevConfig &cfg, const WarpMem
         uint32_t block = 0;
         for (int i = n - 1; i >= 1; --i) {
             if (have == 0) {
-                rnd = philox4x32_10(make_uint4(uint32_t(gid), uint32_t(gid >> 32), RNG_SHUFFLE + uint32_t(side) + 2 * block, episode), key);
+                rnd = philox4x32_10(make_uint4(uint32_t(gid), uint32_t(gid >> 32), RNG_SHUFFLE + uint32_t(side) + 2 * block + 64u * attempt, episode), key);
                 have = 4;
                 ++block;
             }
@@ -708,6 +708,12 @@ struct ResetSource {
     int n_setups;
     const int32_t *setup_idx;  // [2] rows for this env, or null = draw
     bool shuffle;
+    // Which draw: the Philox counter holds (global env id, stream + 64 * attempt, rng_episode).  rng_episode is the game's
+    // episode number, 0 for every game with same_start_pos_everytime (maenv:352-354), or the PREVIOUS episode's number
+    // when the game repeats the last setup from the other side (maenv:530-534); attempt counts re-draws of an unplayable
+    // setup, so that re-drawing never disturbs the episode numbering.
+    uint32_t rng_episode, attempt;
+    bool other_side;           // maenv:530-534: last initial state as player -1 sees it (impl:646-675), player -1 moves first
 };
 
 template <class GT>
@@ -722,7 +728,7 @@ __device__ __forceinline__ void reset_game_inl(const DevConfig &cfg, const WarpM
     if (src.shuffle || src.setups == nullptr) {
         uint8_t *perm = m.scratch, *own_map = m.scratch + cfg.setup_len;
         for (int side = 0; side < 2; ++side) {
-            shuffle_side<GT>(cfg, m, perm, own_map, key, gid, episode, side);
+            shuffle_side<GT>(cfg, m, perm, own_map, key, gid, src.rng_episode, side, src.attempt);
             place_side<GT>(cfg, m, own_map, side);
             GT::sync();
         }
@@ -730,7 +736,7 @@ __device__ __forceinline__ void reset_game_inl(const DevConfig &cfg, const WarpM
         int i0, i1;
         if (src.setup_idx) { i0 = src.setup_idx[0]; i1 = src.setup_idx[1]; }
         else {
-            const uint4 rnd = philox4x32_10(make_uint4(uint32_t(gid), uint32_t(gid >> 32), RNG_RESET, episode), key);
+            const uint4 rnd = philox4x32_10(make_uint4(uint32_t(gid), uint32_t(gid >> 32), RNG_RESET + 64u * src.attempt, src.rng_episode), key);
             i0 = int(__umulhi(rnd.x, uint32_t(src.n_setups)));  // util:313-314: two independent uniform draws
             i1 = int(__umulhi(rnd.y, uint32_t(src.n_setups)));
         }
@@ -738,10 +744,21 @@ __device__ __forceinline__ void reset_game_inl(const DevConfig &cfg, const WarpM
         place_side<GT>(cfg, m, src.setups + size_t(i1) * cfg.setup_len, 1);
     }
     GT::sync();
+    if (src.other_side) {  // impl:646-675 on the fresh board: rotate 180 degrees, swap the owners
+        for (int i = lane; 2 * i < cfg.N; i += GT::L) {
+            const int j = cfg.N - 1 - i;
+            uint32_t x = m.board[i], y = m.board[j];
+            if (x & CELL_RANK) x ^= CELL_OWNER;
+            if (y & CELL_RANK) y ^= CELL_OWNER;
+            if (i == j) m.board[i] = uint8_t(x);
+            else { m.board[i] = uint8_t(y); m.board[j] = uint8_t(x); }
+        }
+        GT::sync();
+    }
     a.turn = 0;
     a.max_turns = cfg.max_turns;  // impl:247
     a.over = 0; a.invalid = 0; a.winner = 0;
-    a.to_move = 0;                // maenv:546
+    a.to_move = src.other_side ? 1 : 0;  // maenv:546 / maenv:534
     a.rfrom[0] = a.rfrom[1] = NO_CELL;
     a.rto[0] = a.rto[1] = NO_CELL;
     a.rcode[0] = a.rcode[1] = 0;
@@ -751,15 +768,17 @@ __device__ __forceinline__ void reset_game_inl(const DevConfig &cfg, const WarpM
 }
 
 // Out-of-line entry: re-sets the game staged in the warp slice at `warp_base`, returns the packed aux words.
+// `draw` packs attempt (bits 0-7), "other side" (bit 8) and "shuffle" (bit 9).
 template <class GT>
 static __device__ __noinline__ uint4 reset_game(const DevConfig *cfg, uint8_t *warp_base, const uint8_t *setups, int n_setups,
-                                         const int32_t *setup_idx, int shuffle, uint2 key, uint64_t gid, uint32_t episode)
+                                         const int32_t *setup_idx, uint32_t draw, uint2 key, uint64_t gid, uint32_t episode,
+                                         uint32_t rng_episode)
 {
     WarpMem m;
     carve_warp(*cfg, warp_base, &m);
     Aux a{};
     a.episode = episode;
-    const ResetSource src{setups, n_setups, setup_idx, shuffle != 0};
+    const ResetSource src{setups, n_setups, setup_idx, (draw & 512u) != 0, rng_episode, draw & 255u, (draw & 256u) != 0};
     reset_game_inl<GT>(*cfg, m, a, src, key, gid);
     uint32_t w[4];
     aux_pack(a, w);

@@ -94,6 +94,47 @@ __device__ __noinline__ bool gen_moves_cold(const DevConfig *cfg, uint8_t *warp_
     return gen_moves<K, GT>(*cfg, m, a, me, false);
 }
 
+// Both players' observations of the game staged in the warp slice (its final position) into the terminal side buffers
+// [env][player index 0 / 1][R][C][channels], same "background by TMA + sparse entries" rendering as the regular outputs.
+// Out of line: a game ends once in hundreds of steps.
+template <int K, class GT>
+static __device__ __noinline__ void render_terminal(const KernelArgs *args, const float *bg_po, const float *bg_fo,
+                                                    uint8_t *warp_base, uint4 auxw, long long env, bool original)
+{
+    const DevConfig &cfg = args->cfg;
+    WarpMem m;
+    carve_warp(cfg, warp_base, &m);
+    const uint32_t w[4] = {auxw.x, auxw.y, auxw.z, auxw.w};
+    Aux a;
+    aux_unpack(w, a);
+    const ObsMap pom = original ? po_map_original() : po_map(), fom = original ? fo_map_original() : fo_map();
+    const uint64_t pol = l2_policy(0);
+    float *tpo = args->out.terminal_partial_obs, *tfo = args->out.terminal_full_obs;
+#pragma unroll 1
+    for (int side = 0; side < 2; ++side) {
+        float *gpo = tpo ? tpo + (env * 2 + side) * cfg.po_floats : nullptr;
+        float *gfo = tfo ? tfo + (env * 2 + side) * cfg.fo_floats : nullptr;
+        if (gpo) {
+            const int k = align_rows(pom.channels, int((reinterpret_cast<uintptr_t>(gpo) >> 2) & 3));
+            emit_tile<GT>(reinterpret_cast<uint8_t *>(gpo), reinterpret_cast<const uint8_t *>(bg_po + k * pom.channels), cfg.po_floats * 4, pol);
+        }
+        if (gfo) {
+            const int k = align_rows(fom.channels, int((reinterpret_cast<uintptr_t>(gfo) >> 2) & 3));
+            emit_tile<GT>(reinterpret_cast<uint8_t *>(gfo), reinterpret_cast<const uint8_t *>(bg_fo + k * fom.channels), cfg.fo_floats * 4, pol);
+        }
+        if (GT::lane() == 0) { bulk_commit(); bulk_wait_all(); }
+        GT::sync();
+        if (original) {
+            if (gpo) patch_obs<K, GT, true>(cfg, m, a, gpo, pom, side, pol);
+            if (gfo) patch_obs<K, GT, true>(cfg, m, a, gfo, fom, side, pol);
+        } else {
+            if (gpo) patch_obs<K, GT>(cfg, m, a, gpo, pom, side, pol);
+            if (gfo) patch_obs<K, GT>(cfg, m, a, gfo, fom, side, pol);
+        }
+        GT::sync();
+    }
+}
+
 // MODE fixes the op set at compile time so that each hot launch type carries only its own code (the
 // whole fused body is ~290 KB of SASS when everything is runtime-selected, far beyond the I-cache):
 enum { MODE_GENERIC = 0, MODE_STEP_PO_MASK = 1, MODE_STEP_PO_FO_MASK = 2, MODE_STEP_LEAN = 3, MODE_MASK = 4, MODE_OBSERVE_PO_MASK = 5 };
@@ -285,11 +326,17 @@ __global__ void __launch_bounds__(K <= 2 ? 1024 : SX_MAX_THREADS, 1) sx_fused_ke
 
         bool dirty = false;
         // out-of-line helpers take and return everything by value so that `a` never has to live in local memory
-        auto do_reset = [&]() {
+        // (Re)starts the game: episode number `episode` (games this env has started so far), draw number `attempt`.
+        // maenv:530-534: every second game repeats the previous setup seen from the other side; maenv:352-354: one setup
+        // for every game of this env.  Both are choices of WHICH Philox counter the draw uses (ResetSource).
+        auto do_reset = [&](uint32_t episode, int attempt) {
             GT::sync();
+            const bool other_side = (flags & SX_REPEAT_OTHER_SIDE) && (episode & 1u);
+            const uint32_t rng_episode = (flags & SX_SAME_SETUP) ? 0u : other_side ? episode - 1u : episode;
+            const uint32_t draw = uint32_t(attempt) | (other_side ? 256u : 0u) | ((flags & SX_RESET_RANDOM_SHUFFLE) ? 512u : 0u);
             const uint4 nw = reset_game<GT>(&cfg, warp_base, args.setups, args.n_setups,
-                                        args.setup_idx ? args.setup_idx + env * 2 : nullptr,
-                                        (flags & SX_RESET_RANDOM_SHUFFLE) != 0, args.key, gid, a.episode);
+                                        args.setup_idx ? args.setup_idx + env * 2 : nullptr, draw, args.key, gid, episode,
+                                        rng_episode);
             const uint32_t w[4] = {nw.x, nw.y, nw.z, nw.w};
             aux_unpack(w, a);
         };
@@ -301,8 +348,9 @@ __global__ void __launch_bounds__(K <= 2 ? 1024 : SX_MAX_THREADS, 1) sx_fused_ke
         };
         if (MODE == MODE_GENERIC && (ops & OP_RESET) && (args.reset_mask == nullptr || args.reset_mask[env] != 0)) {
             // drawn setups only (explicit setup_idx rows are the caller's choice): see the auto-reset below
+            const uint32_t episode = a.episode;
             for (int tries = 0; tries < MAX_REDRAWS; ++tries) {
-                do_reset();
+                do_reset(episode, tries);
                 if (args.setup_idx != nullptr || regen_moves(a.to_move)) break;
             }
             dirty = true;
@@ -350,12 +398,21 @@ __global__ void __launch_bounds__(K <= 2 ? 1024 : SX_MAX_THREADS, 1) sx_fused_ke
             cnt.count_step(status, done, a);
         }
 
+        // maenv:772-773 hands BOTH players their observation of the finished game; with auto-reset the regular outputs
+        // already show the next game, so the terminal observations go to side buffers (cold path).
+        if (done && (args.out.terminal_partial_obs != nullptr || args.out.terminal_full_obs != nullptr)) {
+            uint32_t w[4];
+            aux_pack(a, w);
+            GT::sync();
+            render_terminal<K, GT>(&args, bg.po, bg.fo, warp_base, make_uint4(w[0], w[1], w[2], w[3]), env, original);
+        }
         if (done && (flags & SX_AUTO_RESET)) {
             // A drawn setup in which the player to move has no move cannot be played in the reference either (the only
             // entry of its mask is the noop, which maenv.step rejects: impl:316-347 decodes it to an illegal move), so
-            // such a draw -- 2e-6 of Standard shuffles, none of the human tables -- is drawn again (next episode number).
+            // such a draw -- 2e-6 of Standard shuffles, none of the human tables -- is drawn again (next attempt number).
+            const uint32_t episode = a.episode;
             for (int tries = 0; tries < MAX_REDRAWS; ++tries) {
-                do_reset();
+                do_reset(episode, tries);
                 cnt.resets += 1;
                 viewer = a.to_move;
                 if (!need_moves) break;
@@ -510,6 +567,7 @@ __global__ void __launch_bounds__(512, 1) sx_toy_kernel(const __grid_constant__ 
         StepStatus status = STEP_ILLEGAL;
         bool done = false;
         int viewer = 0, total = 0;
+        uint32_t reset_episode = 0;
         // Move generation is ONE inlined copy run up to three times: pass 0 only for a noop action (legal only when
         // nothing else is, impl:809-814), pass 1 for the next player (stuck check, impl:1031-1036), pass 2 for the fresh
         // game of an auto-reset.
@@ -529,7 +587,9 @@ __global__ void __launch_bounds__(512, 1) sx_toy_kernel(const __grid_constant__ 
             }
             if (pass >= 2) {  // fresh game: an unplayable draw (first player without a move) is drawn again, see sx_fused_kernel
                 if (total > 0 || pass - 1 >= MAX_REDRAWS) break;
-                toy::reset_game(cfg, s, a, args.setups, args.n_setups, (flags & SX_RESET_RANDOM_SHUFFLE) != 0, args.key, gid);
+                a.episode = reset_episode;
+                toy::reset_game(cfg, s, a, args.setups, args.n_setups, (flags & SX_RESET_RANDOM_SHUFFLE) != 0, args.key, gid,
+                                (flags & SX_SAME_SETUP) ? 0u : reset_episode, uint32_t(pass - 1));
                 cnt.resets += 1;
                 viewer = a.to_move;
                 continue;
@@ -553,7 +613,9 @@ __global__ void __launch_bounds__(512, 1) sx_toy_kernel(const __grid_constant__ 
             if (args.out.reward) args.out.reward[env] = (done && !a.invalid) ? float(w) : 0.0f;  // maenv:777-801
             cnt.count_step(status, done, a);
             if (!(done && (flags & SX_AUTO_RESET))) break;
-            toy::reset_game(cfg, s, a, args.setups, args.n_setups, (flags & SX_RESET_RANDOM_SHUFFLE) != 0, args.key, gid);
+            reset_episode = a.episode;
+            toy::reset_game(cfg, s, a, args.setups, args.n_setups, (flags & SX_RESET_RANDOM_SHUFFLE) != 0, args.key, gid,
+                            (flags & SX_SAME_SETUP) ? 0u : reset_episode, 0u);
             cnt.resets += 1;
             viewer = a.to_move;
         }
@@ -1057,7 +1119,8 @@ static int plan_launch_uncached(const sx_config *cfg, uint32_t ops, int mode, lo
 static bool toy_eligible(const sx_config *cfg, const KernelArgs &a, int mode)
 {
     const DevConfig &d = cfg->dev;
-    if (env_int("SX_TOY", 1) == 0 || (a.flags & SX_KERNEL_BASELINE)) return false;
+    if (env_int("SX_TOY", 1) == 0 || (a.flags & (SX_KERNEL_BASELINE | SX_REPEAT_OTHER_SIDE))) return false;
+    if (a.out.terminal_partial_obs || a.out.terminal_full_obs) return false;
     if (mode != MODE_STEP_PO_MASK && mode != MODE_STEP_PO_FO_MASK && mode != MODE_STEP_LEAN) return false;
     if (d.N > 16 || (d.N & 3) != 0 || d.A > 16 || d.board_stride != 16 || d.cap_stride != 8) return false;
     if (d.setup_len > 8 || d.n_pieces > 8 || d.original_channels) return false;
@@ -1159,6 +1222,8 @@ static int launch_fused(const sx_config *cfg, KernelArgs &args, cudaStream_t str
         if (o.illegal) o.illegal += whole;
         if (o.player) o.player += whole;
         if (o.next_action) o.next_action += whole;
+        if (o.terminal_partial_obs) o.terminal_partial_obs += whole * 2 * cfg->dev.po_floats;
+        if (o.terminal_full_obs) o.terminal_full_obs += whole * 2 * cfg->dev.fo_floats;
     }
     if (int rc = plan_launch(cfg, args.ops, mode, args.num_envs, &plan)) return rc;
     args.cfg = cfg->dev;
@@ -1199,7 +1264,7 @@ extern "C" int sx_reset(const sx_config *cfg, sx_state st, int64_t num_envs, int
     KernelArgs a;
     base_args(a, st, num_envs, env_base);
     a.ops = OP_RESET | OP_WRITE_STATE;
-    a.flags = flags & SX_RESET_RANDOM_SHUFFLE;
+    a.flags = flags & (SX_RESET_RANDOM_SHUFFLE | SX_SAME_SETUP | SX_REPEAT_OTHER_SIDE);
     a.setups = setups_d; a.n_setups = n_setups; a.setup_idx = setup_idx_d; a.reset_mask = reset_mask_d;
     a.key = make_key(seed);
     return launch_fused(cfg, a, static_cast<cudaStream_t>(stream));
@@ -1291,6 +1356,7 @@ extern "C" int sx_step(const sx_config *cfg, sx_state st, int64_t num_envs, cons
     a.flags = flags & SX_ALLOW_OSCILLATION;
     a.out = out;
     a.out.partial_obs = nullptr; a.out.full_obs = nullptr; a.out.valid_mask = nullptr; a.out.next_action = nullptr;
+    a.out.terminal_partial_obs = nullptr; a.out.terminal_full_obs = nullptr;
     a.ops = OP_STEP | OP_WRITE_STATE | OP_NEED_MOVES;
     return launch_fused(cfg, a, static_cast<cudaStream_t>(stream));
 }
@@ -1314,6 +1380,8 @@ extern "C" int sx_step_all(const sx_config *cfg, sx_state st, int64_t num_envs, 
     if (action_format != SX_ACTION_SPATIAL && action_format != SX_ACTION_1D) return fail("sx_step_all: unknown action format");
     if ((flags & SX_AUTO_RESET) && !(flags & SX_RESET_RANDOM_SHUFFLE) && (!setups_d || n_setups < 1))
         return fail("sx_step_all: auto-reset needs a setup table or SX_RESET_RANDOM_SHUFFLE");
+    if ((out.terminal_partial_obs && !out.partial_obs) || (out.terminal_full_obs && !out.full_obs))
+        return fail("sx_step_all: a terminal observation buffer needs its regular observation output in the same call");
     KernelArgs a;
     base_args(a, st, num_envs, env_base);
     a.actions = actions_d; a.action_format = action_format;
@@ -1491,6 +1559,8 @@ static sx_outputs offset_outputs(const DevConfig &d, const sx_outputs &o, int64_
     if (r.illegal) r.illegal += lo;
     if (r.player) r.player += lo;
     if (r.next_action) r.next_action += lo;
+    if (r.terminal_partial_obs) r.terminal_partial_obs += lo * 2 * d.po_floats;
+    if (r.terminal_full_obs) r.terminal_full_obs += lo * 2 * d.fo_floats;
     return r;
 }
 
@@ -1545,7 +1615,7 @@ extern "C" int sx_host_env_reset(sx_host_env *h, sx_outputs host_out)
         const int64_t lo = h->num_envs * c / h->n_chunks, hi = h->num_envs * (c + 1) / h->n_chunks;
         cudaStream_t s = h->streams[c % h->streams.size()];
         if (int rc = sx_reset(h->cfg, offset_state(h, lo), hi - lo, h->env_base + lo, nullptr, h->setups_d, h->n_setups, nullptr,
-                              h->seed, h->flags & SX_RESET_RANDOM_SHUFFLE, s))
+                              h->seed, h->flags & (SX_RESET_RANDOM_SHUFFLE | SX_SAME_SETUP | SX_REPEAT_OTHER_SIDE), s))
             return rc;
         sx_outputs o = offset_outputs(h->cfg->dev, h->dev, lo);
         KernelArgs a;

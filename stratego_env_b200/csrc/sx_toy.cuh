@@ -278,13 +278,14 @@ __device__ __forceinline__ void place_side(const DevConfig &cfg, State &s, unsig
 
 // util:13-30 with the warp-level kernel's Philox stream (shuffle_side in sx_device.cuh): draw k (0-based) of a side is
 // word k % 4 of Philox block k / 4; a side of at most 8 setup cells needs at most 7 draws = two blocks
-__device__ __forceinline__ unsigned long long shuffle_side(const DevConfig &cfg, uint2 key, uint64_t gid, uint32_t episode, int side)
+__device__ __forceinline__ unsigned long long shuffle_side(const DevConfig &cfg, uint2 key, uint64_t gid, uint32_t episode, int side,
+                                                           uint32_t attempt)
 {
     const int n = cfg.setup_len;
     uint32_t perm = 0x76543210u;  // perm[i] in nibble i
-    const uint4 r0 = philox4x32_10(make_uint4(uint32_t(gid), uint32_t(gid >> 32), RNG_SHUFFLE + uint32_t(side), episode), key);
+    const uint4 r0 = philox4x32_10(make_uint4(uint32_t(gid), uint32_t(gid >> 32), RNG_SHUFFLE + uint32_t(side) + 64u * attempt, episode), key);
     uint4 r1 = make_uint4(0, 0, 0, 0);
-    if (n > 5) r1 = philox4x32_10(make_uint4(uint32_t(gid), uint32_t(gid >> 32), RNG_SHUFFLE + uint32_t(side) + 2u, episode), key);
+    if (n > 5) r1 = philox4x32_10(make_uint4(uint32_t(gid), uint32_t(gid >> 32), RNG_SHUFFLE + uint32_t(side) + 2u + 64u * attempt, episode), key);
     const uint32_t draws[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
     int k = 0;
 #pragma unroll
@@ -318,8 +319,10 @@ __device__ __forceinline__ unsigned long long load_setup_row(const DevConfig &cf
 }
 
 // impl:213-249 + the setup samplers (reset_game_inl of the warp-level kernel)
+// rng_episode / attempt: see ResetSource (sx_device.cuh).  "Repeat from the other side" games do not come here (the launch
+// goes to the warp-level kernel).
 __device__ __forceinline__ void reset_game(const DevConfig &cfg, State &s, Aux &a, const uint8_t *setups, int n_setups, bool shuffle,
-                                           uint2 key, uint64_t gid)
+                                           uint2 key, uint64_t gid, uint32_t rng_episode, uint32_t attempt)
 {
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
@@ -332,9 +335,9 @@ __device__ __forceinline__ void reset_game(const DevConfig &cfg, State &s, Aux &
     const uint32_t episode = a.episode;
     if (shuffle || setups == nullptr) {
 #pragma unroll 1
-        for (int side = 0; side < 2; ++side) place_side(cfg, s, shuffle_side(cfg, key, gid, episode, side), side);
+        for (int side = 0; side < 2; ++side) place_side(cfg, s, shuffle_side(cfg, key, gid, rng_episode, side, attempt), side);
     } else {
-        const uint4 rnd = philox4x32_10(make_uint4(uint32_t(gid), uint32_t(gid >> 32), RNG_RESET, episode), key);
+        const uint4 rnd = philox4x32_10(make_uint4(uint32_t(gid), uint32_t(gid >> 32), RNG_RESET + 64u * attempt, rng_episode), key);
         const int i0 = int(__umulhi(rnd.x, uint32_t(n_setups))), i1 = int(__umulhi(rnd.y, uint32_t(n_setups)));
         place_side(cfg, s, load_setup_row(cfg, setups + size_t(i0) * cfg.setup_len), 0);
         place_side(cfg, s, load_setup_row(cfg, setups + size_t(i1) * cfg.setup_len), 1);

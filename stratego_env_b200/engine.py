@@ -136,7 +136,9 @@ class StrategoEngine:
         cap = buf[pad(board_b) + pad(aux_b):pad(board_b) + pad(aux_b) + cap_b].view(torch.int16).view(num_envs, lay.captured_stride)
         return DeviceState(board, aux, cap)
 
-    def alloc_outputs(self, num_envs: int, partial=True, full=False, mask=True, sample=False) -> dict:
+    def alloc_outputs(self, num_envs: int, partial=True, full=False, mask=True, sample=False, terminal=False) -> dict:
+        """terminal=True adds the side buffers that receive BOTH players' observations of a game that ends during
+        ``step_all`` (maenv:772-773): [B, 2, R, C, channels], index 0 = player +1's view; rows of games with done = 1"""
         d, R, Cc = self.device, self.rows, self.columns
         out = {
             "reward": torch.zeros(num_envs, dtype=torch.float32, device=d),
@@ -154,6 +156,10 @@ class StrategoEngine:
             out["valid_mask"] = torch.empty((num_envs, R, Cc, self.spatial_channels), dtype=torch.uint8, device=d)
         if sample:
             out["next_action"] = torch.zeros(num_envs, dtype=torch.int32, device=d)
+        if terminal and partial:
+            out["terminal_partial_obs"] = torch.zeros((num_envs, 2, R, Cc, self.po_channels), dtype=torch.float32, device=d)
+        if terminal and full:
+            out["terminal_full_obs"] = torch.zeros((num_envs, 2, R, Cc, self.fo_channels), dtype=torch.float32, device=d)
         return out
 
     @staticmethod
@@ -173,8 +179,12 @@ class StrategoEngine:
 
     # ---- operations ----------------------------------------------------------------------------
     def reset(self, state: DeviceState, seed: int = 0, env_base: int = 0, reset_mask: Optional[torch.Tensor] = None,
-              setups: Optional[torch.Tensor] = None, setup_idx: Optional[torch.Tensor] = None, shuffle: bool = False):
-        flags = _lib.SX_RESET_RANDOM_SHUFFLE if shuffle else 0
+              setups: Optional[torch.Tensor] = None, setup_idx: Optional[torch.Tensor] = None, shuffle: bool = False,
+              same_setup: bool = False, repeat_other_side: bool = False):
+        """same_setup: every game of an env starts from its first draw (maenv:352-354); repeat_other_side: every second
+        game of an env repeats the previous initial position from the other side (maenv:530-534)"""
+        flags = ((_lib.SX_RESET_RANDOM_SHUFFLE if shuffle else 0) | (_lib.SX_SAME_SETUP if same_setup else 0) |
+                 (_lib.SX_REPEAT_OTHER_SIDE if repeat_other_side else 0))
         if setup_idx is not None:
             assert setup_idx.dtype == torch.int32 and setup_idx.shape == (state.num_envs, 2) and setup_idx.is_contiguous()
         if reset_mask is not None:
@@ -264,13 +274,15 @@ class StrategoEngine:
     def step_all(self, state: DeviceState, actions: torch.Tensor, out: dict, one_d: bool = False, env_base: int = 0,
                  auto_reset: bool = False, sample_next: bool = False, allow_piece_oscillation: bool = False,
                  setups: Optional[torch.Tensor] = None, shuffle: bool = False, seed: int = 0,
-                 stats: Optional[torch.Tensor] = None, baseline_kernel: bool = False) -> dict:
+                 stats: Optional[torch.Tensor] = None, baseline_kernel: bool = False, same_setup: bool = False,
+                 repeat_other_side: bool = False) -> dict:
         """baseline_kernel=True runs the general warp-per-game kernel even where a specialised kernel is eligible
         (identical results; the cross-kernel parity tests use it)."""
         assert actions.dtype == torch.int32 and actions.is_contiguous() and actions.shape == (state.num_envs,)
         flags = ((_lib.SX_AUTO_RESET if auto_reset else 0) | (_lib.SX_SAMPLE_NEXT if sample_next else 0) |
                  (_lib.SX_ALLOW_OSCILLATION if allow_piece_oscillation else 0) |
-                 (_lib.SX_RESET_RANDOM_SHUFFLE if shuffle else 0) | (_lib.SX_KERNEL_BASELINE if baseline_kernel else 0))
+                 (_lib.SX_RESET_RANDOM_SHUFFLE if shuffle else 0) | (_lib.SX_KERNEL_BASELINE if baseline_kernel else 0) |
+                 (_lib.SX_SAME_SETUP if same_setup else 0) | (_lib.SX_REPEAT_OTHER_SIDE if repeat_other_side else 0))
         if stats is not None:
             assert stats.dtype == torch.int64 and stats.numel() >= 8
         with torch.cuda.device(self.device):

@@ -10,7 +10,7 @@
 //   thp         mmap + madvise(MADV_HUGEPAGE) + first touch + cudaHostRegister  (2 MiB pages: fewer IOMMU entries)
 //   numa        like thp, first-touched after binding the process to the CPUs of the GPU's NUMA node (sysfs), when the
 //               box exposes more than one node
-// usage: probe_d2h [gib_per_gpu=4] [max_gpus=8]
+// usage: probe_d2h [gib_per_gpu=4] [max_gpus=8] [quick=0]   (quick: fewer combinations -- every GPU count costs box time)
 #include <cuda_runtime.h>
 #include <sched.h>
 #include <sys/mman.h>
@@ -119,6 +119,7 @@ int main(int argc, char **argv)
 {
     const double gib = argc > 1 ? atof(argv[1]) : 4.0;
     const int max_gpus = argc > 2 ? atoi(argv[2]) : 8;
+    const bool quick = argc > 3 && atoi(argv[3]) != 0;
     const size_t bytes = size_t(gib * 1024.0 * 1024.0 * 1024.0);
     // the device count must be learnt WITHOUT creating a CUDA context in the parent (children fork below)
     int n_dev = 0;
@@ -141,6 +142,9 @@ int main(int argc, char **argv)
         for (int n = 1; n <= std::min(n_dev, max_gpus); n *= 2) {
             for (int mode = 0; mode < N_MODES; ++mode) {
                 if (direction == 1 && mode != HOSTALLOC && mode != THP) continue;
+                const bool top = n * 2 > std::min(n_dev, max_gpus);  // the largest GPU count of the sweep
+                if (quick && direction == 1 && !(top && mode == HOSTALLOC)) continue;
+                if (quick && direction == 0 && (mode == WC || mode == NUMA) && !top) continue;
                 new (sh) Shared();
                 sh->ready = 0;
                 sh->go = 0;
