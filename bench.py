@@ -466,9 +466,21 @@ def run_gpu_arm(args):
                     "h2d_bytes_per_step": h2d * world, "d2h_bytes_per_step": d2h * world, "steps": e2e_steps,
                     "envs_per_gpu": e2e_B, "d2h_GBps_aggregate": d2h * world * e2e_steps / secs / 1e9, "what": what}
 
-        e2e = one(True, "HostBufferEnv.step (sx_host_env_step): int32 actions from pinned host memory, every output "
+        def link(entry):
+            """what the box's host link can do with bare copies at this GPU count (profiles/host_link.json)"""
+            try:
+                with open(os.path.join(ROOT, "profiles", "host_link.json")) as f:
+                    probe = json.load(f)["d2h_GBps"].get(str(world))
+            except (OSError, ValueError, KeyError):
+                probe = None
+            if probe:
+                entry["host_link"] = {"bare_copy_d2h_GBps": probe, "fraction_of_bare_copy": entry["d2h_GBps_aggregate"] / probe,
+                                      "source": "tools/probes/probe_d2h.cu, profiles/host_link.json"}
+            return entry
+
+        e2e = link(one(True, "HostBufferEnv.step (sx_host_env_step): int32 actions from pinned host memory, every output "
                         "(obs, mask, reward, done, winner, flags, sampled action) copied back to pinned host memory, "
-                        "pipelined chunks; bound by the host link (profiles/: tools/probes/probe_d2h.cu)")
+                        "pipelined chunks; bound by the host link (profiles/: tools/probes/probe_d2h.cu)"))
         # the same call when the consumer of obs/mask is on the GPU (a policy network): only the per-game scalars
         # cross PCIe.  Reported for context; `e2e` above is the contract's number.
         e2e_device_obs = one(False, "same call (4 chunks), observations and mask stay in HBM; actions H2D, scalars D2H")

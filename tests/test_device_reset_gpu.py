@@ -191,8 +191,13 @@ def test_unplayable_draws_are_drawn_again():
     eng.reset(st, seed=1, setups=setups)
     mask = eng.valid_mask(st).reshape(B, -1)
     assert (mask[:, eng.spatial_channels - 1] == 0).all().item(), "a freshly drawn game has a noop-only mask"
+    # the unplayable row IS drawn (player -1 keeps it: that side never has to move first), but never for player +1;
+    # re-drawing uses an attempt number inside the Philox counter and leaves the episode numbering alone
+    dense, _ = (x.cpu().numpy() for x in eng.export_ref_state(st))
+    p1_pieces, p2_pieces = (dense[:, 0] != 0).sum(axis=(1, 2)), (dense[:, 1] != 0).sum(axis=(1, 2))
+    assert (p1_pieces == 8).all() and (p2_pieces == 2).sum() > B // 32 and set(np.unique(p2_pieces)) == {2, 8}
     episode = st.aux.cpu().numpy().view(np.uint16)[:, 6:8].copy().view(np.uint32).reshape(-1)
-    assert (episode >= 1).all() and (episode > 1).sum() > B // 32  # 1/16 of the first draws were unplayable
+    assert (episode == 1).all()
     # same inside the fused step: play until many games ended, no game may ever show a noop-only mask at turn 0
     out = eng.alloc_outputs(B, partial=True, full=False, mask=True, sample=True)
     eng.observe(st, out=out, partial=True, full=False, mask=True)
