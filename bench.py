@@ -47,6 +47,9 @@ WORKLOADS = {
                  desc="Octa-Barrage 8x8, 512k envs/GPU, random-valid self-play, shuffled setups, PO obs + mask"),
     "standard": dict(version="standard", table="standard", envs=524288, full=False, dephase=3000,
                      desc="Standard 10x10 (40 pieces/side), 512k envs/GPU, human setup table, PO obs + mask"),
+    "standard2": dict(version="standard2", table=None, envs=131072, full=False, dephase=2500,
+                      desc="Standard2 15x15 (3 colonels + flag per side), 128k envs/GPU, shuffled setups, PO obs + mask "
+                           "(8 cells per lane; not a BASELINE configuration)"),
     "standard_both": dict(version="standard", table="standard", envs=262144, full=True, dephase=3000,
                           desc="Standard 10x10, 256k envs/GPU, PO + full obs + mask"),
 }

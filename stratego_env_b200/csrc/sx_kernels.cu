@@ -512,7 +512,8 @@ __global__ void __launch_bounds__(512, 1) sx_toy_kernel(const __grid_constant__ 
     const int po_bytes = do_po ? cfg.po_floats * 4 : 0, fo_bytes = do_fo ? cfg.fo_floats * 4 : 0;
     const int tile_stride = po_bytes + fo_bytes;
     // the warp's two observation tiles hold the background image for the whole launch
-    constexpr int T = 2;  // tiles per warp (4 or 8 tiles with fewer warps were slower, profiles/r1l_toy_sweeps.txt)
+    constexpr int T = 2;  // tiles per warp (4 or 8 tiles with fewer warps were slower, profiles/r1l_toy_sweeps.txt; rendering
+                          // two games per pass, one per half-warp, was bit-exact and 8 % slower, profiles/r2g_*)
     uint32_t undo_po[T], undo_fo[T];
 #pragma unroll
     for (int h = 0; h < T; ++h) undo_po[h] = undo_fo[h] = toy::UNDO_NONE;
@@ -1088,7 +1089,7 @@ static int plan_launch_uncached(const sx_config *cfg, uint32_t ops, int mode, lo
     // 10x10: about 300 KB of output in flight per SM, in multiples of 4 warps.
     const int small_board = std::max(8, std::min(32, ((300 * 1024 / std::max(1, tile_bytes)) + 2) / 4 * 4));
     const int preferred = tile_bytes <= 8 * 1024 ? 32 : tile_bytes <= 32 * 1024 ? (cfg->dev.N >= 100 ? 8 : small_board)
-                          : tile_bytes <= 64 * 1024 ? 6 : 4;
+                          : tile_bytes <= 64 * 1024 ? 6 : 10;  // 15x15 (74 KB per game): 4 warps 39 M, 6: 55 M, 8: 69 M, 10: 75 M env-steps/s
     int warps = std::min(max_warps, std::max(1, env_int("SX_WARPS", std::min(max_warps, preferred))));
     const int games = cfg->games_per_warp;  // each game of a warp has its own slice
     while (warps > 1 && tile_bytes + warps * games * warp_bytes > max_smem_optin) --warps;

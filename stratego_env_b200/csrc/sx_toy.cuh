@@ -448,3 +448,4 @@ __device__ __forceinline__ uint32_t patch_tile(const DevConfig &cfg, const uint8
 
 }  // namespace toy
 }  // namespace sx
+
