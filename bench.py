@@ -1,19 +1,23 @@
 #!/usr/bin/env python
 """Benchmark of the hot path: env-steps/s of the fused step (mask + step + obs + auto-reset).
 
-    python bench.py --gpus N --steps K --warmup W [--workload barrage|micro|tiny|fives|medium|octa|standard|standard_both]
+    python bench.py --gpus N --steps K --warmup W [--workload barrage|micro|tiny|fives|medium|octa|standard|standard_both|standard2]
     python bench.py --impl reference ...      # the CPU restatement of the reference on the host cores
 
 One "step" = one pass of the fused kernel over every game of the batch: each game applies one
 uniformly sampled valid action, is re-set if it ended, and emits the next player's spatial
 valid-action mask and partial observation.  Prints ONE JSON line on rank 0.
+The headline workload is BASELINE configs[2] (Barrage, 256k games per GPU); the other configurations -- micro
+(configs[1]), standard 512k games per GPU (configs[3]) and the conv-policy rollout (configs[4], PO and PO + full) -- run
+in the same process on every rank and are summarised under `other_workloads` (--also).
 
   value      device-resident throughput: actions, state and outputs live in HBM; CUDA events on the
              launching stream; max over ranks.
   e2e        the same step through the C ABI's host-buffer object (sx_host_env_step): actions come from
              pinned HOST memory and every output (obs, mask, reward, done, ...) is copied back to pinned
              HOST memory inside the timed region.
-  roofline   algorithmic bytes per launch / measured launch duration vs the measured HBM peak.
+  roofline   algorithmic bytes per launch / measured launch duration vs the measured HBM peak; `traffic` = DRAM bytes of
+             a full-size launch measured with ncu (profiles/traffic.json).
   cpu_baseline  oracle/ (C restatement of the reference, test infrastructure) timed on the host cores.
 """
 import argparse

@@ -5,7 +5,7 @@
     torchrun --nproc-per-node 8 examples/rollout_conv_policy.py --envs 524288      # one process per GPU
 
 Per step, all on the GPU: observation [B,R,C,67] (a channels-last NCHW view, no copy) -> conv policy -> logits
-[B,R,C,A] -> masked-logit sampling kernel (sx_sample_logits) -> fused env step (sx_step_all).  The counterpart of
+[B,R,C,A] -> masked categorical draw straight from the game state (sx_sample_policy) -> fused env step (sx_step_all).  The counterpart of
 the reference's examples/basic_game_loop.py, where the chooser and the env run on the CPU one game at a time.
 """
 import argparse

@@ -47,6 +47,14 @@ TRAJECTORY_PLAN = {
 }
 
 
+# more games of the two benchmark variants, recorded with other seeds into files of their own (label -> (variant, games,
+# human_inits, max recorded steps, seed)); the first-round files above stay byte-identical
+DEEP_PLAN = {
+    "standard_b": ("standard", 3, True, 5200, 2001),
+    "barrage_b": ("barrage", 6, True, 3200, 2002),
+}
+
+
 def pack_mask(mask):
     return np.packbits(np.asarray(mask, dtype=np.uint8).reshape(-1))
 
@@ -575,6 +583,15 @@ def spatial_alias_vectors(se):
 def main():
     se = import_reference()
     os.makedirs(OUT_DIR, exist_ok=True)
+    if "--deep-only" in sys.argv:  # adds traj_<label>.npz for DEEP_PLAN
+        for label, (version, n_games, human, max_steps, seed) in DEEP_PLAN.items():
+            data = record_trajectories(se, version, n_games, human, max_steps, seed=seed)
+            path = os.path.join(OUT_DIR, "traj_%s.npz" % label)
+            np.savez_compressed(path, **data)
+            print("%-16s steps=%5d obs=%4d terminal=%3d  %7.1f KB" % (
+                label, len(data["actions_spatial"]), len(data["obs_step"]), len(data.get("term_step", [])) // 2,
+                os.path.getsize(path) / 1024))
+        return
     if "--spatial-alias-only" in sys.argv:  # adds spatial_alias.npz from the committed trajectories
         data = spatial_alias_vectors(se)
         path = os.path.join(OUT_DIR, "spatial_alias.npz")
@@ -629,6 +646,9 @@ def main():
     path = os.path.join(OUT_DIR, "spatial_alias.npz")
     np.savez_compressed(path, **data)
     print("spatial_alias.npz %7.1f KB (%d arrays)" % (os.path.getsize(path) / 1024, len(data)))
+    for label, (version, n_games, human, max_steps, seed) in DEEP_PLAN.items():
+        data = record_trajectories(se, version, n_games, human, max_steps, seed=seed)
+        np.savez_compressed(os.path.join(OUT_DIR, "traj_%s.npz" % label), **data)
 
 
 if __name__ == "__main__":

@@ -168,9 +168,8 @@ class BatchedStrategoEnv:
             infos["terminal_observation"] = {1: {k: v[:, 0] for k, v in term.items()}, -1: {k: v[:, 1] for k, v in term.items()}}
         obs = self._obs()
         if self.random_player_assignment and self.auto_reset:
-            # the games that ended have been re-set inside the kernel: their next game gets a fresh agent map (the obs
-            # returned above still carries the old map's `player` for ... no: the observation already belongs to the
-            # NEW game, so its `player` must use the new map)
+            # games that ended were re-set inside the kernel and the returned observation already belongs to their NEXT
+            # game: that game gets a fresh agent map (maenv:537-543), and its `player` is expressed in it
             self._draw_player_map(dones != 0)
             obs["player"] = self.out["player"] * self.player_map
         return obs, rewards, dones, infos

@@ -349,6 +349,7 @@ __global__ void __launch_bounds__(K <= 2 ? 1024 : SX_MAX_THREADS, 1) sx_fused_ke
         if (MODE == MODE_GENERIC && (ops & OP_RESET) && (args.reset_mask == nullptr || args.reset_mask[env] != 0)) {
             // drawn setups only (explicit setup_idx rows are the caller's choice): see the auto-reset below
             const uint32_t episode = a.episode;
+#pragma unroll 1
             for (int tries = 0; tries < MAX_REDRAWS; ++tries) {
                 do_reset(episode, tries);
                 if (args.setup_idx != nullptr || regen_moves(a.to_move)) break;
@@ -411,6 +412,7 @@ __global__ void __launch_bounds__(K <= 2 ? 1024 : SX_MAX_THREADS, 1) sx_fused_ke
             // entry of its mask is the noop, which maenv.step rejects: impl:316-347 decodes it to an illegal move), so
             // such a draw -- 2e-6 of Standard shuffles, none of the human tables -- is drawn again (next attempt number).
             const uint32_t episode = a.episode;
+#pragma unroll 1  // (unrolled eight times this loop alone made the hot kernels 20 % bigger and the small boards 15-25 % slower)
             for (int tries = 0; tries < MAX_REDRAWS; ++tries) {
                 do_reset(episode, tries);
                 cnt.resets += 1;
@@ -580,19 +582,21 @@ __global__ void __launch_bounds__(512, 1) sx_toy_kernel(const __grid_constant__ 
                 cnt.attacks += (status == STEP_MOVED && (end_before & CELL_RANK) != 0) ? 1 : 0;
                 viewer = a.to_move;
             }
+            if (pass >= 2) {  // (re)draw the fresh game: attempt pass - 2 of episode reset_episode (ONE inlined copy of the reset)
+                a.episode = reset_episode;
+                toy::reset_game(cfg, s, a, args.setups, args.n_setups, (flags & SX_RESET_RANDOM_SHUFFLE) != 0, args.key, gid,
+                                (flags & SX_SAME_SETUP) ? 0u : reset_episode, uint32_t(pass - 2));
+                cnt.resets += 1;
+                viewer = a.to_move;
+            }
             const int who = pass == 0 ? mover : viewer;
             total = toy::gen_moves(cfg, geo, s, a, who, false, mv);
             if (pass == 0) {
                 if (total > 0) move.bad = true;
                 continue;
             }
-            if (pass >= 2) {  // fresh game: an unplayable draw (first player without a move) is drawn again, see sx_fused_kernel
+            if (pass >= 2) {  // an unplayable draw (first player without a move) is drawn again, see sx_fused_kernel
                 if (total > 0 || pass - 1 >= MAX_REDRAWS) break;
-                a.episode = reset_episode;
-                toy::reset_game(cfg, s, a, args.setups, args.n_setups, (flags & SX_RESET_RANDOM_SHUFFLE) != 0, args.key, gid,
-                                (flags & SX_SAME_SETUP) ? 0u : reset_episode, uint32_t(pass - 1));
-                cnt.resets += 1;
-                viewer = a.to_move;
                 continue;
             }
             if (status == STEP_MOVED) {
@@ -614,11 +618,7 @@ __global__ void __launch_bounds__(512, 1) sx_toy_kernel(const __grid_constant__ 
             if (args.out.reward) args.out.reward[env] = (done && !a.invalid) ? float(w) : 0.0f;  // maenv:777-801
             cnt.count_step(status, done, a);
             if (!(done && (flags & SX_AUTO_RESET))) break;
-            reset_episode = a.episode;
-            toy::reset_game(cfg, s, a, args.setups, args.n_setups, (flags & SX_RESET_RANDOM_SHUFFLE) != 0, args.key, gid,
-                            (flags & SX_SAME_SETUP) ? 0u : reset_episode, 0u);
-            cnt.resets += 1;
-            viewer = a.to_move;
+            reset_episode = a.episode;  // the next pass draws the new game
         }
         if (args.out.player) args.out.player[env] = viewer == 0 ? 1 : -1;
 

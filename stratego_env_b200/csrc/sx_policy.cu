@@ -113,15 +113,14 @@ __global__ void __launch_bounds__(256) sx_sample_logits_kernel(const T *logits, 
 // ---- the same draw straight from the game STATE ---------------------------------------------------------------------
 // sx_sample_logits streams the 1-byte mask (3 700 bytes per 10x10 game) to find the ~14-25 valid entries.  The mask is a
 // pure function of the compact state (~0.3 KB per game), so this kernel regenerates the mover's move sets from the state
-// with the engine's own move generator (gen_moves: occupancy bit-lines), lists the valid flat indices in shared memory
-// (balanced over the lanes: an entry costs a Philox block and two transcendentals, a scout would otherwise pile ten of
-// them on one lane) and runs the identical Gumbel-max / log-sum-exp per entry.  Same Philox key per (game, step, entry)
+// with the engine's own move generator (gen_moves: occupancy bit-lines), spreads the valid entries evenly over the lanes
+// and runs the identical Gumbel-max / log-sum-exp per entry.  Same Philox key per (game, step, entry)
 // and the same tie rule as the mask kernel, so both return the SAME action for the same key.
 template <typename T, int K, bool LOGPROB>
 __global__ void __launch_bounds__(256) sx_sample_policy_kernel(const __grid_constant__ DevConfig cfg, const uint8_t *board,
                                                                const int16_t *aux, long long num_envs, long long env_base,
                                                                const T *logits, uint2 key, uint32_t step, float inv_temperature,
-                                                               int32_t *actions, float *logprob, int warp_bytes, int list_cap)
+                                                               int32_t *actions, float *logprob, int warp_bytes)
 {
     using GT = Grp<1>;
     extern __shared__ __align__(16) uint8_t smem[];
@@ -131,7 +130,7 @@ __global__ void __launch_bounds__(256) sx_sample_policy_kernel(const __grid_cons
     uint8_t *warp_base = smem + size_t(warp) * warp_bytes;
     WarpMem m;
     const int slice = carve_warp(cfg, warp_base, &m);
-    uint16_t *list = reinterpret_cast<uint16_t *>(warp_base + slice);
+    uint16_t *before = reinterpret_cast<uint16_t *>(warp_base + slice);  // [N] running move count per cell
 
     const uint32_t *gb = reinterpret_cast<const uint32_t *>(board + env * cfg.board_stride);
     for (int i = lane; i < (cfg.board_stride >> 2); i += 32) reinterpret_cast<uint32_t *>(m.board)[i] = gb[i];
@@ -150,7 +149,10 @@ __global__ void __launch_bounds__(256) sx_sample_policy_kernel(const __grid_cons
         }
         return;
     }
-    // list the valid flat indices, ascending, at this lane's offset
+    // Balance the entries over the lanes (an entry costs a Philox block and two transcendentals; a scout would pile a
+    // dozen of them on one lane): moves are numbered 0 .. total-1 in ascending flat-index order, move t goes to lane
+    // t % 32.  A lane finds its move's cell by binary search in the per-cell running count (shared memory) and the
+    // channel as the r-th set bit of that cell's move set.
     int mine = 0;
 #pragma unroll
     for (int k = 0; k < K; ++k) {
@@ -164,15 +166,16 @@ __global__ void __launch_bounds__(256) sx_sample_policy_kernel(const __grid_cons
         if (lane >= off) incl += v;
     }
     const int total = __shfl_sync(FULL, incl, 31);
-    int pos = incl - mine;
-#pragma unroll 1
-    for (int k = 0; k < K; ++k) {
-        const int p = lane * K + k;
-        if (p >= cfg.N) break;
-        unsigned long long bits = (unsigned long long)m.moves[p].x | ((unsigned long long)m.moves[p].y << 32);
-#pragma unroll 1
-        for (; bits != 0; bits &= bits - 1, ++pos)
-            if (pos < list_cap) list[pos] = uint16_t(p * cfg.A + __ffsll((long long)bits) - 1);
+    {
+        int run = incl - mine;
+#pragma unroll
+        for (int k = 0; k < K; ++k) {
+            const int p = lane * K + k;
+            if (p < cfg.N) {
+                before[p] = uint16_t(run);  // moves in cells < p
+                run += __popc(m.moves[p].x) + __popc(m.moves[p].y);
+            }
+        }
     }
     __syncwarp();
 
@@ -180,28 +183,23 @@ __global__ void __launch_bounds__(256) sx_sample_policy_kernel(const __grid_cons
     const uint64_t gid = uint64_t(env_base + env);
     float best = -INFINITY, best_logit = 0.0f, run_max = -INFINITY, run_sum = 0.0f;
     int best_i = -1;
-    auto visit = [&](int i) {
+    for (int t = lane; t < total; t += 32) {  // ascending flat index within a lane, so `>` keeps the lowest index on ties
+        int lo = 0, hi = cfg.N;               // last cell p with before[p] <= t: the cell that holds move t
+        while (hi - lo > 1) {
+            const int mid = (lo + hi) >> 1;
+            if (int(before[mid]) <= t) lo = mid; else hi = mid;
+        }
+        const uint2 bits = m.moves[lo];
+        const int r = t - int(before[lo]), c0 = __popc(bits.x);
+        const int ch = r < c0 ? int(__fns(bits.x, 0, r + 1)) : 32 + int(__fns(bits.y, 0, r - c0 + 1));
+        const int i = lo * cfg.A + ch;
         const float z = load_logit<T>(lrow + i) * inv_temperature;
-        const uint4 r = philox4x32_10(make_uint4(uint32_t(gid), uint32_t(gid >> 32), RNG_POLICY ^ step, uint32_t(i)), key);
-        const float score = z - __logf(-__logf(uniform_open01(r.x)));
-        if (score > best || best_i < 0 || (score == best && i < best_i)) { best = score; best_i = i; best_logit = z; }
+        const uint4 rnd = philox4x32_10(make_uint4(uint32_t(gid), uint32_t(gid >> 32), RNG_POLICY ^ step, uint32_t(i)), key);
+        const float score = z - __logf(-__logf(uniform_open01(rnd.x)));
+        if (score > best || best_i < 0) { best = score; best_i = i; best_logit = z; }
         if (LOGPROB) {  // online log-sum-exp over the valid entries, only when the log-probability is asked for
             if (z > run_max) { run_sum = run_sum * __expf(run_max - z) + 1.0f; run_max = z; }
             else run_sum += __expf(z - run_max);
-        }
-    };
-    const int listed = min(total, list_cap);
-    for (int t = lane; t < listed; t += 32) visit(list[t]);
-    if (total > list_cap) {  // more moves than the list holds (never on stock boards): the owning lanes visit the rest
-        pos = incl - mine;
-#pragma unroll 1
-        for (int k = 0; k < K; ++k) {
-            const int p = lane * K + k;
-            if (p >= cfg.N) break;
-            unsigned long long bits = (unsigned long long)m.moves[p].x | ((unsigned long long)m.moves[p].y << 32);
-#pragma unroll 1
-            for (; bits != 0; bits &= bits - 1, ++pos)
-                if (pos >= list_cap) visit(p * cfg.A + __ffsll((long long)bits) - 1);
         }
     }
 #pragma unroll
@@ -266,13 +264,13 @@ static cudaError_t launch_policy(const sx_config *cfg, sx_state st, int64_t num_
 {
     using namespace sx;
     const DevConfig &d = cfg->dev;
-    const int wpb = 8, list_cap = 4 * d.N;
-    const int warp_bytes = carve_warp(d, nullptr, nullptr) + round16(list_cap * 2);
+    const int wpb = 8;
+    const int warp_bytes = carve_warp(d, nullptr, nullptr) + round16(d.N * 2);
     const unsigned grid = unsigned((num_envs + wpb - 1) / wpb);
     const size_t smem = size_t(wpb) * warp_bytes;
     auto launch = [&](auto kernel) {
         kernel<<<grid, wpb * 32, smem, s>>>(d, st.board, st.aux, num_envs, env_base, logits, key, step, inv_t, actions, logprob,
-                                            warp_bytes, list_cap);
+                                            warp_bytes);
     };
     const bool lp = logprob != nullptr;
     if (d.N <= 64) lp ? launch(sx_sample_policy_kernel<T, 2, true>) : launch(sx_sample_policy_kernel<T, 2, false>);

@@ -8,6 +8,16 @@ GOLDEN_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 VERSIONS = ["barrage", "standard", "short_standard", "short_barrage", "medium_standard", "octa_barrage",
             "standard2", "medium", "fives", "tiny", "micro"]
 
+# more recorded games of the two benchmark variants (other seeds, files of their own: oracle/gen_golden.py DEEP_PLAN)
+DEEP = {"standard_b": "standard", "barrage_b": "barrage"}
+TRAJ_LABELS = VERSIONS + sorted(DEEP)
+
+
+def variant_of(label):
+    """game variant a trajectory label was recorded on"""
+    return DEEP.get(label, label)
+
+
 _cache = {}
 
 

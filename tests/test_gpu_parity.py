@@ -6,7 +6,7 @@ import numpy as np
 import pytest
 import torch
 
-from _golden import VERSIONS, known, traj, transitions, unpack_mask
+from _golden import TRAJ_LABELS, VERSIONS, known, traj, transitions, unpack_mask, variant_of
 
 pytestmark = pytest.mark.gpu
 
@@ -14,13 +14,13 @@ pytestmark = pytest.mark.gpu
 def _engine(version, p2_rot180=True):
     from stratego_env_b200.config import VERSION_CONFIGS, as_version
     from stratego_env_b200.engine import StrategoEngine
-    return StrategoEngine(VERSION_CONFIGS[as_version(version)], device="cuda:0", p2_rot180=p2_rot180)
+    return StrategoEngine(VERSION_CONFIGS[as_version(variant_of(version))], device="cuda:0", p2_rot180=p2_rot180)
 
 
 def _oracle(version):
     from oracle.binding import OracleEnvLogic
     from stratego_env_b200.config import VERSION_CONFIGS, as_version
-    cfg = VERSION_CONFIGS[as_version(version)]
+    cfg = VERSION_CONFIGS[as_version(variant_of(version))]
     return OracleEnvLogic(cfg["rows"], cfg["columns"], cfg["piece_amounts"])
 
 
@@ -32,7 +32,7 @@ def _t(x, dtype):
     return torch.as_tensor(np.ascontiguousarray(x), dtype=dtype, device="cuda:0")
 
 
-@pytest.mark.parametrize("version", VERSIONS)
+@pytest.mark.parametrize("version", TRAJ_LABELS)
 def test_step_all_vs_golden_and_oracle(version):
     """one fused launch over every recorded transition: next state, outcome, next mask, next observations"""
     t = traj(version)
@@ -74,7 +74,7 @@ def test_step_all_vs_golden_and_oracle(version):
     assert checked > 0
 
 
-@pytest.mark.parametrize("version", ["barrage", "standard", "micro", "octa_barrage", "standard2", "fives"])
+@pytest.mark.parametrize("version", ["barrage", "standard", "micro", "octa_barrage", "standard2", "fives", "standard_b"])
 def test_observe_both_players(version):
     """sx_observe (maenv:447-497) for the mover and for the waiting player, incl. terminal states"""
     t = traj(version)

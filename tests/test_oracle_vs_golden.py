@@ -5,7 +5,7 @@ import pytest
 from oracle.binding import OracleEnvLogic, OracleProceduralEnv
 from stratego_env_b200.config import VERSION_CONFIGS, as_version
 
-from _golden import (ALIAS_VERSIONS, VERSIONS, custom_toys, known, original_channels, side_channels, spatial_alias, traj,
+from _golden import (ALIAS_VERSIONS, TRAJ_LABELS, VERSIONS, variant_of, custom_toys, known, original_channels, side_channels, spatial_alias, traj,
                      transitions, unpack_mask)
 
 
@@ -13,11 +13,11 @@ def bits_equal(a, b):
     return np.array_equal(np.asarray(a, np.float32).view(np.uint32), np.asarray(b, np.float32).view(np.uint32))
 
 
-@pytest.mark.parametrize("version", VERSIONS)
+@pytest.mark.parametrize("version", TRAJ_LABELS)
 def test_trajectory_next_state_reward_mask(version):
     t = traj(version)
     R, C, A = int(t["rows"]), int(t["columns"]), int(t["channels"])
-    cfg = VERSION_CONFIGS[as_version(version)]
+    cfg = VERSION_CONFIGS[as_version(variant_of(version))]
     logic = OracleEnvLogic(R, C, cfg["piece_amounts"])
     env = logic.base_env
     states = t["states"].astype(np.int64)
@@ -36,11 +36,11 @@ def test_trajectory_next_state_reward_mask(version):
         assert env.get_game_result_is_invalid(ns) == bool(t["invalid"][i])
 
 
-@pytest.mark.parametrize("version", VERSIONS)
+@pytest.mark.parametrize("version", TRAJ_LABELS)
 def test_trajectory_observations_bitwise(version):
     t = traj(version)
     R, C, A = int(t["rows"]), int(t["columns"]), int(t["channels"])
-    cfg = VERSION_CONFIGS[as_version(version)]
+    cfg = VERSION_CONFIGS[as_version(variant_of(version))]
     logic = OracleEnvLogic(R, C, cfg["piece_amounts"])
     ph, pl, fh, fl = logic.obs_highs_lows()
     assert bits_equal(ph, t["p_obs_highs"]) and bits_equal(pl, t["p_obs_lows"])
