@@ -178,7 +178,9 @@ int sx_step(const sx_config *cfg, sx_state st, int64_t num_envs, const int32_t *
 
 /* The fused hot path, one launch per env-step: maenv.step (maenv:659-828) = action decode
  * (maenv:685-689) -> next state (impl:897) -> outcome (impl:835-849) -> [auto-reset] -> mask +
- * observations of the player to move (maenv:447-497) -> [uniform valid-action sample]. */
+ * observations of the player to move (maenv:447-497) -> [uniform valid-action sample].
+ * stats_d (optional, device, int64[8], accumulated with atomics): games finished, player +1 wins, player -1 wins,
+ * invalid endings, rejected actions, actions processed, attacks, setup draws (re-draws of unplayable setups included). */
 int sx_step_all(const sx_config *cfg, sx_state st, int64_t num_envs, int64_t env_base, const int32_t *actions_d,
                 int32_t action_format, uint32_t flags, const uint8_t *setups_d, int32_t n_setups, uint64_t seed,
                 sx_outputs out, int64_t *stats_d, void *stream);

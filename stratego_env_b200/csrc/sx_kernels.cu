@@ -149,13 +149,14 @@ __host__ __device__ constexpr uint32_t mode_ops(int mode)
          : mode == MODE_OBSERVE_PO_MASK ? (OP_MASK | OP_PO) : 0u;
 }
 
-// end-of-run statistics: per-thread 32-bit counters, published once per launch
+// end-of-run statistics: games, wins per side, invalid endings, rejected actions, actions
+// processed, attacks, setup draws.  Per-thread 32-bit counters of the thread-per-game kernel, published once per launch
 struct StepCounters {
     uint32_t games, p1, p2, invalid, illegal, steps, attacks, resets;
     __device__ __forceinline__ void count_step(StepStatus status, bool done, const Aux &a)
     {
         if (status == STEP_ILLEGAL) illegal += 1;
-        else steps += 1;
+        steps += 1;  // actions processed, accepted or not
         if (done && status != STEP_UNCHANGED) {
             games += 1;
             p1 += a.winner == 1;
@@ -180,6 +181,18 @@ struct StepCounters {
             if (v[i]) atomicAdd(reinterpret_cast<unsigned long long *>(stats + i), (unsigned long long)v[i]);
     }
 };
+// rare events of a step, added to the statistics right away by one lane (sx_fused_kernel)
+__device__ __forceinline__ void count_rare(long long *stats, StepStatus status, bool done, const Aux &a)
+{
+    unsigned long long *s = reinterpret_cast<unsigned long long *>(stats);
+    if (status == STEP_ILLEGAL) atomicAdd(s + 4, 1ull);
+    if (done && status != STEP_UNCHANGED) {
+        atomicAdd(s + 0, 1ull);
+        if (a.winner == 1) atomicAdd(s + 1, 1ull);
+        if (a.winner == -1) atomicAdd(s + 2, 1ull);
+        if (a.invalid) atomicAdd(s + 3, 1ull);
+    }
+}
 // out.illegal: 0 ok, 1 action rejected (game untouched), 2 the game's capture list overflowed (add_capture_inl)
 __device__ __forceinline__ uint8_t illegal_code(StepStatus status, const Aux &a)
 {
@@ -201,8 +214,15 @@ constexpr int MAX_REDRAWS = 8;  // re-draws of an unplayable setup (first player
 #define SX_EXP(flags, bit) false
 #endif
 // K = board cells per lane, G = games per warp (Grp<G>): 10x10 -> K 4, G 1; 3x4 / 4x4 -> K 2, G 4.
+// Threads per block the kernel is compiled for (= its register budget: 65 536 / threads).  10x10 and 15x15: 512 (128
+// registers).  Boards of at most 64 cells with one game per warp (6x6, 8x8): SX_K2_THREADS; several games per warp
+// (3x4 ... 5x5): 1024 threads = 64 registers, which those kernels pay for with spills.
+#ifndef SX_K2_THREADS
+#define SX_K2_THREADS 1024
+#endif
 template <int K, int MODE, int G>
-__global__ void __launch_bounds__(K <= 2 ? 1024 : SX_MAX_THREADS, 1) sx_fused_kernel(const __grid_constant__ KernelArgs args)
+__global__ void __launch_bounds__(K > 2 ? SX_MAX_THREADS : G == 1 ? SX_K2_THREADS : 1024, 1)
+sx_fused_kernel(const __grid_constant__ KernelArgs args)
 {
     using GT = Grp<G>;
     extern __shared__ __align__(16) uint8_t smem[];
@@ -284,7 +304,10 @@ __global__ void __launch_bounds__(K <= 2 ? 1024 : SX_MAX_THREADS, 1) sx_fused_ke
         if (lane == 0) bulk_commit();
     };
 
-    StepCounters cnt{};
+    // statistics: a finished game, a rejected action or a (re)draw are rare and go straight to the counters (one lane,
+    // one atomic each); attacks and the step count stay in registers / are derived, and are published once per launch.
+    // (Eight live counters cost the 64-register kernels of the small boards 30 % more spill traffic.)
+    uint32_t n_attacks = 0, n_steps = 0;
     const long long total_warps = (long long)gridDim.x * warps_per_block;
     long long env = (long long)blockIdx.x * warps_per_block + warp;
     Prefetched pf;
@@ -368,7 +391,8 @@ __global__ void __launch_bounds__(K <= 2 ? 1024 : SX_MAX_THREADS, 1) sx_fused_ke
             int attack;
             status = apply_move<GT>(cfg, m, a, mv, allow_osc, attack);
             dirty |= status != STEP_ILLEGAL;
-            cnt.attacks += attack;
+            n_attacks += attack;
+            n_steps += 1;
         }
 
         // ---- move list of the player the outputs are for -------------------------------------------
@@ -396,7 +420,7 @@ __global__ void __launch_bounds__(K <= 2 ? 1024 : SX_MAX_THREADS, 1) sx_fused_ke
                 if (args.out.illegal) args.out.illegal[env] = illegal_code(status, a);
                 if (args.out.reward) args.out.reward[env] = (done && !a.invalid) ? float(w) : 0.0f;  // maenv:777-801
             }
-            cnt.count_step(status, done, a);
+            if (args.stats && lane == 0 && (status == STEP_ILLEGAL || done)) count_rare(args.stats, status, done, a);
         }
 
         // maenv:772-773 hands BOTH players their observation of the finished game; with auto-reset the regular outputs
@@ -415,7 +439,7 @@ __global__ void __launch_bounds__(K <= 2 ? 1024 : SX_MAX_THREADS, 1) sx_fused_ke
 #pragma unroll 1  // (unrolled eight times this loop alone made the hot kernels 20 % bigger and the small boards 15-25 % slower)
             for (int tries = 0; tries < MAX_REDRAWS; ++tries) {
                 do_reset(episode, tries);
-                cnt.resets += 1;
+                if (args.stats && lane == 0) atomicAdd(reinterpret_cast<unsigned long long *>(args.stats + 7), 1ull);
                 viewer = a.to_move;
                 if (!need_moves) break;
                 any = regen_moves(viewer);
@@ -473,7 +497,10 @@ __global__ void __launch_bounds__(K <= 2 ? 1024 : SX_MAX_THREADS, 1) sx_fused_ke
         GT::sync();
     }
 
-    if (args.stats && lane == 0) cnt.publish(args.stats);  // all lanes of a game carry identical counters
+    if (args.stats && lane == 0) {  // all lanes of a game carry identical counters
+        if (n_steps) atomicAdd(reinterpret_cast<unsigned long long *>(args.stats + 5), (unsigned long long)n_steps);
+        if (n_attacks) atomicAdd(reinterpret_cast<unsigned long long *>(args.stats + 6), (unsigned long long)n_attacks);
+    }
 }
 
 

@@ -12,6 +12,8 @@ from typing import Optional, Tuple
 import torch
 import torch.distributed as dist
 
+# device counters of sx_step_all (include/stratego_b200.h): "steps" = actions processed (accepted or not), "resets" =
+# setups drawn inside the step (re-draws of unplayable setups included)
 STAT_NAMES = ("games_finished", "player_1_wins", "player_2_wins", "invalid_endings", "illegal_actions",
               "steps", "attacks", "resets")
 
