@@ -214,14 +214,19 @@ constexpr int MAX_REDRAWS = 8;  // re-draws of an unplayable setup (first player
 #define SX_EXP(flags, bit) false
 #endif
 // K = board cells per lane, G = games per warp (Grp<G>): 10x10 -> K 4, G 1; 3x4 / 4x4 -> K 2, G 4.
-// Threads per block the kernel is compiled for (= its register budget: 65 536 / threads).  10x10 and 15x15: 512 (128
-// registers).  Boards of at most 64 cells with one game per warp (6x6, 8x8): SX_K2_THREADS; several games per warp
-// (3x4 ... 5x5): 1024 threads = 64 registers, which those kernels pay for with spills.
+// Threads per block the kernel is compiled for (= its register budget: 65 536 / threads).  Everything with one game
+// per warp gets 512 threads = 128 registers: with the 1 024-thread bound of round 1 the 6x6 / 8x8 kernels were held to
+// 64 registers and spilled ~230 bytes per thread -- measured (profiles/r2l_small_board_launch_bound_sweep.txt) 8x8:
+// 222 M env-steps/s at 1 024 threads / 16 warps, 242 M at 768 / 16, 272 M at 512 / 12; 6x6: 307 M / 337 M / 372 M.
+// Several games per warp (3x4 ... 5x5): SX_KG_THREADS.
 #ifndef SX_K2_THREADS
-#define SX_K2_THREADS 1024
+#define SX_K2_THREADS 512
+#endif
+#ifndef SX_KG_THREADS
+#define SX_KG_THREADS 1024
 #endif
 template <int K, int MODE, int G>
-__global__ void __launch_bounds__(K > 2 ? SX_MAX_THREADS : G == 1 ? SX_K2_THREADS : 1024, 1)
+__global__ void __launch_bounds__(K > 2 ? SX_MAX_THREADS : G == 1 ? SX_K2_THREADS : SX_KG_THREADS, 1)
 sx_fused_kernel(const __grid_constant__ KernelArgs args)
 {
     using GT = Grp<G>;
@@ -1112,9 +1117,11 @@ static int plan_launch_uncached(const sx_config *cfg, uint32_t ops, int mode, lo
     // 8 warps is a sharp optimum for one 10x10 observation + mask (7: -11 %, 9 and more: -3 to -12 %, not monotonic).
     // Smaller boards carry less output per game, so more of them fit in the same bytes in flight: 8x8 (19 KB per game)
     // 10 warps 218 M, 12 warps 237 M, 16 warps 255 M env-steps/s with the copy issued late.
-    // 6x6 (10.4 KB per game): 10 warps 234 M, 16 warps 324 M, 24 warps 363 M, 32 warps 330 M.  Rule for boards below
-    // 10x10: about 300 KB of output in flight per SM, in multiples of 4 warps.
-    const int small_board = std::max(8, std::min(32, ((300 * 1024 / std::max(1, tile_bytes)) + 2) / 4 * 4));
+    // 6x6 (10.4 KB per game): 10 warps 234 M, 16 warps 324 M, 24 warps 363 M, 32 warps 330 M (all with the 64-register
+    // build of round 1).  Rule for boards below 10x10: about 230 KB of output in flight per SM -- the same figure that
+    // makes 8 warps the optimum of the 10x10 boards; with 128 registers per thread (no spills) the 8x8 board peaks at
+    // 12 warps (272 M env-steps/s; 16 warps 256 M) and the 6x6 board at the 16 warps that fit (372 M).
+    const int small_board = std::max(8, std::min(32, (232 * 1024 + tile_bytes / 2) / std::max(1, tile_bytes)));
     const int preferred = tile_bytes <= 8 * 1024 ? 32 : tile_bytes <= 32 * 1024 ? (cfg->dev.N >= 100 ? 8 : small_board)
                           : tile_bytes <= 64 * 1024 ? 6 : 10;  // 15x15 (74 KB per game): 4 warps 39 M, 6: 55 M, 8: 69 M, 10: 75 M env-steps/s
     int warps = std::min(max_warps, std::max(1, env_int("SX_WARPS", std::min(max_warps, preferred))));
