@@ -218,12 +218,13 @@ constexpr int MAX_REDRAWS = 8;  // re-draws of an unplayable setup (first player
 // per warp gets 512 threads = 128 registers: with the 1 024-thread bound of round 1 the 6x6 / 8x8 kernels were held to
 // 64 registers and spilled ~230 bytes per thread -- measured (profiles/r2l_small_board_launch_bound_sweep.txt) 8x8:
 // 222 M env-steps/s at 1 024 threads / 16 warps, 242 M at 768 / 16, 272 M at 512 / 12; 6x6: 307 M / 337 M / 372 M.
-// Several games per warp (3x4 ... 5x5): SX_KG_THREADS.
+// Several games per warp (3x4 ... 5x5; SX_KG_THREADS) likewise: 5x5 385 M at 1 024 threads / 32 warps, 456 M at
+// 768 / 24, 492 M at 512 / 16 (profiles/r2m_small_board_sweep.txt).
 #ifndef SX_K2_THREADS
 #define SX_K2_THREADS 512
 #endif
 #ifndef SX_KG_THREADS
-#define SX_KG_THREADS 1024
+#define SX_KG_THREADS 512
 #endif
 template <int K, int MODE, int G>
 __global__ void __launch_bounds__(K > 2 ? SX_MAX_THREADS : G == 1 ? SX_K2_THREADS : SX_KG_THREADS, 1)
@@ -514,8 +515,13 @@ sx_fused_kernel(const __grid_constant__ KernelArgs args)
 // Measured (profiles/r1l_*): throughput follows the number of resident warps (8: 0.87 G, 12: 1.23 G, 16: 1.43 G
 // env-steps/s on Micro), not the number of tiles per warp (2, 4, 8, 16 tiles: same), so the launch keeps two tiles and
 // as many warps as shared memory holds.
+// compiled for the 12 warps it runs with: 144 registers instead of the 120 a 512-thread bound leaves (Micro +1 %, Tiny
+// +4 %, profiles/r2o_toy_register_budget_sweep.txt)
+#ifndef SX_TOY_THREADS
+#define SX_TOY_THREADS 384
+#endif
 template <int MODE>
-__global__ void __launch_bounds__(512, 1) sx_toy_kernel(const __grid_constant__ KernelArgs args)
+__global__ void __launch_bounds__(SX_TOY_THREADS, 1) sx_toy_kernel(const __grid_constant__ KernelArgs args)
 {
     using GT = Grp<1>;
     extern __shared__ __align__(16) uint8_t smem[];
@@ -1197,7 +1203,7 @@ static int plan_toy(const sx_config *cfg, uint32_t ops, ToyPlan *plan)
     plan->warp_bytes = toy_warp_bytes(cfg->dev, ops);
     // 12 warps per SM (or as many as shared memory holds): Micro 8 warps 1.10 G, 10: 1.35 G, 11: 1.42 G, 12: 1.49 G,
     // 13-16: 1.40-1.43 G env-steps/s; Tiny 8: 1.02 G, 10-13: 1.08 G
-    plan->warps = std::max(1, std::min(16, env_int("SX_TOY_WARPS", 12)));
+    plan->warps = std::max(1, std::min(SX_TOY_THREADS / 32, env_int("SX_TOY_WARPS", 12)));
     while (plan->warps > 1 && plan->tile_bytes + plan->warps * plan->warp_bytes > max_smem) --plan->warps;
     plan->smem = plan->tile_bytes + plan->warps * plan->warp_bytes;
     if (plan->smem > max_smem) return fail("toy kernel does not fit in shared memory");
