@@ -122,7 +122,9 @@ static __device__ __noinline__ void render_terminal(const KernelArgs *args, cons
             const int k = align_rows(fom.channels, int((reinterpret_cast<uintptr_t>(gfo) >> 2) & 3));
             emit_tile<GT>(reinterpret_cast<uint8_t *>(gfo), reinterpret_cast<const uint8_t *>(bg_fo + k * fom.channels), cfg.fo_floats * 4, pol);
         }
-        if (GT::lane() == 0) { bulk_commit(); bulk_wait_all(); }
+        if (GT::lane() == 0) bulk_commit();
+        GT::sync();  // commit_group and wait_group are kept apart (SX_TUNE_COMMIT_GAP)
+        if (GT::lane() == 0) bulk_wait_all();
         GT::sync();
         if (original) {
             if (gpo) patch_obs<K, GT, true>(cfg, m, a, gpo, pom, side, pol);
@@ -213,6 +215,15 @@ constexpr int MAX_REDRAWS = 8;  // re-draws of an unplayable setup (first player
 #else
 #define SX_EXP(flags, bit) false
 #endif
+// Result-preserving tuning bits the host sets per variant (sx_step_all): bits 20-21 = where a game's background copy is
+// issued, bit 24 = SX_TUNE_COMMIT_GAP.
+// SX_TUNE_COMMIT_GAP: on the boards that issue the copy LATE, `cp.async.bulk.commit_group` is directly followed by
+// `cp.async.bulk.wait_group 0` (SASS: UTMACMDFLUSH; DEPBAR.LE SB0, 0 back to back), and that pair is slow on B200: ANY
+// instruction between the two -- a warp sync, `nanosleep 0`, or the never-taken experiment branches of a
+// -DSX_EXPERIMENTS build, which is how it was found -- makes the 15x15 board 37 % faster (55 -> 75 M env-steps/s), 5x5
+// 12 %, 6x6 6 %, 8x8 2 % (profiles/r2q_experiment_branch_layout_sweep.txt, r2r_commit_wait_gap.txt).  The 10x10 board
+// with both observations is the one late-issue variant that does not gain (-1 %), so the host leaves the bit clear there.
+constexpr uint32_t SX_TUNE_COMMIT_GAP = 0x1000000u;
 // K = board cells per lane, G = games per warp (Grp<G>): 10x10 -> K 4, G 1; 3x4 / 4x4 -> K 2, G 4.
 // Threads per block the kernel is compiled for (= its register budget: 65 536 / threads).  Everything with one game
 // per warp gets 512 threads = 128 registers: with the 1 024-thread bound of round 1 the 6x6 / 8x8 kernels were held to
@@ -482,7 +493,10 @@ sx_fused_kernel(const __grid_constant__ KernelArgs args)
         }
 
         // ---- render: sparse entries on top of the (by now written) background ---------------------------
-        if (do_tile && issue_at == 0) issue_background(env);
+        if (do_tile && issue_at == 0) {
+            issue_background(env);
+            if (flags & SX_TUNE_COMMIT_GAP) GT::sync();  // keeps commit_group and wait_group apart (see SX_TUNE_COMMIT_GAP)
+        }
         if (do_tile && !SX_EXP(flags, 0x20000u)) {
             if (lane == 0) bulk_wait_all();  // this game's background is in global memory
             GT::sync();
@@ -517,6 +531,9 @@ sx_fused_kernel(const __grid_constant__ KernelArgs args)
 // as many warps as shared memory holds.
 // compiled for the 12 warps it runs with: 144 registers instead of the 120 a 512-thread bound leaves (Micro +1 %, Tiny
 // +4 %, profiles/r2o_toy_register_budget_sweep.txt)
+#ifndef SX_TOY_GAP
+#define SX_TOY_GAP 0
+#endif
 #ifndef SX_TOY_THREADS
 #define SX_TOY_THREADS 384
 #endif
@@ -722,6 +739,9 @@ __global__ void __launch_bounds__(SX_TOY_THREADS, 1) sx_toy_kernel(const __grid_
                         if (do_fo) bulk_store(args.out.full_obs + (env0 + g + h) * cfg.fo_floats, tile + po_bytes, uint32_t(fo_bytes), pol);
                         bulk_commit();
                     }
+#if SX_TOY_GAP
+                    __syncwarp();  // keeps this commit_group apart from the next pass's wait_group (SX_TUNE_COMMIT_GAP)
+#endif
                 }
             }
         }
@@ -1270,6 +1290,9 @@ static int launch_fused(const sx_config *cfg, KernelArgs &args, cudaStream_t str
     args.cfg = cfg->dev;
     args.warp_bytes = plan.warp_bytes;
     args.tile_bytes = plan.tile_bytes;
+    // launches without a step (sx_observe, sx_valid_mask, the observe pass of a reset) issue their copies late
+    if (!(args.ops & OP_STEP)) args.flags |= SX_TUNE_COMMIT_GAP;
+    if (const int gap = env_int("SX_GAP", -1); gap >= 0) args.flags = gap ? (args.flags | SX_TUNE_COMMIT_GAP) : (args.flags & ~SX_TUNE_COMMIT_GAP);
     // (Tried and removed: marking the state range as persisting in L2 with an access-policy window.  A pure store
     // stream loses ~8 % when the ~0.2 KB/game state reads come from DRAM (tools/probes/probe_write.cu), but any L2
     // set-aside large enough to hold the state takes capacity from the output lines that wait for their sparse
@@ -1434,8 +1457,10 @@ extern "C" int sx_step_all(const sx_config *cfg, sx_state st, int64_t num_envs, 
     // copy issued after the outcome (16) at 8 warps per SM; both observations and the smaller boards issue late (0).
     const bool one_obs = (out.partial_obs != nullptr) != (out.full_obs != nullptr);
     const int n = cfg->dev.N;
-    const int tune = env_int("SX_DEBUG", (n >= 100 && n <= 128 && one_obs) ? 16 : 0);
+    const bool ten_by_ten = n >= 100 && n <= 128;
+    const int tune = env_int("SX_DEBUG", (ten_by_ten && one_obs) ? 16 : 0);
     a.flags = (flags & 0xffffu) | (uint32_t(tune) << 16);
+    if ((tune & 0x30) == 0 && !ten_by_ten) a.flags |= SX_TUNE_COMMIT_GAP;  // late issue, not the 10x10 board
     a.out = out;
     a.ops = step_all_ops(out, flags);
     a.setups = setups_d; a.n_setups = n_setups;
