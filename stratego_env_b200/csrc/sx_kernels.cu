@@ -531,9 +531,6 @@ sx_fused_kernel(const __grid_constant__ KernelArgs args)
 // as many warps as shared memory holds.
 // compiled for the 12 warps it runs with: 144 registers instead of the 120 a 512-thread bound leaves (Micro +1 %, Tiny
 // +4 %, profiles/r2o_toy_register_budget_sweep.txt)
-#ifndef SX_TOY_GAP
-#define SX_TOY_GAP 0
-#endif
 #ifndef SX_TOY_THREADS
 #define SX_TOY_THREADS 384
 #endif
@@ -739,9 +736,6 @@ __global__ void __launch_bounds__(SX_TOY_THREADS, 1) sx_toy_kernel(const __grid_
                         if (do_fo) bulk_store(args.out.full_obs + (env0 + g + h) * cfg.fo_floats, tile + po_bytes, uint32_t(fo_bytes), pol);
                         bulk_commit();
                     }
-#if SX_TOY_GAP
-                    __syncwarp();  // keeps this commit_group apart from the next pass's wait_group (SX_TUNE_COMMIT_GAP)
-#endif
                 }
             }
         }
@@ -1223,7 +1217,9 @@ static int plan_toy(const sx_config *cfg, uint32_t ops, ToyPlan *plan)
     plan->warp_bytes = toy_warp_bytes(cfg->dev, ops);
     // 12 warps per SM (or as many as shared memory holds): Micro 8 warps 1.10 G, 10: 1.35 G, 11: 1.42 G, 12: 1.49 G,
     // 13-16: 1.40-1.43 G env-steps/s; Tiny 8: 1.02 G, 10-13: 1.08 G
-    plan->warps = std::max(1, std::min(SX_TOY_THREADS / 32, env_int("SX_TOY_WARPS", 12)));
+    // (Tiny 4x4 peaks at 11 warps: 1 113 M vs 1 072 M at 12, measured twice, profiles/r2o_*, r2t_*.  A warp sync between a
+    // pass's commit_group and the next pass's wait_group.read changes nothing here: that wait is for an older group.)
+    plan->warps = std::max(1, std::min(SX_TOY_THREADS / 32, env_int("SX_TOY_WARPS", cfg->dev.N <= 12 ? 12 : 11)));
     while (plan->warps > 1 && plan->tile_bytes + plan->warps * plan->warp_bytes > max_smem) --plan->warps;
     plan->smem = plan->tile_bytes + plan->warps * plan->warp_bytes;
     if (plan->smem > max_smem) return fail("toy kernel does not fit in shared memory");
