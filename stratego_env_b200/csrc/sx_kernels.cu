@@ -54,6 +54,7 @@ struct KernelArgs {
     const uint8_t *reset_mask;
     uint2 key;
     long long *stats;
+    int chunk_log2;  // log2 of the run of consecutive games a warp takes before it jumps ahead (0 = interleaved)
     int warp_bytes;  // shared-memory slice of one game (state + move sets + scratch)
     int tile_bytes;  // the block's background images (0 = this launch renders nothing)
 };
@@ -278,6 +279,7 @@ sx_fused_kernel(const __grid_constant__ KernelArgs args)
     __syncthreads();
     const bool hints = !SX_EXP(flags, 0x40000u);
     const uint64_t pol_keep = l2_policy(hints ? 1 : 0), pol_stream = l2_policy(hints ? 2 : 0);
+    const uint64_t pol_bg = pol_stream;
 
     // ---- software pipeline -----------------------------------------------------------------------------
     // While game i runs, (1) game i+1's state / action loads are in flight in registers and (2) game i+1's
@@ -304,19 +306,19 @@ sx_fused_kernel(const __grid_constant__ KernelArgs args)
         // the small mask copy goes first (measured: +3 % over observation-first at 10 warps per SM)
         if (do_mask) {
             uint8_t *gmask = args.out.valid_mask + e * cfg.mask_bytes;
-            emit_tile<GT>(gmask, bg.mask + (reinterpret_cast<uintptr_t>(gmask) & 15), cfg.mask_bytes, pol_stream);
+            emit_tile<GT>(gmask, bg.mask + (reinterpret_cast<uintptr_t>(gmask) & 15), cfg.mask_bytes, pol_bg);
         }
         if (do_po) {
             float *g = args.out.partial_obs + e * cfg.po_floats;
             const int k = align_rows(pom.channels, int((reinterpret_cast<uintptr_t>(g) >> 2) & 3));
             emit_tile<GT>(reinterpret_cast<uint8_t *>(g), reinterpret_cast<const uint8_t *>(bg.po + k * pom.channels),
-                          cfg.po_floats * 4, pol_stream);
+                          cfg.po_floats * 4, pol_bg);
         }
         if (do_fo) {
             float *g = args.out.full_obs + e * cfg.fo_floats;
             const int k = align_rows(fom.channels, int((reinterpret_cast<uintptr_t>(g) >> 2) & 3));
             emit_tile<GT>(reinterpret_cast<uint8_t *>(g), reinterpret_cast<const uint8_t *>(bg.fo + k * fom.channels),
-                          cfg.fo_floats * 4, pol_stream);
+                          cfg.fo_floats * 4, pol_bg);
         }
         if (lane == 0) bulk_commit();
     };
@@ -325,8 +327,16 @@ sx_fused_kernel(const __grid_constant__ KernelArgs args)
     // one atomic each); attacks and the step count stay in registers / are derived, and are published once per launch.
     // (Eight live counters cost the 64-register kernels of the small boards 30 % more spill traffic.)
     uint32_t n_attacks = 0, n_steps = 0;
+    // Which games a warp takes: chunks of 2^chunk_log2 consecutive games, chunk c to game slot c mod (slots in the grid).
+    // chunk_log2 = 0 is the plain interleaving (game g to slot g mod slots).  Games are independent, so any order gives
+    // the same results; the order decides which addresses are written at the same time.
     const long long total_warps = (long long)gridDim.x * warps_per_block;
-    long long env = (long long)blockIdx.x * warps_per_block + warp;
+    const int chunk_lg = args.chunk_log2;
+    const long long chunk_mask = (1LL << chunk_lg) - 1;
+    auto next_game = [&](long long e) -> long long {
+        return (e & chunk_mask) != chunk_mask ? e + 1 : (((e >> chunk_lg) + total_warps) << chunk_lg);
+    };
+    long long env = ((long long)blockIdx.x * warps_per_block + warp) << chunk_lg;
     Prefetched pf;
     // Where a game's background copy is issued.  The sparse entries must reach L2 while the background lines are
     // still resident there (otherwise every 4-byte store becomes a DRAM read-modify-write; measured: storing them one
@@ -336,7 +346,7 @@ sx_fused_kernel(const __grid_constant__ KernelArgs args)
     // (SX_DEBUG bits 4-5 override).
     const int issue_at = (flags >> 20) & 3;
     if (env < args.num_envs) load_state(env, pf);
-    for (; env < args.num_envs; env += total_warps) {
+    for (; env < args.num_envs; env = next_game(env)) {
         const uint64_t gid = uint64_t(args.env_base + env);
         // ---- this game's state has arrived in registers: move it to the working slice, request the next ----
         GT::sync();
@@ -353,7 +363,7 @@ sx_fused_kernel(const __grid_constant__ KernelArgs args)
             aux_unpack(w, a);
         }
         GT::sync();
-        const long long next_env = env + total_warps;
+        const long long next_env = next_game(env);
         const bool has_next = next_env < args.num_envs;
         if (has_next) load_state(next_env, pf);
         if (do_tile && issue_at == 2) issue_background(env);
@@ -1288,6 +1298,7 @@ static int launch_fused(const sx_config *cfg, KernelArgs &args, cudaStream_t str
     args.tile_bytes = plan.tile_bytes;
     // launches without a step (sx_observe, sx_valid_mask, the observe pass of a reset) issue their copies late
     if (!(args.ops & OP_STEP)) args.flags |= SX_TUNE_COMMIT_GAP;
+    args.chunk_log2 = std::max(0, std::min(10, env_int("SX_CHUNK_LOG2", 0)));
     if (const int gap = env_int("SX_GAP", -1); gap >= 0) args.flags = gap ? (args.flags | SX_TUNE_COMMIT_GAP) : (args.flags & ~SX_TUNE_COMMIT_GAP);
     // (Tried and removed: marking the state range as persisting in L2 with an access-policy window.  A pure store
     // stream loses ~8 % when the ~0.2 KB/game state reads come from DRAM (tools/probes/probe_write.cu), but any L2
