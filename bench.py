@@ -482,7 +482,8 @@ def run_gpu_arm(args):
                 probe = None
             if probe:
                 entry["host_link"] = {"bare_copy_d2h_GBps": probe, "fraction_of_bare_copy": entry["d2h_GBps_aggregate"] / probe,
-                                      "source": "tools/probes/probe_d2h.cu, profiles/host_link.json"}
+                                      "source": "tools/probes/probe_d2h.cu, profiles/host_link.json (probed on the 8-GPU box of "
+                                                "visit r2d; a fraction above 1 means this box's host link is faster than that one's)"}
             return entry
 
         e2e = link(one(True, "HostBufferEnv.step (sx_host_env_step): int32 actions from pinned host memory, every output "
