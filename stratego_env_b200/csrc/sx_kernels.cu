@@ -541,6 +541,9 @@ sx_fused_kernel(const __grid_constant__ KernelArgs args)
 // as many warps as shared memory holds.
 // compiled for the 12 warps it runs with: 144 registers instead of the 120 a 512-thread bound leaves (Micro +1 %, Tiny
 // +4 %, profiles/r2o_toy_register_budget_sweep.txt)
+#ifndef SX_TOY_TILES
+#define SX_TOY_TILES 2  /* observation tiles per warp: one is rendered while the copy of the other is read; divides 32 */
+#endif
 #ifndef SX_TOY_THREADS
 #define SX_TOY_THREADS 384
 #endif
@@ -576,8 +579,12 @@ __global__ void __launch_bounds__(SX_TOY_THREADS, 1) sx_toy_kernel(const __grid_
     const int po_bytes = do_po ? cfg.po_floats * 4 : 0, fo_bytes = do_fo ? cfg.fo_floats * 4 : 0;
     const int tile_stride = po_bytes + fo_bytes;
     // the warp's two observation tiles hold the background image for the whole launch
-    constexpr int T = 2;  // tiles per warp (4 or 8 tiles with fewer warps were slower, profiles/r1l_toy_sweeps.txt; rendering
-                          // two games per pass, one per half-warp, was bit-exact and 8 % slower, profiles/r2g_*)
+    // T tiles per warp.  Measured and not kept (profiles/r1l_toy_sweeps.txt, r2g_*, r2x_*, r2y_*): 4 or 8 tiles per warp
+    // (Micro 1 198 M / 847 M vs 1 448 M env-steps/s), two or four consecutive games per tile set leaving as ONE larger bulk
+    // copy (1 234 M / 914 M), two games rendered per pass by the half-warps (1 360 M).  Every one of them needs more
+    // shared memory per warp, and the block's shared memory comes out of the SM's 256 KB L1: this kernel keeps ~100 bytes
+    // of per-thread arrays in local memory, so it wants the L1 that 150 KB of shared memory leaves.
+    constexpr int T = SX_TOY_TILES;
     uint32_t undo_po[T], undo_fo[T];
 #pragma unroll
     for (int h = 0; h < T; ++h) undo_po[h] = undo_fo[h] = toy::UNDO_NONE;
@@ -609,7 +616,10 @@ __global__ void __launch_bounds__(SX_TOY_THREADS, 1) sx_toy_kernel(const __grid_
         const long long env0 = group * toy::GAMES, env = env0 + lane;
         const uint64_t gid = uint64_t(args.env_base + env);
         if (do_tile) {
-            if (lane == 0) bulk_wait_read();  // the previous group's copies have left shared memory
+            // the mask image is about to be rewritten: its copy is the OLDEST group of the previous 32 games, so it is
+            // enough that all but the newest T - 1 groups (the last observation tiles, which the render loop below waits
+            // for tile by tile) have been read; draining everything here stalled the warp once per 32 games (Micro +1 %)
+            if (lane == 0) asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(SX_TOY_TILES - 1) : "memory");
             __syncwarp();
             if (do_mask)
                 for (int i = lane; i < (mask_img_bytes >> 4); i += 32) reinterpret_cast<uint4 *>(mask_img)[i] = make_uint4(0, 0, 0, 0);
@@ -1210,7 +1220,7 @@ static int toy_warp_bytes(const DevConfig &d, uint32_t ops)
 {
     const int mask_img = (ops & OP_MASK) ? round16(toy::GAMES * d.mask_bytes + 16) : 0;
     const int tile = ((ops & OP_PO) ? d.po_floats * 4 : 0) + ((ops & OP_FO) ? d.fo_floats * 4 : 0);
-    return toy::GAMES * toy::STAGE_BYTES + mask_img + 2 * tile;
+    return toy::GAMES * toy::STAGE_BYTES + mask_img + SX_TOY_TILES * tile;
 }
 
 struct ToyPlan {
