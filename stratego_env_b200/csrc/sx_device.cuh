@@ -67,12 +67,28 @@ struct DevConfig {
     uint8_t piece_seq[128];  // pieces in placement order (piece code ascending, util:24-28)
 };
 
+// Two small values indexed by player (0 / 1).  A plain `int x[2]` indexed with a run-time player index makes the
+// compiler put the whole Aux object into local memory (85 LDL / STL instructions in the thread-per-game kernel, ~100 in
+// the warp-level ones); this keeps both values in registers and turns the index into a select.
+struct PerPlayer {
+    int v0, v1;
+    struct Ref {
+        int &v0, &v1;
+        int i;
+        __device__ __forceinline__ operator int() const { return i ? v1 : v0; }
+        __device__ __forceinline__ int operator=(int x) { if (i) v1 = x; else v0 = x; return x; }
+        __device__ __forceinline__ int operator=(const Ref &o) { return *this = int(o); }
+    };
+    __device__ __forceinline__ Ref operator[](int i) { return Ref{v0, v1, i}; }
+    __device__ __forceinline__ int operator[](int i) const { return i ? v1 : v0; }
+};
+
 // ---- scalar part of a game's state (aux tensor, 8 x int16) ----------------------------------------
 struct Aux {
     int turn, max_turns;
     int over, invalid, winner;  // winner in {-1, 0, +1}
     int to_move;                // 0 = player +1, 1 = player -1
-    int rfrom[2], rto[2], rcode[2];  // recent-move squares per player (NO_CELL = none); rcode = -code of `to` (1..3)
+    PerPlayer rfrom, rto, rcode;  // recent-move squares per player (NO_CELL = none); rcode = -code of `to` (1..3)
     int ncap;
     int overflow;               // sticky: a capture did not fit the capture list -> the compact state lost information
     uint32_t episode;
