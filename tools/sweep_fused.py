@@ -1,5 +1,8 @@
 """Tuning sweep of the fused step (development aid): one process, one de-phased state, many (warps per SM, SX_DEBUG)
-settings.  usage: python tools/sweep_fused.py <workload> "<W>:<debug>,<W>:<debug>,..." [envs]
+settings.  The knobs exist only in an EXPERIMENTS build of the library (the shipped one never reads the environment):
+    python -c "from stratego_env_b200 import _build; print(_build.build_experiments('exp'))"
+    SX_LIB=stratego_env_b200/csrc/libstratego_b200_exp.so python tools/sweep_fused.py <workload> "<W>:<debug>,..." [envs]
+Other knobs of that build: SX_CHUNK_LOG2 (runs of consecutive games per warp), SX_BLOCKS, SX_TOY_WARPS, SX_GAP.
 SX_DEBUG bits (sx_step_all): 1 skip TMA, 2 skip wait + sparse stores, 8 skip sparse stores, 16 / 32 background issue
 point (0 late, 16 after outcome, 32 top of the game), 64 no state write-back, 128 output skeleton only."""
 import os
@@ -14,6 +17,9 @@ from stratego_env_b200.engine import StrategoEngine, load_setup_table  # noqa: E
 
 
 def main():
+    if not os.environ.get("SX_LIB"):
+        raise SystemExit("set SX_LIB to an experiments build of the library (see the docstring): the shipped library "
+                         "ignores SX_WARPS / SX_DEBUG")
     wl = sys.argv[1] if len(sys.argv) > 1 else "barrage"
     combos = [tuple(c.split(":")) for c in (sys.argv[2] if len(sys.argv) > 2 else "10:32").split(",")]
     w = WORKLOADS[wl]
