@@ -115,3 +115,59 @@ def test_random_synthetic_states_differential(shape, n_states):
                         assert np.array_equal(ns_o, ns_r), (shape, a, allow)
                         checked_moves += 1
     assert checked_moves > n_states
+
+
+@pytest.mark.parametrize("version,human,n_states", [("barrage", True, 6), ("micro", False, 30), ("tiny", False, 16),
+                                                    ("octa_barrage", False, 4)])
+def test_every_flat_spatial_action_live(version, human, n_states):
+    """EVERY flat spatial index through the live reference's own conversion chain (maenv:685-691) against the oracle's
+    apply_spatial_action, on states reached by random play: accepted / rejected and the next state -- incl. the
+    out-of-mask indices whose unchecked targets alias other moves (impl:316-347, 264-277, 700-720)."""
+    import os
+    se = import_reference()
+    from stratego_env.game.enums import GameVersions, ObservationComponents as OC
+    np.random.seed(777)
+    random.seed(777)
+    rng = np.random.default_rng(5)
+    env = se.StrategoMultiAgentEnv({"version": GameVersions(version), "human_inits": human})
+    base = env.base_env
+    cfg = VERSION_CONFIGS[as_version(version)]
+    logic = OracleEnvLogic(cfg["rows"], cfg["columns"], cfg["piece_amounts"])
+    R, C, A = base.spatial_action_size
+    obs = env.reset()
+    saved = os.dup(1)  # the reference prints a reason for every rejected move from compiled code
+    null = os.open(os.devnull, os.O_WRONLY)
+    outside = 0
+    try:
+        os.dup2(null, 1)
+        for s in range(n_states):
+            for _ in range(int(rng.integers(1, 9))):  # walk a few random moves between the sampled states
+                player = list(obs.keys())[0]
+                valid = np.flatnonzero(obs[player][OC.VALID_ACTIONS_MASK.value].reshape(-1))
+                obs, _, dones, _ = env.step({player: int(valid[rng.integers(len(valid))])})
+                if dones["__all__"]:
+                    obs = env.reset()
+            player = list(obs.keys())[0]
+            state = env.state.copy()
+            mask = obs[player][OC.VALID_ACTIONS_MASK.value].reshape(-1)
+            for a in range(R * C * A):
+                idx = np.unravel_index(a, base.spatial_action_size)
+                a1 = base.get_action_1d_index_from_player_perspective(
+                    action_index=base.get_action_1d_index_from_spatial_index(idx), player=player)
+                try:
+                    ref_next, _ = base.get_next_state(state, player, a1)
+                except ValueError:
+                    ref_next = None
+                try:
+                    orc_next, _ = logic.apply_spatial_action(state, player, a)
+                except ValueError:
+                    orc_next = None
+                assert (ref_next is None) == (orc_next is None), (version, s, a)
+                if ref_next is not None:
+                    assert np.array_equal(ref_next, orc_next), (version, s, a)
+                    outside += not mask[a]
+    finally:
+        os.dup2(saved, 1)
+        os.close(saved)
+        os.close(null)
+    assert outside > 0
