@@ -140,6 +140,14 @@ int sx_config_create(const sx_config_desc *desc, sx_config **out);
 void sx_config_destroy(sx_config *cfg);
 int sx_config_layout(const sx_config *cfg, sx_layout *out);
 
+/* Launch tuning of the warp-level kernel; a development aid (tools/sweep_fused.py times the shipped library with it).
+ * Every setting gives bit-identical results -- only the speed changes.  -1 keeps the built-in choice.
+ *   warps_per_block  resident warps per SM (0 = built-in again)
+ *   issue_point      where a game's background copy is handed to the TMA engine: 0 right before the sparse entries,
+ *                    1 after the outcome of the move is known, 2 at the top of the game
+ *   compact_movers   0 / 1: move generation hands the movable pieces to lanes instead of walking cells (10x10 class) */
+int sx_config_set_tuning(sx_config *cfg, int32_t warps_per_block, int32_t issue_point, int32_t compact_movers);
+
 /* Replaces penv.create_initial_state (penv:38 -> impl:213-249) + the setup samplers
  * (util:33-53 random, util:301-319 human).  Re-sets every env b with reset_mask_d[b] != 0 (all when
  * NULL).  Setups come from `setups_d` ([n_setups][setup_len] own-frame piece maps): rows

@@ -371,7 +371,7 @@ __device__ __forceinline__ int dir_base(const DevConfig &cfg, int dir)  // first
 
 // Enumerates the moves of player index `me`, in `me`'s frame, into m.moves.  Returns (warp-uniform)
 // whether any move exists.
-template <int K, class GT>
+template <int K, class GT, bool COMPACT = false>
 __device__ __forceinline__ bool gen_moves(const DevConfig &cfg, const WarpMem &m, const Aux &a, int me, bool allow_osc)
 {
     const int lane = GT::lane();
@@ -389,27 +389,72 @@ __device__ __forceinline__ bool gen_moves(const DevConfig &cfg, const WarpMem &m
     const Blocked blk = blocked_move(cfg, m, a, me, flip, allow_osc);
     const int b1 = cfg.R - 1, b2 = 2 * b1, b3 = b2 + cfg.C - 1;
     const int blocked_bit = blk.cell < 0 ? 0 : (blk.dir == 0 ? 0 : blk.dir == 1 ? b1 : blk.dir == 2 ? b2 : b3) + blk.dist - 1;
+    // the moves of the piece on cell p (a piece of `me` that can move, impl:420), two-square rule applied
+    auto piece_moves = [&](int p, int rank) {
+        const int r = fast_div(p, cfg.magic_C), c = p - r * cfg.C;
+        const uint32_t col_any = m.lines[GT::H + c], col_en = m.lines[GT::L + GT::H + c];
+        const uint32_t row_any = m.lines[r], row_en = m.lines[GT::L + r];
+        int n0 = ray_up(col_any, col_en, r, cfg.R), n1 = ray_down(col_any, col_en, r);
+        int n2 = ray_up(row_any, row_en, c, cfg.C), n3 = ray_down(row_any, row_en, c);
+        if (rank != SP_SCOUT) { n0 = min(n0, 1); n1 = min(n1, 1); n2 = min(n2, 1); n3 = min(n3, 1); }  // impl:492-499
+        unsigned long long bits = (unsigned long long)((1u << n0) - 1u) | ((unsigned long long)((1u << n1) - 1u) << b1) |
+                                  ((unsigned long long)((1u << n2) - 1u) << b2) | ((unsigned long long)((1u << n3) - 1u) << b3);
+        if (p == blk.cell) bits &= ~(1ull << blocked_bit);  // impl:439-445, 501-505
+        return bits;
+    };
     int found = 0;
-#pragma unroll UNROLL_K
-    for (int k = 0; k < K; ++k) {
-        const int p = lane * K + k;
-        if (p < cfg.N) {
-            unsigned long long bits = 0;
-            const uint32_t b = m.board[view(p, flip, cfg.N)];
-            const int rank = b & CELL_RANK;
-            if (rank != 0 && rank <= SP_MARSHAL && int((b >> 4) & 1) == me) {  // impl:420
-                const int r = fast_div(p, cfg.magic_C), c = p - r * cfg.C;
-                const uint32_t col_any = m.lines[GT::H + c], col_en = m.lines[GT::L + GT::H + c];
-                const uint32_t row_any = m.lines[r], row_en = m.lines[GT::L + r];
-                int n0 = ray_up(col_any, col_en, r, cfg.R), n1 = ray_down(col_any, col_en, r);
-                int n2 = ray_up(row_any, row_en, c, cfg.C), n3 = ray_down(row_any, row_en, c);
-                if (rank != SP_SCOUT) { n0 = min(n0, 1); n1 = min(n1, 1); n2 = min(n2, 1); n3 = min(n3, 1); }  // impl:492-499
-                bits = (unsigned long long)((1u << n0) - 1u) | ((unsigned long long)((1u << n1) - 1u) << b1) |
-                       ((unsigned long long)((1u << n2) - 1u) << b2) | ((unsigned long long)((1u << n3) - 1u) << b3);
-                if (p == blk.cell) bits &= ~(1ull << blocked_bit);  // impl:439-445, 501-505
-                found |= bits != 0;
+    if constexpr (COMPACT) {
+        // Dense big boards (Standard: up to 33 movable pieces on 100 cells): a cell-major loop runs the ray arithmetic K
+        // times because SOME lane has a mover each time.  Instead the lanes classify their cells (one ballot per k), mover
+        // number t goes to lane t, and the ray arithmetic runs once per 32 movers.  Measured (profiles/r3g_*, r3j_*):
+        // Standard 168.5 -> 175.8 M env-steps/s, the state-based sampler 0.194 -> 0.162 ms, the mask kernel 0.252 -> 0.206
+        // ms; on a sparse board (Barrage, 8 pieces) the ballots cost what the loop did and the 170 extra hot instructions
+        // raise the instruction-fetch stalls (185.8 -> 180.3 M), so the host picks per variant (sx_config::compact_movers).
+        uint32_t movers[K];
+        int total = 0;
+#pragma unroll
+        for (int k = 0; k < K; ++k) {
+            const int p = lane * K + k;
+            bool mv = false;
+            if (p < cfg.N) {
+                const uint32_t b = m.board[view(p, flip, cfg.N)];
+                const int rank = b & CELL_RANK;
+                mv = rank != 0 && rank <= SP_MARSHAL && int((b >> 4) & 1) == me;
+                m.moves[p] = make_uint2(0, 0);
             }
+            movers[k] = GT::ballot(mv);
+            total += __popc(movers[k]);
+        }
+        GT::sync();
+        for (int t = lane; t < total; t += GT::L) {
+            int r = t, k = 0;
+#pragma unroll
+            for (int j = 0; j + 1 < K; ++j) {  // which k-class mover t falls in, and its number inside the class
+                const int c = __popc(movers[j]);
+                if (k == j && r >= c) { r -= c; k = j + 1; }
+            }
+            uint32_t mk = movers[0];
+#pragma unroll
+            for (int j = 1; j < K; ++j) mk = k == j ? movers[j] : mk;
+            const int p = int(__fns(mk, 0, r + 1)) * K + k;
+            const unsigned long long bits = piece_moves(p, m.board[view(p, flip, cfg.N)] & CELL_RANK);
+            found |= bits != 0;
             m.moves[p] = make_uint2(uint32_t(bits), uint32_t(bits >> 32));
+        }
+    } else {
+#pragma unroll UNROLL_K
+        for (int k = 0; k < K; ++k) {
+            const int p = lane * K + k;
+            if (p < cfg.N) {
+                unsigned long long bits = 0;
+                const uint32_t b = m.board[view(p, flip, cfg.N)];
+                const int rank = b & CELL_RANK;
+                if (rank != 0 && rank <= SP_MARSHAL && int((b >> 4) & 1) == me) {  // impl:420
+                    bits = piece_moves(p, rank);
+                    found |= bits != 0;
+                }
+                m.moves[p] = make_uint2(uint32_t(bits), uint32_t(bits >> 32));
+            }
         }
     }
     GT::sync();

@@ -18,6 +18,10 @@ struct sx_config {
     sx_layout layout;
     int cells_per_lane;  // K
     int games_per_warp;  // G
+    bool compact_movers;  // gen_moves<.., COMPACT>: dense 10x10 boards (sx_device.cuh)
+    bool compact_forced = false;  // sx_config_set_tuning chose compact_movers: it then applies to every launch mode
+    int tune_warps = 0;   // sx_config_set_tuning: resident warps per SM of the warp-level kernel (0 = built-in choice)
+    int tune_issue = -1;  // sx_config_set_tuning: where a game's background copy is issued (-1 = built-in choice)
     // launch shapes already worked out, keyed by (device, ops, mode): the occupancy / attribute queries cost tens
     // of microseconds, which matters for the one-game API
     mutable std::mutex plan_mutex;

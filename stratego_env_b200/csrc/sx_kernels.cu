@@ -55,6 +55,7 @@ struct KernelArgs {
     uint2 key;
     long long *stats;
     int chunk_log2;  // log2 of the run of consecutive games a warp takes before it jumps ahead (0 = interleaved)
+    int exp_nap, exp_stagger;  // experiments builds only: ns to sleep before the copy wait / per warp index at the start
     int warp_bytes;  // shared-memory slice of one game (state + move sets + scratch)
     int tile_bytes;  // the block's background images (0 = this launch renders nothing)
 };
@@ -84,7 +85,7 @@ __host__ __device__ inline int carve_tile(const DevConfig &cfg, uint32_t ops, ui
 // and the sparse entries are then stored straight to global memory, where they merge with the freshly
 // written lines in L2.  No warp owns a 30 KB tile, so shared memory no longer limits residency.
 // Arguments and result by value so that the caller's state stays in registers.
-template <int K, class GT>
+template <int K, class GT, bool CM>
 __device__ __noinline__ bool gen_moves_cold(const DevConfig *cfg, uint8_t *warp_base, uint4 auxw, int me)
 {
     WarpMem m;
@@ -92,7 +93,7 @@ __device__ __noinline__ bool gen_moves_cold(const DevConfig *cfg, uint8_t *warp_
     const uint32_t w[4] = {auxw.x, auxw.y, auxw.z, auxw.w};
     Aux a;
     aux_unpack(w, a);
-    return gen_moves<K, GT>(*cfg, m, a, me, false);
+    return gen_moves<K, GT, CM>(*cfg, m, a, me, false);
 }
 
 // Both players' observations of the game staged in the warp slice (its final position) into the terminal side buffers
@@ -238,7 +239,7 @@ constexpr uint32_t SX_TUNE_COMMIT_GAP = 0x1000000u;
 #ifndef SX_KG_THREADS
 #define SX_KG_THREADS 512
 #endif
-template <int K, int MODE, int G>
+template <int K, int MODE, int G, bool CM = false>  // CM: gen_moves hands movers to lanes (dense 10x10 boards)
 __global__ void __launch_bounds__(K > 2 ? SX_MAX_THREADS : G == 1 ? SX_K2_THREADS : SX_KG_THREADS, 1)
 sx_fused_kernel(const __grid_constant__ KernelArgs args)
 {
@@ -337,6 +338,9 @@ sx_fused_kernel(const __grid_constant__ KernelArgs args)
         return (e & chunk_mask) != chunk_mask ? e + 1 : (((e >> chunk_lg) + total_warps) << chunk_lg);
     };
     long long env = ((long long)blockIdx.x * warps_per_block + warp) << chunk_lg;
+#ifdef SX_EXPERIMENTS
+    if (args.exp_stagger > 0) __nanosleep(args.exp_stagger * warp);
+#endif
     Prefetched pf;
     // Where a game's background copy is issued.  The sparse entries must reach L2 while the background lines are
     // still resident there (otherwise every 4-byte store becomes a DRAM read-modify-write; measured: storing them one
@@ -394,7 +398,7 @@ sx_fused_kernel(const __grid_constant__ KernelArgs args)
             uint32_t w[4];
             aux_pack(a, w);
             GT::sync();
-            return gen_moves_cold<K, GT>(&cfg, warp_base, make_uint4(w[0], w[1], w[2], w[3]), me);
+            return gen_moves_cold<K, GT, CM>(&cfg, warp_base, make_uint4(w[0], w[1], w[2], w[3]), me);
         };
         if (MODE == MODE_GENERIC && (ops & OP_RESET) && (args.reset_mask == nullptr || args.reset_mask[env] != 0)) {
             // drawn setups only (explicit setup_idx rows are the caller's choice): see the auto-reset below
@@ -427,7 +431,7 @@ sx_fused_kernel(const __grid_constant__ KernelArgs args)
         if (player_override) viewer = player_override[env] == 1 ? 0 : 1;
         bool any = false;
         const bool have_moves = need_moves && (status == STEP_MOVED || !do_step || do_mask || do_sample || (ops & OP_MASK_1D));
-        if (have_moves) any = gen_moves<K, GT>(cfg, m, a, viewer, false);
+        if (have_moves) any = gen_moves<K, GT, CM>(cfg, m, a, viewer, false);
 
         if (status == STEP_MOVED) {
             if (have_moves && !any && !a.over) { a.over = 1; a.winner = mover == 0 ? 1 : -1; }  // impl:1031-1036
@@ -508,6 +512,9 @@ sx_fused_kernel(const __grid_constant__ KernelArgs args)
             if (flags & SX_TUNE_COMMIT_GAP) GT::sync();  // keeps commit_group and wait_group apart (see SX_TUNE_COMMIT_GAP)
         }
         if (do_tile && !SX_EXP(flags, 0x20000u)) {
+#ifdef SX_EXPERIMENTS
+            if (args.exp_nap > 0) __nanosleep(args.exp_nap);
+#endif
             if (lane == 0) bulk_wait_all();  // this game's background is in global memory
             GT::sync();
             if (SX_EXP(flags, 0x80000u)) continue;  // experiment: wait but skip the sparse stores
@@ -1049,6 +1056,10 @@ extern "C" int sx_config_create(const sx_config_desc *desc, sx_config **out)
     const int lanes = 32 / c->games_per_warp;
     const int k = (d.N + lanes - 1) / lanes;
     c->cells_per_lane = k <= 2 ? 2 : k <= 4 ? 4 : 8;
+    // dense boards of the 10x10 class: movers are handed to lanes (measured: Standard, 40 pieces a side, +4 %; Barrage, 8
+    // pieces, -3 %; profiles/r3g_all_boards.txt)
+    c->compact_movers = c->cells_per_lane == 4 && c->games_per_warp == 1 && pieces > 16;
+    if (const int cm = env_int("SX_COMPACT", -1); cm >= 0) c->compact_movers = cm != 0 && c->cells_per_lane == 4 && c->games_per_warp == 1;
     sx_layout &l = c->layout;
     l.rows = d.R; l.cols = d.C; l.cells = d.N; l.spatial_channels = d.A; l.spatial_actions = d.mask_bytes;
     l.action_size = d.action_size; l.board_stride = d.board_stride; l.aux_stride = 8; l.captured_stride = d.cap_stride;
@@ -1060,6 +1071,21 @@ extern "C" int sx_config_create(const sx_config_desc *desc, sx_config **out)
 
 extern "C" void sx_config_destroy(sx_config *cfg) { delete cfg; }
 
+// Result-preserving launch tuning (include/stratego_b200.h): lets tools/sweep_fused.py time the SHIPPED library under
+// other launch shapes than the built-in ones.  None of the three settings changes a result.
+extern "C" int sx_config_set_tuning(sx_config *cfg, int32_t warps_per_block, int32_t issue_point, int32_t compact_movers)
+{
+    if (!cfg) return fail("sx_config_set_tuning: null config");
+    if (warps_per_block > 32 || issue_point > 2) return fail("sx_config_set_tuning: warps_per_block <= 32, issue_point 0..2");
+    if (warps_per_block >= 0) cfg->tune_warps = warps_per_block;
+    if (issue_point >= 0) cfg->tune_issue = issue_point;
+    if (compact_movers >= 0) {
+        cfg->compact_movers = compact_movers != 0 && cfg->cells_per_lane == 4 && cfg->games_per_warp == 1;
+        cfg->compact_forced = true;
+    }
+    return 0;
+}
+
 extern "C" int sx_config_layout(const sx_config *cfg, sx_layout *out)
 {
     if (!cfg || !out) return fail("sx_config_layout: null argument");
@@ -1068,16 +1094,16 @@ extern "C" int sx_config_layout(const sx_config *cfg, sx_layout *out)
 }
 
 typedef void (*fused_fn)(const KernelArgs);
-template <int K, int G>
+template <int K, int G, bool CM = false>
 static fused_fn fused_for_mode(int mode)
 {
     switch (mode) {
-    case MODE_STEP_PO_MASK: return sx_fused_kernel<K, MODE_STEP_PO_MASK, G>;
-    case MODE_STEP_PO_FO_MASK: return sx_fused_kernel<K, MODE_STEP_PO_FO_MASK, G>;
-    case MODE_STEP_LEAN: return sx_fused_kernel<K, MODE_STEP_LEAN, G>;
-    case MODE_MASK: return sx_fused_kernel<K, MODE_MASK, G>;
-    case MODE_OBSERVE_PO_MASK: return sx_fused_kernel<K, MODE_OBSERVE_PO_MASK, G>;
-    default: return sx_fused_kernel<K, MODE_GENERIC, G>;
+    case MODE_STEP_PO_MASK: return sx_fused_kernel<K, MODE_STEP_PO_MASK, G, CM>;
+    case MODE_STEP_PO_FO_MASK: return sx_fused_kernel<K, MODE_STEP_PO_FO_MASK, G, CM>;
+    case MODE_STEP_LEAN: return sx_fused_kernel<K, MODE_STEP_LEAN, G, CM>;
+    case MODE_MASK: return sx_fused_kernel<K, MODE_MASK, G, CM>;
+    case MODE_OBSERVE_PO_MASK: return sx_fused_kernel<K, MODE_OBSERVE_PO_MASK, G, CM>;
+    default: return sx_fused_kernel<K, MODE_GENERIC, G, CM>;
     }
 }
 // (cells per lane, games per warp) instantiations: (2,4) boards up to 4x4, (2,2) up to 5x5 (both dimensions must fit
@@ -1089,7 +1115,15 @@ static fused_fn fused_for(const sx_config *cfg, int mode)
     if (g == 2) return fused_for_mode<2, 2>(mode);
     switch (k) {
     case 2: return fused_for_mode<2, 1>(mode);
-    case 4: return fused_for_mode<4, 1>(mode);
+    case 4: {
+        // measured on the shipped library (profiles/r3o_shipped_tuning_sweep.txt): Standard with one observation 169.0 ->
+        // 176.0 M env-steps/s with compact movers, with both observations 89.9 -> 88.1 M (6 warps per SM there)
+        // (observe-only launches: 0.730 -> 0.753 ms per 131 072 Standard games; mask-only 0.252 -> 0.201 ms, lean step 0.243
+        // -> 0.188 ms, profiles/r3p_all_boards.txt)
+        const bool compact = cfg->compact_movers &&
+                             (cfg->compact_forced || (mode != MODE_STEP_PO_FO_MASK && mode != MODE_OBSERVE_PO_MASK));
+        return compact ? fused_for_mode<4, 1, true>(mode) : fused_for_mode<4, 1>(mode);
+    }
     default: return fused_for_mode<8, 1>(mode);
     }
 }
@@ -1164,7 +1198,7 @@ static int plan_launch_uncached(const sx_config *cfg, uint32_t ops, int mode, lo
     const int small_board = std::max(8, std::min(32, (232 * 1024 + tile_bytes / 2) / std::max(1, tile_bytes)));
     const int preferred = tile_bytes <= 8 * 1024 ? 32 : tile_bytes <= 32 * 1024 ? (cfg->dev.N >= 100 ? 8 : small_board)
                           : tile_bytes <= 64 * 1024 ? 6 : 10;  // 15x15 (74 KB per game): 4 warps 39 M, 6: 55 M, 8: 69 M, 10: 75 M env-steps/s
-    int warps = std::min(max_warps, std::max(1, env_int("SX_WARPS", std::min(max_warps, preferred))));
+    int warps = std::min(max_warps, std::max(1, env_int("SX_WARPS", std::min(max_warps, cfg->tune_warps > 0 ? cfg->tune_warps : preferred))));
     const int games = cfg->games_per_warp;  // each game of a warp has its own slice
     while (warps > 1 && tile_bytes + warps * games * warp_bytes > max_smem_optin) --warps;
     const int smem = tile_bytes + warps * games * warp_bytes;
@@ -1309,6 +1343,8 @@ static int launch_fused(const sx_config *cfg, KernelArgs &args, cudaStream_t str
     // launches without a step (sx_observe, sx_valid_mask, the observe pass of a reset) issue their copies late
     if (!(args.ops & OP_STEP)) args.flags |= SX_TUNE_COMMIT_GAP;
     args.chunk_log2 = std::max(0, std::min(10, env_int("SX_CHUNK_LOG2", 0)));
+    args.exp_nap = env_int("SX_NAP", 0);
+    args.exp_stagger = env_int("SX_STAGGER", 0);
     if (const int gap = env_int("SX_GAP", -1); gap >= 0) args.flags = gap ? (args.flags | SX_TUNE_COMMIT_GAP) : (args.flags & ~SX_TUNE_COMMIT_GAP);
     // (Tried and removed: marking the state range as persisting in L2 with an access-policy window.  A pure store
     // stream loses ~8 % when the ~0.2 KB/game state reads come from DRAM (tools/probes/probe_write.cu), but any L2
@@ -1475,7 +1511,7 @@ extern "C" int sx_step_all(const sx_config *cfg, sx_state st, int64_t num_envs, 
     const bool one_obs = (out.partial_obs != nullptr) != (out.full_obs != nullptr);
     const int n = cfg->dev.N;
     const bool ten_by_ten = n >= 100 && n <= 128;
-    const int tune = env_int("SX_DEBUG", (ten_by_ten && one_obs) ? 16 : 0);
+    const int tune = env_int("SX_DEBUG", cfg->tune_issue >= 0 ? cfg->tune_issue << 4 : (ten_by_ten && one_obs) ? 16 : 0);
     a.flags = (flags & 0xffffu) | (uint32_t(tune) << 16);
     if ((tune & 0x30) == 0 && !ten_by_ten) a.flags |= SX_TUNE_COMMIT_GAP;  // late issue, not the 10x10 board
     a.out = out;

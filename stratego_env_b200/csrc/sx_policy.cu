@@ -116,7 +116,7 @@ __global__ void __launch_bounds__(256) sx_sample_logits_kernel(const T *logits, 
 // with the engine's own move generator (gen_moves: occupancy bit-lines), spreads the valid entries evenly over the lanes
 // and runs the identical Gumbel-max / log-sum-exp per entry.  Same Philox key per (game, step, entry)
 // and the same tie rule as the mask kernel, so both return the SAME action for the same key.
-template <typename T, int K, bool LOGPROB>
+template <typename T, int K, bool LOGPROB, bool CM = false>
 __global__ void __launch_bounds__(256) sx_sample_policy_kernel(const __grid_constant__ DevConfig cfg, const uint8_t *board,
                                                                const int16_t *aux, long long num_envs, long long env_base,
                                                                const T *logits, uint2 key, uint32_t step, float inv_temperature,
@@ -141,7 +141,7 @@ __global__ void __launch_bounds__(256) sx_sample_policy_kernel(const __grid_cons
         aux_unpack(w, a);
     }
     __syncwarp();
-    const bool any = gen_moves<K, GT>(cfg, m, a, a.to_move, false);  // the mover's frame, like the mask (maenv:452-454)
+    const bool any = gen_moves<K, GT, CM>(cfg, m, a, a.to_move, false);  // the mover's frame, like the mask (maenv:452-454)
     if (!any) {  // finished game or stuck player: the mask holds the noop entry [0,0,A-1] only (impl:514-515)
         if (lane == 0) {
             actions[env] = cfg.A - 1;
@@ -274,6 +274,8 @@ static cudaError_t launch_policy(const sx_config *cfg, sx_state st, int64_t num_
     };
     const bool lp = logprob != nullptr;
     if (d.N <= 64) lp ? launch(sx_sample_policy_kernel<T, 2, true>) : launch(sx_sample_policy_kernel<T, 2, false>);
+    else if (d.N <= 128 && cfg->compact_movers)
+        lp ? launch(sx_sample_policy_kernel<T, 4, true, true>) : launch(sx_sample_policy_kernel<T, 4, false, true>);
     else if (d.N <= 128) lp ? launch(sx_sample_policy_kernel<T, 4, true>) : launch(sx_sample_policy_kernel<T, 4, false>);
     else lp ? launch(sx_sample_policy_kernel<T, 8, true>) : launch(sx_sample_policy_kernel<T, 8, false>);
     return cudaGetLastError();

@@ -116,6 +116,11 @@ class StrategoEngine:
         self.spatial_action_size = (self.rows, self.columns, lay.spatial_channels)
         self.action_size = lay.action_size
 
+    def set_tuning(self, warps_per_block: int = -1, issue_point: int = -1, compact_movers: int = -1) -> None:
+        """Result-preserving launch tuning of the warp-level kernel (sx_config_set_tuning; -1 keeps the built-in choice)."""
+        _lib.check(self.lib.sx_config_set_tuning(self._cfg, int(warps_per_block), int(issue_point), int(compact_movers)),
+                   "sx_config_set_tuning")
+
     def __del__(self):
         try:
             if getattr(self, "_cfg", None):

@@ -50,6 +50,12 @@ def test_config_validation_without_gpu():
         (10, 10, 100, 37, 3700, 2001)                     # impl:253-259
     assert (lay.po_floats, lay.fo_floats, lay.pieces_per_side, lay.setup_len) == (6700, 7900, 8, 40)
     assert lay.board_stride % 16 == 0 and lay.captured_stride >= 16
+    # launch tuning is host state only: accepted ranges, -1 keeps, null config rejected
+    assert lib.sx_config_set_tuning(handle, 10, 2, 1) == 0
+    assert lib.sx_config_set_tuning(handle, -1, -1, -1) == 0
+    assert lib.sx_config_set_tuning(handle, 33, 0, 0) != 0 and b"warps_per_block" in lib.sx_last_error()
+    assert lib.sx_config_set_tuning(handle, 8, 3, 0) != 0
+    assert lib.sx_config_set_tuning(None, 8, 1, 0) != 0
     lib.sx_config_destroy(handle)
     desc.rows = 2
     assert lib.sx_config_create(ctypes.byref(desc), ctypes.byref(handle)) != 0

@@ -504,16 +504,20 @@ def _synthetic_states(R, C, n, rng):
     return states
 
 
-@pytest.mark.parametrize("shape", [(10, 10), (4, 4), (3, 4), (6, 6)])
-def test_fused_step_on_synthetic_states_vs_oracle(shape):
+@pytest.mark.parametrize("shape,config_lakes", [((10, 10), False), ((10, 10), True), ((4, 4), False), ((3, 4), False),
+                                                ((6, 6), False)])
+def test_fused_step_on_synthetic_states_vs_oracle(shape, config_lakes):
     """the fused step on synthetic boards (every rank on every board size, incl. scouts / bombs / spies on the toy boards
-    through the thread-per-game kernel): legality, next state, next mask and raw observations against the oracle"""
+    through the thread-per-game kernel): legality, next state, next mask and raw observations against the oracle.
+    config_lakes: the engine's configuration has the standard lakes (its background image then carries them) while the
+    imported boards have their own random lakes -- both kinds of disagreement must still render exactly."""
     from oracle.binding import OracleProceduralEnv
     from stratego_env_b200.engine import StrategoEngine
     R, C = shape
     rng = np.random.default_rng(R * 1000 + C)
     n = 256
-    cfg = {'rows': R, 'columns': C, 'max_turns': 40, 'obstacle_locations': [], 'piece_amounts': {},
+    lakes = [(4, 2), (5, 2), (4, 3), (5, 3), (4, 6), (5, 6), (4, 7), (5, 7)] if config_lakes else []
+    cfg = {'rows': R, 'columns': C, 'max_turns': 40, 'obstacle_locations': lakes, 'piece_amounts': {},
            'initial_state_usable_rows': 1}
     eng = StrategoEngine(cfg, device="cuda:0", normalize=False, capture_capacity=8 if R * C <= 16 else R * C)
     orc = OracleProceduralEnv(R, C)

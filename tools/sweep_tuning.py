@@ -1,11 +1,7 @@
-"""Tuning sweep of the fused step (development aid): one process, one de-phased state, many (warps per SM, SX_DEBUG)
-settings.  The knobs exist only in an EXPERIMENTS build of the library (the shipped one never reads the environment):
-    python -c "from stratego_env_b200 import _build; print(_build.build_experiments('exp'))"
-    SX_LIB=stratego_env_b200/csrc/libstratego_b200_exp.so python tools/sweep_fused.py <workload> "<W>:<debug>[:<nap ns>:<stagger ns>:<chunk log2>:<compact 0/1>:<lakes 0/1>],..." [envs]
-Other knobs of that build: SX_CHUNK_LOG2 (runs of consecutive games per warp), SX_BLOCKS, SX_TOY_WARPS, SX_GAP.
-SX_DEBUG bits (sx_step_all): 1 skip TMA, 2 skip wait + sparse stores, 8 skip sparse stores, 16 / 32 background issue
-point (0 late, 16 after outcome, 32 top of the game), 64 no state write-back, 128 output skeleton only."""
-import os
+"""Launch-shape sweep of the SHIPPED library through sx_config_set_tuning (result-preserving knobs only): one process,
+one de-phased state, many (warps per SM, issue point, compact movers) settings; `-` keeps the built-in choice.
+    python tools/sweep_tuning.py <workload> "<warps>:<issue 0|1|2>:<compact 0|1>,..." [envs]
+(tools/sweep_fused.py does the same for an EXPERIMENTS build and its result-changing switches.)"""
 import sys
 
 import torch
@@ -17,21 +13,14 @@ from stratego_env_b200.engine import StrategoEngine, load_setup_table  # noqa: E
 
 
 def main():
-    if not os.environ.get("SX_LIB"):
-        raise SystemExit("set SX_LIB to an experiments build of the library (see the docstring): the shipped library "
-                         "ignores SX_WARPS / SX_DEBUG")
     wl = sys.argv[1] if len(sys.argv) > 1 else "barrage"
-    combos = [tuple(c.split(":")) for c in (sys.argv[2] if len(sys.argv) > 2 else "10:32").split(",")]
+    combos = [tuple(c.split(":")) for c in (sys.argv[2] if len(sys.argv) > 2 else "-:-:-").split(",")]
     w = WORKLOADS[wl]
     B = int(sys.argv[3]) if len(sys.argv) > 3 else w["envs"]
     cfg = VERSION_CONFIGS[as_version(w["version"])]
     table = load_setup_table(w["table"]) if w["table"] else None
     shuffle = table is None
-
-    def engine():
-        return StrategoEngine(cfg, device="cuda:0", p2_rot180=table is None)
-
-    eng = engine()
+    eng = StrategoEngine(cfg, device="cuda:0", p2_rot180=table is None)
     setups = eng.upload_setups(table) if table is not None else None
     st0 = eng.alloc_state(B)
     eng.reset(st0, seed=1, setups=setups, shuffle=shuffle)
@@ -48,14 +37,9 @@ def main():
     lay = eng.layout
     nbytes = algorithmic_bytes_per_step(lay.cells, lay.spatial_channels, lay.pieces_per_side, w["full"])
     out = eng.alloc_outputs(B, partial=True, full=w["full"], mask=True, sample=True)
-    for warps, debug, *extra in combos:
-        for k, v in (("SX_WARPS", warps), ("SX_DEBUG", debug)) + tuple(zip(("SX_NAP", "SX_STAGGER", "SX_CHUNK_LOG2", "SX_COMPACT", "SX_LAKES"),
-                                                                          tuple(extra) + ("-",) * (5 - len(extra)))):
-            if v in ("", "-"):
-                os.environ.pop(k, None)
-            else:
-                os.environ[k] = v
-        e = engine()
+    for combo in combos:
+        e = StrategoEngine(cfg, device="cuda:0", p2_rot180=table is None)
+        e.set_tuning(*[-1 if v in ("", "-") else int(v) for v in combo])
         st, acts = st0.clone(), a0.clone()
         times = []
         for rep in range(3):
@@ -72,8 +56,8 @@ def main():
                     times.append(e0.elapsed_time(e1) / n)
         ms = min(times)
         info = e.launch_info(partial=True, full=w["full"], mask=True)
-        print("%-14s W=%-3s debug=%-4s %-9s warps %2d regs %3d : %7.3f ms  %6.1f M env-steps/s  %5.0f GB/s  frac %.3f  (reps %s)" % (
-            wl, warps, debug, ":".join(extra), info["warps_per_block"], info["regs_per_thread"], ms, B / ms / 1e3, B * nbytes / ms / 1e6,
+        print("%-14s warps:issue:compact=%-8s warps %2d regs %3d : %7.3f ms  %6.1f M env-steps/s  %5.0f GB/s  frac %.3f  (reps %s)" % (
+            wl, ":".join(combo), info["warps_per_block"], info["regs_per_thread"], ms, B / ms / 1e3, B * nbytes / ms / 1e6,
             B * nbytes / ms / 1e6 / 6546.6, " ".join("%.3f" % t for t in times)), flush=True)
 
 
