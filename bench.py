@@ -473,8 +473,35 @@ def run_gpu_arm(args):
                     "h2d_bytes_per_step": h2d * world, "d2h_bytes_per_step": d2h * world, "steps": e2e_steps,
                     "envs_per_gpu": e2e_B, "d2h_GBps_aggregate": d2h * world * e2e_steps / secs / 1e9, "what": what}
 
+        def bare_d2h_GBps(nbytes=2 << 30, reps=3):
+            """bare device -> pinned-host copies on THIS box, all ranks at once (no engine involved): the ceiling the
+            e2e path is measured against.  Outside every timed region."""
+            dev = torch.empty(nbytes, dtype=torch.uint8, device=device)
+            host = torch.empty(nbytes, dtype=torch.uint8, pin_memory=True)
+            host.copy_(dev, non_blocking=True)
+            best = 0.0
+            for _ in range(reps):
+                barrier()
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                host.copy_(dev, non_blocking=True)
+                e1.record()
+                torch.cuda.synchronize(device)
+                ms = max_over_ranks(e0.elapsed_time(e1))
+                best = max(best, world * nbytes / (ms * 1e-3) / 1e9)
+            del dev, host
+            return best
+
         def link(entry):
-            """what the box's host link can do with bare copies at this GPU count (profiles/host_link.json)"""
+            """what the box's host link can do with bare copies at this GPU count: measured now (live) and the committed
+            probe of the 8-GPU box (profiles/host_link.json)"""
+            try:
+                live = bare_d2h_GBps()
+                entry["host_link_live"] = {"bare_copy_d2h_GBps": live, "fraction_of_bare_copy": entry["d2h_GBps_aggregate"] / live,
+                                           "how": "2 GiB cudaMemcpyAsync device -> pinned host per rank, all ranks at once, "
+                                                  "best of 3, measured on this box right after the e2e leg"}
+            except Exception as exc:  # noqa: BLE001
+                entry["host_link_live"] = {"error": repr(exc)[:200]}
             try:
                 with open(os.path.join(ROOT, "profiles", "host_link.json")) as f:
                     probe = json.load(f)["d2h_GBps"].get(str(world))
