@@ -3,6 +3,7 @@
 TAG=${1:-r2i}
 OUT=gpurun_out/${TAG}_sanitizer.txt
 mkdir -p gpurun_out
+if [ "$2" != "compact" ]; then
 echo "compute-sanitizer on a B200 (gpurun), library built from the current tree (round 2: spatial aliasing decode, re-draws, batched options, terminal observations, state-based sampler):" > $OUT
 echo "== memcheck: batched options (same setup / other side / terminal observations), device resets, spatial aliasing (micro, tiny)" >> $OUT
 timeout 1500 compute-sanitizer --tool memcheck python -m pytest tests/test_batched_options_gpu.py tests/test_device_reset_gpu.py tests/test_spatial_alias_gpu.py -x -q \
@@ -16,3 +17,13 @@ timeout 900 compute-sanitizer --tool racecheck python __graft_entry__.py smoke 2
 echo "== synccheck: repeat-from-other-side reset + terminal observations (short_barrage)" >> $OUT
 timeout 900 compute-sanitizer --tool synccheck python -m pytest tests/test_batched_options_gpu.py -x -q -k "short_barrage and (other_side or terminal)" 2>&1 | grep -E "COMPUTE-SANITIZER|passed|failed|ERROR SUMMARY" | head >> $OUT
 cat $OUT
+fi
+if [ "$2" = "compact" ]; then
+OUT2=gpurun_out/${TAG}_sanitizer_compact.txt
+echo "compute-sanitizer over gen_moves<.., COMPACT> (movers handed to lanes): Standard, 192 games x 6 fused steps + observe + state-based sampler, compact 0 and 1 compared (tools/sanitize_compact.py)" > $OUT2
+for tool in memcheck racecheck synccheck; do
+  echo "== $tool" >> $OUT2
+  timeout 900 compute-sanitizer --tool $tool python tools/sanitize_compact.py 2>&1 | grep -E "COMPUTE-SANITIZER|sanitize run ok|SUMMARY|hazard|Invalid|Error" | head -12 >> $OUT2
+done
+cat $OUT2
+fi
