@@ -148,6 +148,18 @@ int sx_config_layout(const sx_config *cfg, sx_layout *out);
  *   compact_movers   0 / 1: move generation hands the movable pieces to lanes instead of walking cells (10x10 class) */
 int sx_config_set_tuning(sx_config *cfg, int32_t warps_per_block, int32_t issue_point, int32_t compact_movers);
 
+/* Curriculum start states (curriculum_start_states_path, maenv:341-351 / 519-527, util:373-387): from now on every
+ * (re)set of a game with this configuration -- sx_reset and the auto-reset inside sx_step_all -- copies a uniformly
+ * drawn entry of `table` (n_states compact states, e.g. made with sx_import_ref_state from the file's dense states)
+ * instead of dealing setups; the turn counter restarts at 0 with the configured max_turns (util:382-383) and the player
+ * to move is drawn uniformly (maenv:523).  The table must stay allocated while it is set.  n_states = 0 (or a NULL
+ * board pointer) switches back to setups.
+ * start_index_d (optional, device, int32): start_index_d[global env id - index_env_base] receives the entry every game
+ * was (re)started from -- maenv:524-527 maps the players through the entry's likely winner.  Global env id = env_base +
+ * the env's position in the call, as everywhere else. */
+int sx_config_set_start_states(sx_config *cfg, sx_state table, int64_t n_states, int32_t *start_index_d,
+                               int64_t index_env_base);
+
 /* Replaces penv.create_initial_state (penv:38 -> impl:213-249) + the setup samplers
  * (util:33-53 random, util:301-319 human).  Re-sets every env b with reset_mask_d[b] != 0 (all when
  * NULL).  Setups come from `setups_d` ([n_setups][setup_len] own-frame piece maps): rows

@@ -22,6 +22,7 @@ Semantics that differ from the one-game API because many games advance at once:
 """
 from typing import Optional
 
+import numpy as np
 import torch
 
 from . import sharding
@@ -42,13 +43,16 @@ class BatchedStrategoEnv:
         self.version = cfg['version']
         version_config = VERSION_CONFIGS[self.version]
         cfg = with_base_config(version_config, cfg)
-        for key in ('vs_human', 'vs_bot', 'curriculum_start_states_path'):
+        for key in ('vs_human', 'vs_bot'):
             if cfg[key]:
                 raise NotImplementedError("%s is a single-game option (use StrategoMultiAgentEnv)" % key)
+        assert not (cfg['human_inits'] and cfg['curriculum_start_states_path'])  # maenv:332
+        self.use_curriculum_inits = bool(cfg['curriculum_start_states_path'])
         self.same_start_pos_everytime = bool(cfg['same_start_pos_everytime'])
         self.repeat_games_from_other_side = bool(cfg['repeat_games_from_other_side'])
         self.random_player_assignment = bool(cfg['random_player_assignment'])
         assert not (self.random_player_assignment and self.repeat_games_from_other_side)  # maenv:358
+        assert not (self.use_curriculum_inits and (self.random_player_assignment or self.repeat_games_from_other_side))
         self.terminal_observations = bool(terminal_observations)
         mode = cfg['observation_mode']
         mode = mode if isinstance(mode, ObservationModes) else ObservationModes(mode)
@@ -78,6 +82,15 @@ class BatchedStrategoEnv:
         self._map_rng = torch.Generator(device=self.device)
         self._map_rng.manual_seed((self.seed * 1000003 + self.env_base) & (2 ** 62 - 1))
         self.stats = torch.zeros(8, dtype=torch.int64, device=self.device)
+        # curriculum starts (maenv:341-351, 519-527): every game starts from a drawn entry of the file's states, the player
+        # to move is drawn, and agent +1 is the entry's likely winner ("player 1 gets the advantage", maenv:525-527)
+        self._start_index = self._likely_winner = None
+        if self.use_curriculum_inits:
+            from . import setups as _setups
+            states, winners = _setups.load_curriculum_table(cfg['curriculum_start_states_path'])
+            self._likely_winner = torch.as_tensor(np.asarray(winners), dtype=torch.int8, device=self.device)
+            self._start_index = self.engine.set_start_states(torch.as_tensor(np.asarray(states)), self.num_envs,
+                                                             self.env_base)
         self._spare_actions = torch.zeros(self.num_envs, dtype=torch.int32, device=self.device) if sample_actions else None
 
     @classmethod
@@ -98,7 +111,7 @@ class BatchedStrategoEnv:
         self.player_map = new if where is None else torch.where(where, new, self.player_map)
 
     def _obs(self) -> dict:
-        player = self.out["player"] * self.player_map if self.random_player_assignment else self.out["player"]
+        player = self.out["player"] * self.player_map if self._mapped else self.out["player"]
         d = {OC.VALID_ACTIONS_MASK.value: self.out["valid_mask"], "player": player}
         if self._po:
             d[OC.PARTIAL_OBSERVATION.value] = self.out["partial_obs"]
@@ -110,6 +123,15 @@ class BatchedStrategoEnv:
             d["sampled_action"] = self.out["next_action"]
         return d
 
+    @property
+    def _mapped(self) -> bool:
+        """agent ids differ from internal player ids: random_player_assignment (maenv:537-543) or curriculum (maenv:524-527)"""
+        return self.random_player_assignment or self.use_curriculum_inits
+
+    def _curriculum_player_map(self):
+        """maenv:526: player_map(p) = p * likely_winner of the entry the env's current game was started from"""
+        self.player_map = self._likely_winner[self._start_index.long()]
+
     def reset(self, reset_mask: Optional[torch.Tensor] = None) -> dict:
         """(re)starts every game (or those with reset_mask[b] != 0) from freshly sampled setups"""
         self.engine.reset(self.state, seed=self.seed, env_base=self.env_base, reset_mask=reset_mask,
@@ -117,6 +139,8 @@ class BatchedStrategoEnv:
                           repeat_other_side=self.repeat_games_from_other_side)
         if self.random_player_assignment:
             self._draw_player_map(None if reset_mask is None else reset_mask != 0)
+        if self.use_curriculum_inits:
+            self._curriculum_player_map()
         self.engine.observe(self.state, out=self.out, partial=self._po, full=self._fo, mask=True)
         if self.sample_actions:
             self.out["next_action"] = self.engine.sample_valid(self.out["valid_mask"], seed=self.seed, step=0,
@@ -150,7 +174,7 @@ class BatchedStrategoEnv:
         dones = out["done"]
         infos = {"winner": out["winner"], "game_result_was_invalid": out["ending_invalid"],
                  "illegal_action": out["illegal"]}
-        if self.random_player_assignment:  # maenv:807-811: everything keyed by player is re-keyed by agent id
+        if self._mapped:  # maenv:807-811: everything keyed by player is re-keyed by agent id
             m = self.player_map
             rewards = {1: torch.where(m == 1, reward_p1, reward_p2), -1: torch.where(m == 1, reward_p2, reward_p1)}
             infos["winner"] = out["winner"] * m
@@ -161,12 +185,15 @@ class BatchedStrategoEnv:
             for key, name in ((OC.PARTIAL_OBSERVATION.value, "terminal_partial_obs"), (OC.FULL_OBSERVATION.value, "terminal_full_obs")):
                 if name in out:
                     t = out[name]
-                    if self.random_player_assignment:
+                    if self._mapped:
                         swap = (self.player_map == -1).view(-1, 1, 1, 1, 1)
                         t = torch.where(swap, t.flip(1), t)
                     term[key] = t
             infos["terminal_observation"] = {1: {k: v[:, 0] for k, v in term.items()}, -1: {k: v[:, 1] for k, v in term.items()}}
         obs = self._obs()
+        if self.use_curriculum_inits and self.auto_reset:
+            self._curriculum_player_map()  # the kernel re-started the finished games from freshly drawn entries
+            obs["player"] = self.out["player"] * self.player_map
         if self.random_player_assignment and self.auto_reset:
             # games that ended were re-set inside the kernel and the returned observation already belongs to their NEXT
             # game: that game gets a fresh agent map (maenv:537-543), and its `player` is expressed in it

@@ -846,6 +846,41 @@ static __device__ __noinline__ uint4 reset_game(const DevConfig *cfg, uint8_t *w
     return make_uint4(w[0], w[1], w[2], w[3]);
 }
 
+// Curriculum start (util:373-387, maenv:519-527): the game staged at `warp_base` becomes a uniformly drawn entry of a table
+// of compact states; the turn counter restarts at 0 with the configured max_turns (util:382-383), the player to move is
+// drawn uniformly (maenv:523), the markers of recent moves and the captured pieces stay as the entry has them.  Same
+// Philox stream as a setup draw (RNG_RESET, attempt number, episode).  Returns the packed aux words.
+template <class GT>
+static __device__ __noinline__ uint4 reset_from_table(const DevConfig *cfg, uint8_t *warp_base, const uint8_t *t_board,
+                                                      const int16_t *t_aux, const uint16_t *t_cap, uint32_t n_states,
+                                                      uint32_t attempt, uint2 key, uint64_t gid, uint32_t episode,
+                                                      uint32_t rng_episode, int32_t *index_out)
+{
+    WarpMem m;
+    carve_warp(*cfg, warp_base, &m);
+    const int lane = GT::lane();
+    const uint4 rnd = philox4x32_10(make_uint4(uint32_t(gid), uint32_t(gid >> 32), RNG_RESET + 64u * attempt, rng_episode), key);
+    const size_t idx = __umulhi(rnd.x, n_states);
+    GT::sync();
+    const uint32_t *gb = reinterpret_cast<const uint32_t *>(t_board + idx * cfg->board_stride);
+    const uint32_t *gc = reinterpret_cast<const uint32_t *>(t_cap + idx * cfg->cap_stride);
+    for (int i = lane; i < (cfg->board_stride >> 2); i += GT::L) reinterpret_cast<uint32_t *>(m.board)[i] = gb[i];
+    for (int i = lane; i < (cfg->cap_stride >> 1); i += GT::L) reinterpret_cast<uint32_t *>(m.cap)[i] = gc[i];
+    const uint4 aw = *reinterpret_cast<const uint4 *>(t_aux + idx * 8);
+    const uint32_t w0[4] = {aw.x, aw.y, aw.z, aw.w};
+    Aux a;
+    aux_unpack(w0, a);
+    a.turn = 0;
+    a.max_turns = cfg->max_turns;
+    a.to_move = int(rnd.y & 1u);
+    a.episode = episode + 1;
+    if (index_out != nullptr && lane == 0) *index_out = int32_t(idx);
+    GT::sync();
+    uint32_t w[4];
+    aux_pack(a, w);
+    return make_uint4(w[0], w[1], w[2], w[3]);
+}
+
 // ---- observation tiles (impl:1232-1397 + maenv:499-508) ---------------------------------------------
 // Channel map of the partial (impl:1306-1332) and full (impl:1200-1227) observations.
 struct ObsMap {

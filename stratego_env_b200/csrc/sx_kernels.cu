@@ -55,6 +55,12 @@ struct KernelArgs {
     uint2 key;
     long long *stats;
     int chunk_log2;  // log2 of the run of consecutive games a warp takes before it jumps ahead (0 = interleaved)
+    const uint8_t *start_board;  // curriculum table (sx_config_set_start_states), n_start == 0: setups
+    const int16_t *start_aux;
+    const uint16_t *start_cap;
+    uint32_t n_start;
+    int32_t *start_index;  // [global env id - start_index_base], may be null
+    long long start_index_base;
     int exp_nap, exp_stagger;  // experiments builds only: ns to sleep before the copy wait / per warp index at the start
     int warp_bytes;  // shared-memory slice of one game (state + move sets + scratch)
     int tile_bytes;  // the block's background images (0 = this launch renders nothing)
@@ -388,9 +394,12 @@ sx_fused_kernel(const __grid_constant__ KernelArgs args)
             const bool other_side = (flags & SX_REPEAT_OTHER_SIDE) && (episode & 1u);
             const uint32_t rng_episode = (flags & SX_SAME_SETUP) ? 0u : other_side ? episode - 1u : episode;
             const uint32_t draw = uint32_t(attempt) | (other_side ? 256u : 0u) | ((flags & SX_RESET_RANDOM_SHUFFLE) ? 512u : 0u);
-            const uint4 nw = reset_game<GT>(&cfg, warp_base, args.setups, args.n_setups,
-                                        args.setup_idx ? args.setup_idx + env * 2 : nullptr, draw, args.key, gid, episode,
-                                        rng_episode);
+            const uint4 nw = args.n_start != 0
+                ? reset_from_table<GT>(&cfg, warp_base, args.start_board, args.start_aux, args.start_cap, args.n_start,
+                                       uint32_t(attempt), args.key, gid, episode, (flags & SX_SAME_SETUP) ? 0u : episode,
+                                       args.start_index ? args.start_index + (args.env_base + env - args.start_index_base) : nullptr)
+                : reset_game<GT>(&cfg, warp_base, args.setups, args.n_setups,
+                                 args.setup_idx ? args.setup_idx + env * 2 : nullptr, draw, args.key, gid, episode, rng_episode);
             const uint32_t w[4] = {nw.x, nw.y, nw.z, nw.w};
             aux_unpack(w, a);
         };
@@ -1071,12 +1080,31 @@ extern "C" int sx_config_create(const sx_config_desc *desc, sx_config **out)
 
 extern "C" void sx_config_destroy(sx_config *cfg) { delete cfg; }
 
+extern "C" int sx_config_set_start_states(sx_config *cfg, sx_state table, int64_t n_states, int32_t *start_index_d,
+                                          int64_t index_env_base)
+{
+    if (!cfg) return fail("sx_config_set_start_states: null config");
+    if (n_states < 0 || n_states > 0x7fffffffLL) return fail("sx_config_set_start_states: n_states out of range");
+    if (n_states > 0 && table.board != nullptr && (!table.aux || !table.captured))
+        return fail("sx_config_set_start_states: the table needs board, aux and captured tensors");
+    const bool on = n_states > 0 && table.board != nullptr;
+    cfg->start_states = on ? table : sx_state{nullptr, nullptr, nullptr};
+    cfg->n_start_states = on ? n_states : 0;
+    cfg->start_index = on ? start_index_d : nullptr;
+    cfg->start_index_base = index_env_base;
+    return 0;
+}
+
 // Result-preserving launch tuning (include/stratego_b200.h): lets tools/sweep_fused.py time the SHIPPED library under
 // other launch shapes than the built-in ones.  None of the three settings changes a result.
 extern "C" int sx_config_set_tuning(sx_config *cfg, int32_t warps_per_block, int32_t issue_point, int32_t compact_movers)
 {
     if (!cfg) return fail("sx_config_set_tuning: null config");
     if (warps_per_block > 32 || issue_point > 2) return fail("sx_config_set_tuning: warps_per_block <= 32, issue_point 0..2");
+    {
+        std::lock_guard<std::mutex> lock(cfg->plan_mutex);
+        cfg->plans.clear();  // launch shapes are cached per configuration
+    }
     if (warps_per_block >= 0) cfg->tune_warps = warps_per_block;
     if (issue_point >= 0) cfg->tune_issue = issue_point;
     if (compact_movers >= 0) {
@@ -1230,6 +1258,7 @@ static bool toy_eligible(const sx_config *cfg, const KernelArgs &a, int mode)
     const DevConfig &d = cfg->dev;
     if (env_int("SX_TOY", 1) == 0 || (a.flags & (SX_KERNEL_BASELINE | SX_REPEAT_OTHER_SIDE))) return false;
     if (a.out.terminal_partial_obs || a.out.terminal_full_obs) return false;
+    if (cfg->n_start_states > 0) return false;  // curriculum starts are a warp-level kernel feature
     if (mode != MODE_STEP_PO_MASK && mode != MODE_STEP_PO_FO_MASK && mode != MODE_STEP_LEAN) return false;
     if (d.N > 16 || (d.N & 3) != 0 || d.A > 16 || d.board_stride != 16 || d.cap_stride != 8) return false;
     if (d.setup_len > 8 || d.n_pieces > 8 || d.original_channels) return false;
@@ -1307,6 +1336,9 @@ static int launch_toy(const sx_config *cfg, KernelArgs &args, int mode, cudaStre
 static int launch_fused(const sx_config *cfg, KernelArgs &args, cudaStream_t stream)
 {
     if (args.num_envs <= 0) return 0;
+    args.start_board = cfg->start_states.board; args.start_aux = cfg->start_states.aux; args.start_cap = cfg->start_states.captured;
+    args.n_start = cfg->start_states.board ? uint32_t(cfg->n_start_states) : 0u;
+    args.start_index = cfg->start_index; args.start_index_base = cfg->start_index_base;
     LaunchPlan plan;
     const int mode = mode_for(cfg, args);
     if (toy_eligible(cfg, args, mode)) {
@@ -1377,7 +1409,8 @@ extern "C" int sx_reset(const sx_config *cfg, sx_state st, int64_t num_envs, int
                         void *stream)
 {
     if (int rc = check_state(cfg, st, "sx_reset")) return rc;
-    if (!(flags & SX_RESET_RANDOM_SHUFFLE) && (!setups_d || n_setups < 1)) return fail("sx_reset: a setup table or SX_RESET_RANDOM_SHUFFLE is required");
+    if (!(flags & SX_RESET_RANDOM_SHUFFLE) && (!setups_d || n_setups < 1) && cfg->n_start_states == 0)
+        return fail("sx_reset: a setup table or SX_RESET_RANDOM_SHUFFLE is required");
     KernelArgs a;
     base_args(a, st, num_envs, env_base);
     a.ops = OP_RESET | OP_WRITE_STATE;
@@ -1495,7 +1528,7 @@ extern "C" int sx_step_all(const sx_config *cfg, sx_state st, int64_t num_envs, 
     if (int rc = check_state(cfg, st, "sx_step_all")) return rc;
     if (!actions_d) return fail("sx_step_all: null actions");
     if (action_format != SX_ACTION_SPATIAL && action_format != SX_ACTION_1D) return fail("sx_step_all: unknown action format");
-    if ((flags & SX_AUTO_RESET) && !(flags & SX_RESET_RANDOM_SHUFFLE) && (!setups_d || n_setups < 1))
+    if ((flags & SX_AUTO_RESET) && !(flags & SX_RESET_RANDOM_SHUFFLE) && (!setups_d || n_setups < 1) && cfg->n_start_states == 0)
         return fail("sx_step_all: auto-reset needs a setup table or SX_RESET_RANDOM_SHUFFLE");
     if ((out.terminal_partial_obs && !out.partial_obs) || (out.terminal_full_obs && !out.full_obs))
         return fail("sx_step_all: a terminal observation buffer needs its regular observation output in the same call");

@@ -116,6 +116,27 @@ class StrategoEngine:
         self.spatial_action_size = (self.rows, self.columns, lay.spatial_channels)
         self.action_size = lay.action_size
 
+    def set_start_states(self, dense: Optional[torch.Tensor], num_envs: int = 0, env_base: int = 0):
+        """Curriculum starts (curriculum_start_states_path, maenv:341-351 / 519-527, util:373-387): from now on ``reset`` and
+        the auto-reset of ``step_all`` start every game from a uniformly drawn entry of ``dense`` (int64 [n, 34, R, C],
+        the reference's state layout) with the turn counter at 0, this configuration's max_turns and a uniformly drawn
+        player to move, instead of dealing setups.  ``None`` switches back.  Returns an int32 [num_envs] tensor that always
+        holds the entry each env's current game came from (None when num_envs is 0)."""
+        if dense is None:
+            _lib.check(self.lib.sx_config_set_start_states(self._cfg, _lib.SxState(), 0, None, 0), "sx_config_set_start_states")
+            self._start_table = self._start_index = None
+            return None
+        dense = dense.to(self.device, dtype=torch.int64).clone()
+        dense[:, 5, 0, 0] = 0                    # StateData.TURN_COUNT   (util:382)
+        dense[:, 5, 1, 0] = int(self.game_version_config['max_turns'])  # StateData.MAX_TURNS (util:383)
+        table = self.import_ref_state(dense)
+        index = torch.zeros(num_envs, dtype=torch.int32, device=self.device) if num_envs else None
+        _lib.check(self.lib.sx_config_set_start_states(self._cfg, table.as_struct(), table.num_envs,
+                                                       index.data_ptr() if index is not None else None, int(env_base)),
+                   "sx_config_set_start_states")
+        self._start_table, self._start_index = table, index  # the library keeps raw pointers: keep the tensors alive
+        return index
+
     def set_tuning(self, warps_per_block: int = -1, issue_point: int = -1, compact_movers: int = -1) -> None:
         """Result-preserving launch tuning of the warp-level kernel (sx_config_set_tuning; -1 keeps the built-in choice)."""
         _lib.check(self.lib.sx_config_set_tuning(self._cfg, int(warps_per_block), int(issue_point), int(compact_movers)),

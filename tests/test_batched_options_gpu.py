@@ -154,3 +154,73 @@ def test_terminal_observations_for_both_players(version, human, steps, mode):
                 assert np.array_equal(_bits(term[p]["full_observation"][b].cpu().numpy()), _bits(fo)), (version, s, b, p)
             checked += 1
     assert checked >= 20
+
+
+# ---- curriculum start states in the batched path (maenv:341-351, 519-527; util:373-387) ----------------------------------
+def _curriculum_file(tmp_path, version, n=37, seed=5):
+    """a curriculum file made of positions the unmodified reference reached (golden trajectory), with likely winners"""
+    from _golden import traj
+    t = traj(version)
+    rng = np.random.default_rng(seed)
+    states = t["states"].astype(np.int64)
+    live = np.flatnonzero(states[:, 5, 0, 1] == 0)  # StateData.GAME_OVER == 0
+    pick = rng.choice(live, n, replace=False)
+    winners = rng.choice([1, -1], n).astype(np.int64)
+    path = str(tmp_path / ("curriculum_%s.npz" % version))
+    np.savez(path, state=states[pick], winner=winners)
+    return path, states[pick], winners
+
+
+@pytest.mark.parametrize("version", ["barrage", "micro"])
+def test_curriculum_start_states(tmp_path, version):
+    """every game starts from a uniformly drawn entry of the file (turn 0, the variant's max_turns), the player to move is
+    drawn, agent +1 is the entry's likely winner; observations / masks of the started games equal the oracle's, and the
+    auto-reset inside the fused step draws a fresh entry"""
+    from stratego_env_b200.config import VERSION_CONFIGS
+    path, table, winners = _curriculum_file(tmp_path, version)
+    B = 4096
+    env = _env(version, False, num_envs=B, seed=11, terminal_observations=False,
+               config={"curriculum_start_states_path": path})
+    orc = _oracle(env)
+    max_turns = VERSION_CONFIGS[env.version]["max_turns"]
+    expect = table.copy()
+    expect[:, 5, 0, 0] = 0
+    expect[:, 5, 1, 0] = max_turns
+
+    def check_started(envs, dense, player, obs):
+        idx = env._start_index.cpu().numpy()
+        for b in envs:
+            assert np.array_equal(dense[b], expect[idx[b]]), b
+        return idx
+
+    obs = env.reset()
+    dense, player = (x.cpu().numpy() for x in env.export_states())
+    idx = check_started(range(B), dense, player, obs)
+    # uniform over the entries, and the first player is a fair coin independent of the entry
+    counts = np.bincount(idx, minlength=len(table))
+    chi2 = float(((counts - B / len(table)) ** 2 / (B / len(table))).sum())
+    assert chi2 < 90.0, chi2  # 36 degrees of freedom: P(chi2 > 90) ~ 2e-6
+    assert abs(int((player == 1).sum()) - B / 2) < 5 * (B / 4) ** 0.5
+    assert np.array_equal(obs["player"].cpu().numpy(), player * winners[idx])  # maenv:526
+    res = {k: v.cpu().numpy() for k, v in obs.items() if hasattr(v, "cpu")}
+    for b in range(0, B, 257):
+        m, po, fo = orc.current_obs(dense[b], int(player[b]), 3)
+        assert np.array_equal(res["valid_actions_mask"][b], m)
+        assert np.array_equal(_bits(res["partial_observation"][b]), _bits(po))
+        assert np.array_equal(_bits(res["full_observation"][b]), _bits(fo))
+    # play on: finished games restart from a (new) entry inside the fused step
+    restarted = 0
+    for t in range(60):
+        old_map = env.player_map.clone()
+        obs, rewards, dones, infos = env.step(obs["sampled_action"])
+        assert not infos["illegal_action"].any().item()
+        done = np.flatnonzero(dones.cpu().numpy())
+        if len(done):
+            dense, player = (x.cpu().numpy() for x in env.export_states())
+            idx = check_started(done, dense, player, obs)
+            w = infos["winner"].cpu().numpy()
+            raw_w = env.out["winner"].cpu().numpy()
+            assert np.array_equal(w[done], (raw_w * old_map.cpu().numpy())[done])  # the FINISHED game's map
+            assert np.array_equal(obs["player"].cpu().numpy()[done], (player * winners[idx])[done])  # the new game's
+            restarted += len(done)
+    assert restarted > (B // 20 if version == "micro" else 0)
