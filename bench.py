@@ -473,7 +473,7 @@ def run_gpu_arm(args):
                     "h2d_bytes_per_step": h2d * world, "d2h_bytes_per_step": d2h * world, "steps": e2e_steps,
                     "envs_per_gpu": e2e_B, "d2h_GBps_aggregate": d2h * world * e2e_steps / secs / 1e9, "what": what}
 
-        def bare_d2h_GBps(nbytes=2 << 30, reps=3):
+        def bare_d2h_GBps(nbytes=1 << 30, reps=3):
             """bare device -> pinned-host copies on THIS box, all ranks at once (no engine involved): the ceiling the
             e2e path is measured against.  Outside every timed region."""
             dev = torch.empty(nbytes, dtype=torch.uint8, device=device)
@@ -498,7 +498,7 @@ def run_gpu_arm(args):
             try:
                 live = bare_d2h_GBps()
                 entry["host_link_live"] = {"bare_copy_d2h_GBps": live, "fraction_of_bare_copy": entry["d2h_GBps_aggregate"] / live,
-                                           "how": "2 GiB cudaMemcpyAsync device -> pinned host per rank, all ranks at once, "
+                                           "how": "1 GiB cudaMemcpyAsync device -> pinned host per rank, all ranks at once, "
                                                   "best of 3, measured on this box right after the e2e leg"}
             except Exception as exc:  # noqa: BLE001
                 entry["host_link_live"] = {"error": repr(exc)[:200]}
