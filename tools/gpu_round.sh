@@ -7,6 +7,7 @@ mkdir -p gpurun_out
 nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.limit --format=csv > gpurun_out/${TAG}_box.txt 2>&1
 nproc >> gpurun_out/${TAG}_box.txt; lscpu | grep -E "Model name|^CPU\(s\)|Socket|NUMA" >> gpurun_out/${TAG}_box.txt
 timeout 1500 python -m pytest tests -m gpu -x -q > gpurun_out/${TAG}_gpu_tests.log 2>&1; echo "pytest rc=$?" >> gpurun_out/${TAG}_gpu_tests.log
+timeout 300 python -c "import __graft_entry__ as g; g.smoke(); print('smoke ok')" >> gpurun_out/${TAG}_gpu_tests.log 2>&1
 timeout 900 python bench.py --workload $WL > gpurun_out/${TAG}_bench_${WL}.json 2> gpurun_out/${TAG}_bench_${WL}.err
 timeout 600 python bench.py --impl reference --workload $WL --steps 3 --warmup 1 > gpurun_out/${TAG}_bench_reference.json 2>/dev/null
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/${TAG}_${WL}_ncu_launches.csv \
