@@ -1544,7 +1544,10 @@ extern "C" int sx_step_all(const sx_config *cfg, sx_state st, int64_t num_envs, 
     const bool one_obs = (out.partial_obs != nullptr) != (out.full_obs != nullptr);
     const int n = cfg->dev.N;
     const bool ten_by_ten = n >= 100 && n <= 128;
-    const int tune = env_int("SX_DEBUG", cfg->tune_issue >= 0 ? cfg->tune_issue << 4 : (ten_by_ten && one_obs) ? 16 : 0);
+    // boards up to 10x10 with one observation issue the copy after the outcome (shipped-library sweeps, profiles/
+    // r3o_shipped_tuning_sweep.txt, r3y_small_boards_tuning.txt: 8x8 +2.1 %, 6x6 +3.5 %, 5x5 +3.8 % over a late issue); both
+    // observations and the 15x15 board issue late (15x15: 79.8 M late, 76.8 M after the outcome)
+    const int tune = env_int("SX_DEBUG", cfg->tune_issue >= 0 ? cfg->tune_issue << 4 : (n <= 128 && one_obs) ? 16 : 0);
     a.flags = (flags & 0xffffu) | (uint32_t(tune) << 16);
     if ((tune & 0x30) == 0 && !ten_by_ten) a.flags |= SX_TUNE_COMMIT_GAP;  // late issue, not the 10x10 board
     a.out = out;
