@@ -116,6 +116,22 @@ __global__ void __launch_bounds__(256) sx_sample_logits_kernel(const T *logits, 
 // with the engine's own move generator (gen_moves: occupancy bit-lines), spreads the valid entries evenly over the lanes
 // and runs the identical Gumbel-max / log-sum-exp per entry.  Same Philox key per (game, step, entry)
 // and the same tie rule as the mask kernel, so both return the SAME action for the same key.
+// position of the n-th (0-based) set bit of a 64-bit set that has more than n bits: six popcount-guided halvings
+// (one __fns per 32-bit half costs about twice as many instructions)
+__device__ __forceinline__ int nth_set_bit64(uint2 bits, int n)
+{
+    int pos = 0;
+    uint32_t x = bits.x;
+    const int c0 = __popc(bits.x);
+    if (n >= c0) { n -= c0; x = bits.y; pos = 32; }
+#pragma unroll
+    for (int w = 16; w >= 1; w >>= 1) {
+        const int c = __popc(x & ((1u << w) - 1u));
+        if (n >= c) { n -= c; x >>= w; pos += w; }
+    }
+    return pos;
+}
+
 template <typename T, int K, bool LOGPROB, bool CM = false>
 __global__ void __launch_bounds__(256) sx_sample_policy_kernel(const __grid_constant__ DevConfig cfg, const uint8_t *board,
                                                                const int16_t *aux, long long num_envs, long long env_base,
@@ -133,7 +149,12 @@ __global__ void __launch_bounds__(256) sx_sample_policy_kernel(const __grid_cons
     uint16_t *before = reinterpret_cast<uint16_t *>(warp_base + slice);  // [N] running move count per cell
 
     const uint32_t *gb = reinterpret_cast<const uint32_t *>(board + env * cfg.board_stride);
-    for (int i = lane; i < (cfg.board_stride >> 2); i += 32) reinterpret_cast<uint32_t *>(m.board)[i] = gb[i];
+    {   // board_stride <= 256 bytes (K cells per lane, 32 lanes): at most K / 4 words per lane, no loop
+        const int words = cfg.board_stride >> 2;
+#pragma unroll
+        for (int j = 0; j < (K + 3) / 4; ++j)
+            if (lane + 32 * j < words) reinterpret_cast<uint32_t *>(m.board)[lane + 32 * j] = gb[lane + 32 * j];
+    }
     const uint4 aw = *reinterpret_cast<const uint4 *>(aux + env * 8);
     Aux a;
     {
@@ -190,8 +211,7 @@ __global__ void __launch_bounds__(256) sx_sample_policy_kernel(const __grid_cons
             if (int(before[mid]) <= t) lo = mid; else hi = mid;
         }
         const uint2 bits = m.moves[lo];
-        const int r = t - int(before[lo]), c0 = __popc(bits.x);
-        const int ch = r < c0 ? int(__fns(bits.x, 0, r + 1)) : 32 + int(__fns(bits.y, 0, r - c0 + 1));
+        const int ch = nth_set_bit64(bits, t - int(before[lo]));
         const int i = lo * cfg.A + ch;
         const float z = load_logit<T>(lrow + i) * inv_temperature;
         const uint4 rnd = philox4x32_10(make_uint4(uint32_t(gid), uint32_t(gid >> 32), RNG_POLICY ^ step, uint32_t(i)), key);
