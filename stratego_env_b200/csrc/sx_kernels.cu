@@ -650,7 +650,7 @@ __global__ void __launch_bounds__(SX_TOY_THREADS, 1) sx_toy_kernel(const __grid_
             aux_unpack(w, a);
         }
         const int action = pf_action;
-        uint32_t mv[16];
+        toy::MoveSets mv;
 
         // ---- step: decode, validate, apply (impl:897-1028) ----------------------------------------------------
         const int mover = a.to_move;
@@ -693,8 +693,7 @@ __global__ void __launch_bounds__(SX_TOY_THREADS, 1) sx_toy_kernel(const __grid_
                     a.over = 1;
                     a.invalid = 1;
                     total = 0;
-#pragma unroll
-                    for (int p = 0; p < 16; ++p) mv[p] = 0;
+                    toy::clear_sets(mv);
                 }
             }
             done = status != STEP_ILLEGAL && a.over;
@@ -731,9 +730,7 @@ __global__ void __launch_bounds__(SX_TOY_THREADS, 1) sx_toy_kernel(const __grid_
         __syncwarp();  // the mask image is zero
         if (do_mask) {
             uint8_t *row = mask_rows + lane * cfg.mask_bytes;
-#pragma unroll
-            for (int p = 0; p < 16; ++p)
-                for (uint32_t w = mv[p]; w != 0; w &= w - 1) row[p * cfg.A + __ffs(w) - 1] = 1;
+            toy::mark_row(cfg, mv, row);
             if (total == 0) row[cfg.A - 1] = 1;  // [0,0,A-1], impl:514-515
         }
         {

@@ -104,15 +104,68 @@ __device__ __forceinline__ Geometry make_geometry(const DevConfig &cfg)
     return g;
 }
 
-// Valid moves of player index `me` in `me`'s frame (impl:400-517): mv[p] = set of spatial channels of cell p.
-// One-square moves of all pieces come from four shifts of the occupancy sets; scouts (absent from the stock toy
-// variants, possible in custom ones) walk their rays in a rolled loop.  Returns the number of moves.
+// Move sets of a player, CHANNEL-major: bit p of a set = "the piece on cell p (the player's frame) may play this channel".
+// The four one-square channels are exactly the four shifted occupancy sets move generation produces, so nothing is
+// composed per cell; channels of two and more squares exist only with scouts on the board (none in the stock toy
+// variants) and live in `far`, two 16-bit sets per word.  (Round 2: the cell-major mv[16] this replaces cost 189 static /
+// 368 executed instructions per pass to compose and made the mask marking and the sampled-move select 16-way unrolled.)
+struct MoveSets {
+    // named members, not arrays: a run-time index into a register array makes the compiler keep the whole object in
+    // local memory (the same trap as Aux's per-player pairs)
+    uint32_t down, up, right, left;          // one-square channels 0, R-1, 2(R-1), 2(R-1)+C-1 (impl:292-311)
+    uint32_t f0, f1, f2, f3, f4, f5, f6, f7;  // channel c (not a one-square channel): word c >> 1, half c & 1
+    uint32_t any_far;                         // OR of f0..f7: 0 selects the fast paths
+};
+__device__ __forceinline__ void clear_sets(MoveSets &ms)
+{
+    ms.down = ms.up = ms.right = ms.left = 0;
+    ms.f0 = ms.f1 = ms.f2 = ms.f3 = ms.f4 = ms.f5 = ms.f6 = ms.f7 = 0;
+    ms.any_far = 0;
+}
+#define SX_TOY_FAR_WORD(ms, i, STMT)                                                                              \
+    switch (i) {                                                                                                  \
+    case 0: { uint32_t &w = ms.f0; STMT; } break;                                                                 \
+    case 1: { uint32_t &w = ms.f1; STMT; } break;                                                                 \
+    case 2: { uint32_t &w = ms.f2; STMT; } break;                                                                 \
+    case 3: { uint32_t &w = ms.f3; STMT; } break;                                                                 \
+    case 4: { uint32_t &w = ms.f4; STMT; } break;                                                                 \
+    case 5: { uint32_t &w = ms.f5; STMT; } break;                                                                 \
+    case 6: { uint32_t &w = ms.f6; STMT; } break;                                                                 \
+    default: { uint32_t &w = ms.f7; STMT; } break;                                                                \
+    }
+// set / clear (cell p, channel ch) where ch is NOT a one-square channel
+__device__ __forceinline__ void far_put(MoveSets &ms, int ch, int p)
+{
+    const uint32_t v = 1u << (p + 16 * (ch & 1));
+    SX_TOY_FAR_WORD(ms, ch >> 1, w |= v)
+    ms.any_far |= v;
+}
+__device__ __forceinline__ void far_clear(MoveSets &ms, int ch, int p)
+{
+    const uint32_t v = ~(1u << (p + 16 * (ch & 1)));
+    SX_TOY_FAR_WORD(ms, ch >> 1, w &= v)
+}
+// the 16-bit channel set of cell p (bit = channel), the cell-major view the slow paths use
+__device__ __forceinline__ uint32_t cell_channels(const DevConfig &cfg, const MoveSets &ms, int p)
+{
+    const int b1 = cfg.R - 1, b2 = 2 * b1, b3 = b2 + cfg.C - 1;
+    uint32_t bits = ((ms.down >> p) & 1u) | (((ms.up >> p) & 1u) << b1) | (((ms.right >> p) & 1u) << b2) |
+                    (((ms.left >> p) & 1u) << b3);
+    const uint32_t far[8] = {ms.f0, ms.f1, ms.f2, ms.f3, ms.f4, ms.f5, ms.f6, ms.f7};
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+        bits |= (((far[i] >> p) & 1u) << (2 * i)) | (((far[i] >> (p + 16)) & 1u) << (2 * i + 1));
+    return bits;
+}
+
+// Valid moves of player index `me` in `me`'s frame (impl:400-517).  One-square moves of all pieces come from four shifts
+// of the occupancy sets; scouts (absent from the stock toy variants, possible in custom ones) walk their rays in a
+// rolled loop.  Returns the number of moves.
 __device__ __forceinline__ int gen_moves(const DevConfig &cfg, const Geometry &geo, const State &s, const Aux &a, int me,
-                                         bool allow_osc, uint32_t mv[16])
+                                         bool allow_osc, MoveSets &ms)
 {
     const int N = cfg.N, R = cfg.R, C = cfg.C;
-#pragma unroll
-    for (int p = 0; p < 16; ++p) mv[p] = 0;
+    clear_sets(ms);
     if (a.over) return 0;  // impl:414
     const Sets t = make_sets(s);
     const int flip = me;
@@ -121,11 +174,10 @@ __device__ __forceinline__ int gen_moves(const DevConfig &cfg, const Geometry &g
     const int b1 = R - 1, b2 = 2 * b1, b3 = b2 + C - 1;
     // impl:492-512: a piece may step onto any neighbouring square that holds neither an own piece nor a lake
     const uint32_t walkers = movers & ~scouts;
-    const uint32_t down = walkers & geo.has_down & ~(block >> C), up = walkers & geo.has_up & ~(block << C);
-    const uint32_t right = walkers & geo.has_right & ~(block >> 1), left = walkers & geo.has_left & ~(block << 1);
-#pragma unroll
-    for (int p = 0; p < 16; ++p)
-        mv[p] = ((down >> p) & 1u) | (((up >> p) & 1u) << b1) | (((right >> p) & 1u) << b2) | (((left >> p) & 1u) << b3);
+    ms.down = walkers & geo.has_down & ~(block >> C);
+    ms.up = walkers & geo.has_up & ~(block << C);
+    ms.right = walkers & geo.has_right & ~(block >> 1);
+    ms.left = walkers & geo.has_left & ~(block << 1);
     if (scouts != 0) {  // impl:426-490: slide until the edge, a lake or a piece; an enemy piece may be taken
         const uint32_t any = to_frame(t.any, flip, N), enemy = to_frame(t.enemy[me], flip, N);
 #pragma unroll 1
@@ -137,10 +189,19 @@ __device__ __forceinline__ int gen_moves(const DevConfig &cfg, const Geometry &g
             for (int k = 1; r - k >= 0; ++k) { const int q = p - k * C; if ((any >> q) & 1u) { n1 += int((enemy >> q) & 1u); break; } ++n1; }
             for (int k = 1; c + k < C; ++k) { const int q = p + k; if ((any >> q) & 1u) { n2 += int((enemy >> q) & 1u); break; } ++n2; }
             for (int k = 1; c - k >= 0; ++k) { const int q = p - k; if ((any >> q) & 1u) { n3 += int((enemy >> q) & 1u); break; } ++n3; }
-            const uint32_t bits = ((1u << n0) - 1u) | (((1u << n1) - 1u) << b1) | (((1u << n2) - 1u) << b2) | (((1u << n3) - 1u) << b3);
-#pragma unroll
-            for (int q = 0; q < 16; ++q)
-                if (q == p) mv[q] = bits;
+            const uint32_t bit = 1u << p;
+            if (n0 > 0) ms.down |= bit;
+            if (n1 > 0) ms.up |= bit;
+            if (n2 > 0) ms.right |= bit;
+            if (n3 > 0) ms.left |= bit;
+#pragma unroll 1
+            for (int k = 2; k <= n0; ++k) far_put(ms, k - 1, p);
+#pragma unroll 1
+            for (int k = 2; k <= n1; ++k) far_put(ms, b1 + k - 1, p);
+#pragma unroll 1
+            for (int k = 2; k <= n2; ++k) far_put(ms, b2 + k - 1, p);
+#pragma unroll 1
+            for (int k = 2; k <= n3; ++k) far_put(ms, b3 + k - 1, p);
         }
     }
     // the one move the two-square rule forbids (impl:439-445, 501-505), in `me`'s frame
@@ -149,17 +210,23 @@ __device__ __forceinline__ int gen_moves(const DevConfig &cfg, const Geometry &g
         const int sc_ = view(a.rto[me], flip, N), ec_ = view(a.rfrom[me], flip, N);
         const int sr = fast_div(sc_, cfg.magic_C), sc = sc_ - sr * C, er = fast_div(ec_, cfg.magic_C), ec = ec_ - er * C;
         if ((sr == er || sc == ec) && sc_ != ec_) {
-            int bit;
-            if (sc == ec) bit = (er > sr ? 0 : b1) + (er > sr ? er - sr : sr - er) - 1;
-            else bit = (ec > sc ? b2 : b3) + (ec > sc ? ec - sc : sc - ec) - 1;
-#pragma unroll
-            for (int q = 0; q < 16; ++q)
-                if (q == sc_) mv[q] &= ~(1u << bit);
+            const int dir = sc == ec ? (er > sr ? 0 : 1) : (ec > sc ? 2 : 3);
+            const int dist = sc == ec ? (er > sr ? er - sr : sr - er) : (ec > sc ? ec - sc : sc - ec);
+            const uint32_t keep = ~(1u << sc_);
+            if (dist == 1) {
+                if (dir == 0) ms.down &= keep;
+                else if (dir == 1) ms.up &= keep;
+                else if (dir == 2) ms.right &= keep;
+                else ms.left &= keep;
+            } else {
+                far_clear(ms, (dir == 0 ? 0 : dir == 1 ? b1 : dir == 2 ? b2 : b3) + dist - 1, sc_);
+            }
         }
     }
-    int total = 0;
-#pragma unroll
-    for (int p = 0; p < 16; ++p) total += __popc(mv[p]);
+    int total = __popc(ms.down) + __popc(ms.up) + __popc(ms.right) + __popc(ms.left);
+    if (ms.any_far != 0)
+        total += __popc(ms.f0) + __popc(ms.f1) + __popc(ms.f2) + __popc(ms.f3) + __popc(ms.f4) + __popc(ms.f5) + __popc(ms.f6) +
+                 __popc(ms.f7);
     return total;
 }
 
@@ -355,24 +422,62 @@ __device__ __forceinline__ void reset_game(const DevConfig &cfg, State &s, Aux &
 }
 
 // t-th move in ascending (cell, channel) order of the mover's frame (sample_move of the warp-level kernel)
-__device__ __forceinline__ int pick_move(const DevConfig &cfg, const uint32_t mv[16], int total, uint32_t rnd)
+__device__ __forceinline__ int pick_move(const DevConfig &cfg, const MoveSets &ms, int total, uint32_t rnd)
 {
     if (total == 0) return cfg.A - 1;
     int t = int(__umulhi(rnd, uint32_t(total)));
-    int action = 0;
-    bool found = false;
+    if (ms.any_far == 0) {
+        // one-square moves only: the cell that holds move t is the last cell with at most t moves in the cells before it
+        auto below = [&](int p) {
+            const uint32_t low = (1u << p) - 1u;
+            return __popc(ms.down & low) + __popc(ms.up & low) + __popc(ms.right & low) + __popc(ms.left & low);
+        };
+        int p = 0;
 #pragma unroll
-    for (int p = 0; p < 16; ++p) {
-        const int cnt = __popc(mv[p]);
-        if (!found && t < cnt) {
-            uint32_t w = mv[p];
+        for (int w = 8; w >= 1; w >>= 1)
+            if (below(p + w) <= t) p += w;
+        int r = t - below(p);
+        // the cell's channels in ascending order: down 0 < up R-1 < right 2(R-1) < left 2(R-1)+C-1
+        const int b1 = cfg.R - 1, b2 = 2 * b1, b3 = b2 + cfg.C - 1;
+        const int d0 = int((ms.down >> p) & 1u), d1 = int((ms.up >> p) & 1u), d2 = int((ms.right >> p) & 1u);
+        int ch = b3;
+        if (r < d0) ch = 0;
+        else if (r < d0 + d1) ch = b1;
+        else if (r < d0 + d1 + d2) ch = b2;
+        return p * cfg.A + ch;
+    }
+    int action = 0;
+#pragma unroll 1
+    for (int p = 0; p < cfg.N; ++p) {  // scouts on the board: walk the cells
+        uint32_t w = cell_channels(cfg, ms, p);
+        const int cnt = __popc(w);
+        if (t < cnt) {
             for (int skip = t; skip > 0; --skip) w &= w - 1;
             action = p * cfg.A + __ffs(w) - 1;
-            found = true;
+            break;
         }
         t -= cnt;
     }
     return action;
+}
+
+// the 0/1 mask row [cell][channel] of a game: a 1 at every move (the row is zero on entry)
+__device__ __forceinline__ void mark_row(const DevConfig &cfg, const MoveSets &ms, uint8_t *row)
+{
+    const int A = cfg.A, b1 = cfg.R - 1, b2 = 2 * b1, b3 = b2 + cfg.C - 1;
+    for (uint32_t w = ms.down; w != 0; w &= w - 1) row[(__ffs(w) - 1) * A] = 1;
+    for (uint32_t w = ms.up; w != 0; w &= w - 1) row[(__ffs(w) - 1) * A + b1] = 1;
+    for (uint32_t w = ms.right; w != 0; w &= w - 1) row[(__ffs(w) - 1) * A + b2] = 1;
+    for (uint32_t w = ms.left; w != 0; w &= w - 1) row[(__ffs(w) - 1) * A + b3] = 1;
+    if (ms.any_far != 0) {
+        const uint32_t far[8] = {ms.f0, ms.f1, ms.f2, ms.f3, ms.f4, ms.f5, ms.f6, ms.f7};
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+            for (uint32_t w = far[i]; w != 0; w &= w - 1) {
+                const int b = __ffs(w) - 1;
+                row[(b & 15) * A + 2 * i + (b >> 4)] = 1;
+            }
+    }
 }
 
 // Observation tiles hold the background image permanently; per game the lanes first put the background back where the
