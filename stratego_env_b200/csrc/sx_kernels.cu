@@ -603,7 +603,7 @@ __global__ void __launch_bounds__(SX_TOY_THREADS, 1) sx_toy_kernel(const __grid_
     constexpr int T = SX_TOY_TILES;
     uint32_t undo_po[T], undo_fo[T];
 #pragma unroll
-    for (int h = 0; h < T; ++h) undo_po[h] = undo_fo[h] = toy::UNDO_NONE;
+    for (int h = 0; h < T; ++h) undo_po[h] = undo_fo[h] = lane < 16 ? 0u : toy::UNDO_NONE;  // cell lanes: "channel 0" four times
     for (int h = 0; h < T; ++h) {
         if (do_po)
             for (int i = lane; i < (po_bytes >> 4); i += 32)
@@ -749,6 +749,8 @@ __global__ void __launch_bounds__(SX_TOY_THREADS, 1) sx_toy_kernel(const __grid_
             if (lane == 0) bulk_commit();
         }
         if (do_po || do_fo) {
+            float *gpo = do_po ? args.out.partial_obs + env0 * cfg.po_floats : nullptr;  // walked, not re-multiplied, per game
+            float *gfo = do_fo ? args.out.full_obs + env0 * cfg.fo_floats : nullptr;
 #pragma unroll 1
             for (int g = 0; g < toy::GAMES; g += T) {
 #pragma unroll
@@ -765,10 +767,12 @@ __global__ void __launch_bounds__(SX_TOY_THREADS, 1) sx_toy_kernel(const __grid_
                     fence_async_smem();
                     __syncwarp();
                     if (lane == 0) {
-                        if (do_po) bulk_store(args.out.partial_obs + (env0 + g + h) * cfg.po_floats, tile, uint32_t(po_bytes), pol);
-                        if (do_fo) bulk_store(args.out.full_obs + (env0 + g + h) * cfg.fo_floats, tile + po_bytes, uint32_t(fo_bytes), pol);
+                        if (do_po) bulk_store(gpo, tile, uint32_t(po_bytes), pol);
+                        if (do_fo) bulk_store(gfo, tile + po_bytes, uint32_t(fo_bytes), pol);
                         bulk_commit();
                     }
+                    if (do_po) gpo += cfg.po_floats;
+                    if (do_fo) gfo += cfg.fo_floats;
                 }
             }
         }

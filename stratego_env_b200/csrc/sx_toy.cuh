@@ -484,20 +484,18 @@ __device__ __forceinline__ void mark_row(const DevConfig &cfg, const MoveSets &m
 // tile's previous game had entries (restore_tile, from a per-lane undo word) and then add the new game's entries
 // (patch_tile, one pass of patch_obs of the warp-level kernel): lanes 0..N-1 their cell's one-hot / lake / still entries,
 // lanes 16..19 the recent-move squares, lanes 20..27 the capture entries.  Undo word: cell lanes = four channel
-// numbers (0xff = none); the others = bit 31 valid | capture type << 16 | float offset.
+// numbers (0 = none or channel 0: both restore to the zero background); the others = bit 31 valid | capture type << 16 |
+// float offset, UNDO_NONE = nothing.
 constexpr uint32_t UNDO_NONE = 0xffffffffu;
 
 __device__ __forceinline__ void restore_tile(const DevConfig &cfg, float *tile, const ObsMap om, int lane, uint32_t undo)
 {
-    if (lane < 16) {
+    if (lane < cfg.N) {  // four unconditional stores: "no entry" is recorded as channel 0, whose background is zero too
         float *cell = tile + lane * om.channels;
         const float zero = cfg.unit_lut[0];
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            const uint32_t ch = (undo >> (8 * k)) & 0xffu;
-            if (ch != 0xffu) cell[ch] = zero;
-        }
-    } else if (undo != UNDO_NONE) {
+        for (int k = 0; k < 4; ++k) cell[(undo >> (8 * k)) & 0xffu] = zero;
+    } else if (lane >= 16 && undo != UNDO_NONE) {
         tile[undo & 0xffffu] = lane < 20 ? cfg.recent_lut[3] : cfg.cap_lut[((undo >> 16) & 15u) * 9];
     }
 }
@@ -526,7 +524,8 @@ __device__ __forceinline__ uint32_t patch_tile(const DevConfig &cfg, const uint8
         if (c1 != 0xff) cell[c1] = one;
         if (c2 != 0xff) cell[c2] = one;
         if (c3 != 0xff) cell[c3] = one;
-        undo = c0 | (c1 << 8) | (c2 << 16) | (c3 << 24);
+        // undo word: the channels written, none = channel 0 (own_true's first plane: background zero, restore_tile)
+        undo = (c0 == 0xff ? 0u : c0) | ((c1 == 0xff ? 0u : c1) << 8) | ((c2 == 0xff ? 0u : c2) << 16) | ((c3 == 0xff ? 0u : c3) << 24);
     } else if (lane >= 16 && lane < 20) {  // lanes 16/17 own from/to, 18/19 enemy from/to
         const int l = lane - 16, who = (l < 2) ? me : (me ^ 1);
         const uint32_t sq = who == 0 ? (info0 & 0xffffu) : (info0 >> 16);
