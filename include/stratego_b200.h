@@ -154,11 +154,12 @@ int sx_config_set_tuning(sx_config *cfg, int32_t warps_per_block, int32_t issue_
  * instead of dealing setups; the turn counter restarts at 0 with the configured max_turns (util:382-383) and the player
  * to move is drawn uniformly (maenv:523).  The table must stay allocated while it is set.  n_states = 0 (or a NULL
  * board pointer) switches back to setups.
- * start_index_d (optional, device, int32): start_index_d[global env id - index_env_base] receives the entry every game
- * was (re)started from -- maenv:524-527 maps the players through the entry's likely winner.  Global env id = env_base +
- * the env's position in the call, as everywhere else. */
+ * start_index_d (optional, device, int32 [index_len]): start_index_d[global env id - index_env_base] receives the entry
+ * every game was (re)started from -- maenv:524-527 maps the players through the entry's likely winner.  Global env id =
+ * env_base + the env's position in the call, as everywhere else; ids outside [index_env_base, index_env_base +
+ * index_len) are not recorded. */
 int sx_config_set_start_states(sx_config *cfg, sx_state table, int64_t n_states, int32_t *start_index_d,
-                               int64_t index_env_base);
+                               int64_t index_env_base, int64_t index_len);
 
 /* Replaces penv.create_initial_state (penv:38 -> impl:213-249) + the setup samplers
  * (util:33-53 random, util:301-319 human).  Re-sets every env b with reset_mask_d[b] != 0 (all when

@@ -53,7 +53,7 @@ SYMBOLS = {
     "sx_config_destroy": (None, [_vp]),
     "sx_config_layout": (C.c_int, [_vp, C.POINTER(SxLayout)]),
     "sx_config_set_tuning": (C.c_int, [_vp, C.c_int32, C.c_int32, C.c_int32]),
-    "sx_config_set_start_states": (C.c_int, [_vp, SxState, _i64, _vp, _i64]),
+    "sx_config_set_start_states": (C.c_int, [_vp, SxState, _i64, _vp, _i64, _i64]),
     "sx_reset": (C.c_int, [_vp, SxState, _i64, _i64, _vp, _vp, _i32, _vp, _u64, _u32, _vp]),
     "sx_import_ref_state": (C.c_int, [_vp, SxState, _i64, _vp, _vp, _vp, _vp]),
     "sx_export_ref_state": (C.c_int, [_vp, SxState, _i64, _vp, _vp, _vp]),

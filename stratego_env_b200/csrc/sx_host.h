@@ -23,7 +23,7 @@ struct sx_config {
     sx_state start_states{nullptr, nullptr, nullptr};  // sx_config_set_start_states: curriculum table (device)
     long long n_start_states = 0;
     int32_t *start_index = nullptr;  // [env id - start_index_base] entry each game was started from (optional)
-    long long start_index_base = 0;
+    long long start_index_base = 0, start_index_len = 0;
     int tune_warps = 0;   // sx_config_set_tuning: resident warps per SM of the warp-level kernel (0 = built-in choice)
     int tune_issue = -1;  // sx_config_set_tuning: where a game's background copy is issued (-1 = built-in choice)
     // launch shapes already worked out, keyed by (device, ops, mode): the occupancy / attribute queries cost tens

@@ -60,7 +60,7 @@ struct KernelArgs {
     const uint16_t *start_cap;
     uint32_t n_start;
     int32_t *start_index;  // [global env id - start_index_base], may be null
-    long long start_index_base;
+    long long start_index_base, start_index_len;
     int exp_nap, exp_stagger;  // experiments builds only: ns to sleep before the copy wait / per warp index at the start
     int warp_bytes;  // shared-memory slice of one game (state + move sets + scratch)
     int tile_bytes;  // the block's background images (0 = this launch renders nothing)
@@ -245,6 +245,13 @@ constexpr uint32_t SX_TUNE_COMMIT_GAP = 0x1000000u;
 #ifndef SX_KG_THREADS
 #define SX_KG_THREADS 512
 #endif
+// where the table entry a game is started from is recorded (sx_config_set_start_states); null = not recorded
+__device__ __forceinline__ int32_t *start_index_slot(const KernelArgs &args, long long env)
+{
+    const long long i = args.env_base + env - args.start_index_base;
+    return (args.start_index != nullptr && i >= 0 && i < args.start_index_len) ? args.start_index + i : nullptr;
+}
+
 template <int K, int MODE, int G, bool CM = false>  // CM: gen_moves hands movers to lanes (dense 10x10 boards)
 __global__ void __launch_bounds__(K > 2 ? SX_MAX_THREADS : G == 1 ? SX_K2_THREADS : SX_KG_THREADS, 1)
 sx_fused_kernel(const __grid_constant__ KernelArgs args)
@@ -397,7 +404,7 @@ sx_fused_kernel(const __grid_constant__ KernelArgs args)
             const uint4 nw = args.n_start != 0
                 ? reset_from_table<GT>(&cfg, warp_base, args.start_board, args.start_aux, args.start_cap, args.n_start,
                                        uint32_t(attempt), args.key, gid, episode, (flags & SX_SAME_SETUP) ? 0u : episode,
-                                       args.start_index ? args.start_index + (args.env_base + env - args.start_index_base) : nullptr)
+                                       start_index_slot(args, env))
                 : reset_game<GT>(&cfg, warp_base, args.setups, args.n_setups,
                                  args.setup_idx ? args.setup_idx + env * 2 : nullptr, draw, args.key, gid, episode, rng_episode);
             const uint32_t w[4] = {nw.x, nw.y, nw.z, nw.w};
@@ -1082,7 +1089,7 @@ extern "C" int sx_config_create(const sx_config_desc *desc, sx_config **out)
 extern "C" void sx_config_destroy(sx_config *cfg) { delete cfg; }
 
 extern "C" int sx_config_set_start_states(sx_config *cfg, sx_state table, int64_t n_states, int32_t *start_index_d,
-                                          int64_t index_env_base)
+                                          int64_t index_env_base, int64_t index_len)
 {
     if (!cfg) return fail("sx_config_set_start_states: null config");
     if (n_states < 0 || n_states > 0x7fffffffLL) return fail("sx_config_set_start_states: n_states out of range");
@@ -1091,8 +1098,9 @@ extern "C" int sx_config_set_start_states(sx_config *cfg, sx_state table, int64_
     const bool on = n_states > 0 && table.board != nullptr;
     cfg->start_states = on ? table : sx_state{nullptr, nullptr, nullptr};
     cfg->n_start_states = on ? n_states : 0;
-    cfg->start_index = on ? start_index_d : nullptr;
+    cfg->start_index = (on && index_len > 0) ? start_index_d : nullptr;
     cfg->start_index_base = index_env_base;
+    cfg->start_index_len = cfg->start_index ? index_len : 0;
     return 0;
 }
 
@@ -1339,7 +1347,7 @@ static int launch_fused(const sx_config *cfg, KernelArgs &args, cudaStream_t str
     if (args.num_envs <= 0) return 0;
     args.start_board = cfg->start_states.board; args.start_aux = cfg->start_states.aux; args.start_cap = cfg->start_states.captured;
     args.n_start = cfg->start_states.board ? uint32_t(cfg->n_start_states) : 0u;
-    args.start_index = cfg->start_index; args.start_index_base = cfg->start_index_base;
+    args.start_index = cfg->start_index; args.start_index_base = cfg->start_index_base; args.start_index_len = cfg->start_index_len;
     LaunchPlan plan;
     const int mode = mode_for(cfg, args);
     if (toy_eligible(cfg, args, mode)) {

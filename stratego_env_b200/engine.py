@@ -123,7 +123,7 @@ class StrategoEngine:
         player to move, instead of dealing setups.  ``None`` switches back.  Returns an int32 [num_envs] tensor that always
         holds the entry each env's current game came from (None when num_envs is 0)."""
         if dense is None:
-            _lib.check(self.lib.sx_config_set_start_states(self._cfg, _lib.SxState(), 0, None, 0), "sx_config_set_start_states")
+            _lib.check(self.lib.sx_config_set_start_states(self._cfg, _lib.SxState(), 0, None, 0, 0), "sx_config_set_start_states")
             self._start_table = self._start_index = None
             return None
         dense = dense.to(self.device, dtype=torch.int64).clone()
@@ -132,7 +132,8 @@ class StrategoEngine:
         table = self.import_ref_state(dense)
         index = torch.zeros(num_envs, dtype=torch.int32, device=self.device) if num_envs else None
         _lib.check(self.lib.sx_config_set_start_states(self._cfg, table.as_struct(), table.num_envs,
-                                                       index.data_ptr() if index is not None else None, int(env_base)),
+                                                       index.data_ptr() if index is not None else None, int(env_base),
+                                                       int(num_envs)),
                    "sx_config_set_start_states")
         self._start_table, self._start_index = table, index  # the library keeps raw pointers: keep the tensors alive
         return index

@@ -57,12 +57,12 @@ def test_config_validation_without_gpu():
     assert lib.sx_config_set_tuning(handle, 8, 3, 0) != 0
     assert lib.sx_config_set_tuning(None, 8, 1, 0) != 0
     # curriculum table: host state only; a table needs all three tensors, n_states = 0 switches back to setups
-    assert lib.sx_config_set_start_states(handle, _lib.SxState(), 0, None, 0) == 0
+    assert lib.sx_config_set_start_states(handle, _lib.SxState(), 0, None, 0, 0) == 0
     partial = _lib.SxState()
     partial.board = 4096
-    assert lib.sx_config_set_start_states(handle, partial, 3, None, 0) != 0 and b"board, aux and captured" in lib.sx_last_error()
-    assert lib.sx_config_set_start_states(handle, partial, -1, None, 0) != 0
-    assert lib.sx_config_set_start_states(None, _lib.SxState(), 0, None, 0) != 0
+    assert lib.sx_config_set_start_states(handle, partial, 3, None, 0, 0) != 0 and b"board, aux and captured" in lib.sx_last_error()
+    assert lib.sx_config_set_start_states(handle, partial, -1, None, 0, 0) != 0
+    assert lib.sx_config_set_start_states(None, _lib.SxState(), 0, None, 0, 0) != 0
     lib.sx_config_destroy(handle)
     desc.rows = 2
     assert lib.sx_config_create(ctypes.byref(desc), ctypes.byref(handle)) != 0
