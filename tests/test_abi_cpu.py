@@ -29,6 +29,35 @@ def test_library_exports_every_declared_symbol():
     assert lib.sx_version() >= 1
 
 
+def test_binding_signatures_match_the_header():
+    """every prototype of include/stratego_b200.h has as many parameters as the ctypes binding passes, and the struct
+    bindings have the header's field counts (a drifted signature corrupts the stack silently)"""
+    import re
+    from stratego_env_b200 import _lib
+    text = re.sub(r"/\*.*?\*/", "", open(os.path.join(ROOT, "include", "stratego_b200.h")).read(), flags=re.S)
+    protos = re.findall(r"^(?:const\s+)?[A-Za-z_][\w\s\*]*?\b(sx_\w+)\s*\(([^;{]*?)\)\s*;", text, flags=re.M)
+    seen = {}
+    for name, params in protos:
+        params = params.strip()
+        seen[name] = 0 if params in ("", "void") else params.count(",") + 1
+    for name, (restype, argtypes) in _lib.SYMBOLS.items():
+        assert name in seen, name
+        assert seen[name] == len(argtypes), (name, seen[name], len(argtypes))
+
+    def fields(struct_name):
+        body = re.search(r"typedef struct\s*\{([^{}]*)\}\s*%s\s*;" % struct_name, text).group(1)
+        n = 0
+        for decl in body.split(";"):
+            decl = re.sub(r"\[[^\]]*\]", "", decl).strip()
+            if decl:
+                n += decl.count(",") + 1
+        return n
+    assert fields("sx_outputs") == len(_lib.SxOutputs._fields_)
+    assert fields("sx_state") == len(_lib.SxState._fields_)
+    assert fields("sx_layout") == len(_lib.SxLayout._fields_)
+    assert fields("sx_config_desc") == len(_lib.SxConfigDesc._fields_)
+
+
 def test_config_validation_without_gpu():
     """sx_config_create is pure host code: geometry, strides and error behaviour (penv:28-30)"""
     from stratego_env_b200 import _lib
